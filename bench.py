@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""
+bench.py -- cell-updates/s of the fire-spread stepper (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one `RothermelFireManager.update` (simfire/game/managers/fire.py:616-719) over
+every env of the batch.  Default workload = the configuration the metric is quoted on
+(north_star target): 2048 x 2048 synthetic flat terrain x 1024 independent envs per GPU
+sharing one terrain (weak scaling: each rank owns 1024 envs, no collective on the data
+path).  One JSON line is printed by rank 0.
+
+value     device-timed (CUDA events on the engine's stream), state resident in HBM
+e2e       same metric through the public batched API with HOST buffers: per step the
+          mitigation points go host -> device from pinned memory and every env's fire_map
+          comes back device -> host into pinned memory
+roofline  dominant kernel (k_sweep) against the measured HBM peak
+cpu_baseline / --impl reference
+          the NumPy oracle port of the reference algorithm on the host cores (the reference
+          is pure Python and does not travel to the GPU box)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell_updates_per_s"
+UNIT = "cell-updates/s"
+
+# bytes per cell-update of a kernel that streams every plane each step
+SURVEY_BYTES_PER_ENV_STATIC = 52.0
+SURVEY_BYTES_SHARED = lambda E: 20.0 + 32.0 / E  # noqa: E731
+
+
+def workload_spec(name: str):
+    """name -> (H, W, envs per GPU, shared_static, flat, description)"""
+    specs = {
+        # north_star target: "2048^2 x 1024-env batch at 1 GPU", synthetic flat terrain
+        "target": (2048, 2048, 1024, True, True),
+        # BASELINE configs[2]/[3]: 512^2 x 1024 envs per GPU, per-env terrain replaced by shared
+        "cfg3": (512, 512, 1024, True, False),
+        # BASELINE configs[1]
+        "cfg2": (1024, 1024, 1, False, False),
+        "small": (256, 256, 64, True, True),
+    }
+    return specs[name]
+
+
+def make_workload(name: str):
+    from simfire_b200.workloads import synthetic_operational
+
+    H, W, E, shared, flat = workload_spec(name)
+    wl = synthetic_operational(H, W, seed=0, flat=flat)
+    return wl, E, shared
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {
+        0x0000000000000004: "sw_power_cap",
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000080: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _run(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for bit, nm in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nvml is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm; test/bench infrastructure only)
+# --------------------------------------------------------------------------------------
+def _oracle_sim(wl, crop: int, start):
+    from oracle.dense_numpy import DenseFire, DenseParams
+
+    planes = {k: np.ascontiguousarray(np.broadcast_to(v, (wl.H, wl.W))[:crop, :crop]) for k, v in wl.planes.items()}
+    p = DenseParams(pixel_scale=wl.pixel_scale, update_rate=wl.update_rate, max_fire_duration=wl.max_fire_duration,
+                    max_time=wl.max_time, attenuate_line_ros=wl.attenuate_line_ros,
+                    diagonal_spread=wl.diagonal_spread, M_f=wl.M_f)  # fmt: skip
+    return DenseFire(planes, p, start)
+
+
+def _crop_start(wl, crop: int, seed: int):
+    rng = np.random.default_rng(seed)
+    w0 = np.broadcast_to(wl.planes["w_0"], (wl.H, wl.W))
+    while True:
+        x, y = int(rng.integers(crop // 4, 3 * crop // 4)), int(rng.integers(crop // 4, 3 * crop // 4))
+        if w0[y, x] > 0:
+            return (x, y)
+
+
+def cpu_baseline_leg(wl, budget_s: float = 12.0):
+    """One host core, one env of the full grid, as many steps as fit the budget."""
+    sim = _oracle_sim(wl, min(wl.H, wl.W), _crop_start(wl, min(wl.H, wl.W), 1))
+    sim.step()  # warm-up (first call pays NumPy dispatch caches)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        sim.step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 400:
+            break
+    side = min(wl.H, wl.W)
+    return {"value": side * side * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle/dense_numpy.py, 1 env of {side}x{side} of the bench terrain, {n} steps in {dt:.1f} s"}  # fmt: skip
+
+
+def _ref_worker(args):
+    name, crop, seed, n_steps, barrier_dir = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    wl, _, _ = make_workload(name)
+    sim = _oracle_sim(wl, crop, _crop_start(wl, crop, seed))
+    t = []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        sim.step()
+        t.append(time.perf_counter() - t0)
+    return t
+
+
+def reference_arm(args):
+    """`--impl reference`: the oracle port on all host cores, one env per worker process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    wl, E, shared = make_workload(args.workload)
+    # bounded sample: crop the terrain so warmup + steps finish in ~2 minutes
+    probe = _oracle_sim(wl, 256, _crop_start(wl, 256, 0))
+    probe.step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        probe.step()
+    per_cell = (time.perf_counter() - t0) / 3 / (256 * 256)
+    total_steps = args.steps + args.warmup
+    crop = min(wl.H, wl.W)
+    while crop > 128 and per_cell * crop * crop * total_steps * 1.5 > 100.0:
+        crop //= 2
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        t_start = time.perf_counter()
+        res = pool.map(_ref_worker, [(args.workload, crop, 100 + i, total_steps, None) for i in range(workers)])
+        wall_all = time.perf_counter() - t_start
+    # a "step" = every worker advances its env once; its time = the slowest worker's
+    per_step = np.max(np.array(res), axis=0)
+    timed = per_step[args.warmup :]
+    secs = float(timed.sum())
+    value = workers * crop * crop * args.steps / secs
+    sample = (f"oracle/dense_numpy.py (NumPy port of fire.py:616-719), {workers} processes x 1 env of {crop}x{crop} "
+              f"cropped from the {wl.H}x{wl.W} bench terrain; pool wall {wall_all:.1f} s")  # fmt: skip
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32/f64", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": [wl.H, wl.W], "sample_grid": [crop, crop], "envs": workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def load_traffic_note(workload: str):
+    """Per-launch DRAM bytes of k_sweep from the committed ncu capture, if it matches."""
+    path = os.path.join(ROOT, "profiles", "ncu_sweep_summary.json")
+    try:
+        with open(path) as f:
+            j = json.load(f)
+        if j.get("workload") == workload:
+            return j.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+def gpu_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the stepper has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from simfire_b200 import FireEngine
+
+    wl, E, shared = make_workload(args.workload)
+    if args.envs:
+        E = args.envs
+    H, W = wl.H, wl.W
+    eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
+                     **wl.engine_kwargs())  # fmt: skip
+    eng.set_static(wl.planes)
+    starts = wl.burnable_starts(E, seed=1000 + rank)
+    eng.reset(starts)
+    eng.step(args.burn_in)  # untimed: let the fronts develop so the timed steps see real fires
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.step(args.warmup)
+    l0 = eng.launch_counts()[1]
+    with ClockSampler(local) as clocks:
+        barrier()
+        ms = eng.step_timed(args.steps)
+        barrier()
+    launches = eng.launch_counts()[1] - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    cells_per_step = H * W * E * world
+    value = cells_per_step * args.steps / (ms_max * 1e-3)
+
+    # ---- dominant-kernel timing for the roofline (separate, per-step synchronised pass)
+    eng.set_kernel_timing(True)
+    eng.step(args.roofline_steps)
+    sweep_ms, eval_ms, n_t = eng.kernel_ms()
+    eng.set_kernel_timing(False)
+    q_entries, q_cap, q_ovf = eng.queue_stats()
+    sweep_s = sweep_ms / n_t * 1e-3
+    eval_s = eval_ms / n_t * 1e-3
+
+    # ---- end to end through the batched API with host buffers
+    pinned_maps = torch.empty((E, H, W), dtype=torch.int8, pin_memory=True)
+    maps_np = pinned_maps.numpy()
+    pinned_pts = torch.empty((E, 4), dtype=torch.int32, pin_memory=True)
+    pts_np = pinned_pts.numpy()
+    rng = np.random.default_rng(5 + rank)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        pts_np[:, 0] = np.arange(E)
+        pts_np[:, 1] = rng.integers(0, W, E)
+        pts_np[:, 2] = rng.integers(0, H, E)
+        pts_np[:, 3] = 3  # BurnStatus.FIRELINE
+        eng.apply_points(pts_np)          # host -> device
+        eng.step(1, sync=False)
+        eng.fire_map(0, E, out=maps_np)   # device -> host (synchronises)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = cells_per_step * e2e_steps / float(t.item())
+
+    # ---- sanity: the timed steps really advanced fires
+    st, el, nsteps = eng.status()
+    burned = int((maps_np[: min(E, 8)] == 2).sum())
+    running = int(st.sum())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    peak_src = "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_src = "measured"
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+
+    # algorithmic bytes per launch of k_sweep in THIS design (DESIGN.md "Kernels"): every cell's
+    # packed state is read once (1 B/cell-update) plus one halo row pair per chunk; work items
+    # are 8 B each.  The survey's figure (a kernel that streams all planes) is kept beside it.
+    cells_rank = H * W * E
+    sweep_bytes = cells_rank * 1.0 + q_entries * 8.0
+    achieved = sweep_bytes / sweep_s / 1e9
+    survey_b = SURVEY_BYTES_SHARED(E) if shared else SURVEY_BYTES_PER_ENV_STATIC
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32/f64", "data": "synthetic",
+        "config": {
+            "workload": args.workload, "grid": [H, W], "envs_per_gpu": E, "envs_total": E * world,
+            "static_planes": "shared" if shared else "per-env", "terrain": wl.description,
+            "burn_in_steps": args.burn_in, "l2": "state plane per GPU (%.0f MB) exceeds the 126 MB L2" % (cells_rank / 1e6),
+            "parallelism": f"env-sharded x{world}, no collective",
+        },
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes) * world,
+                "d2h_bytes_per_step": int(maps_np.nbytes) * world, "steps": e2e_steps,
+                "api": "FireEngine.apply_points + step + fire_map (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": {
+            "bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+            "traffic": load_traffic_note(args.workload),
+            "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,
+            "ms_per_launch": sweep_s * 1e3, "k_eval_ms_per_launch": eval_s * 1e3,
+            "sweep_share_of_step": sweep_s / (sweep_s + eval_s),
+            "work_items_per_step": q_entries, "queue_overflowed": q_ovf,
+            "survey_model": {"bytes_per_cell_update": survey_b,
+                             "achieved": cells_rank * survey_b / (sweep_s + eval_s) / 1e9,
+                             "frac": cells_rank * survey_b / (sweep_s + eval_s) / 1e9 / peak_gbs,
+                             "note": "SURVEY.md 8d counts a kernel that streams every plane each step; this design "
+                                     "sweeps 1 B/cell and gathers the rest only at the fire front"},
+        },
+        "sanity": {"envs_running": running, "burned_cells_first_envs": burned, "steps_done_env0": int(nsteps[0])},
+    }  # fmt: skip
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_budget)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="target", choices=["target", "cfg3", "cfg2", "small"])
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--burn-in", type=int, default=60)
+    ap.add_argument("--rows-per-chunk", type=int, default=0)
+    ap.add_argument("--roofline-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,210 @@
+/*
+ * simfire_b200.h -- C ABI of the B200 fire-spread stepper (libsimfire_b200.so).
+ *
+ * The reference (mitrefireline/simfire, pure Python) has no FFI: the seam this library
+ * replaces is the manager object that FireSimulation constructs and steps,
+ *     simfire/sim/simulation.py:273-291   _create_fire()  -> RothermelFireManager(...)
+ *     simfire/sim/simulation.py:533-535   run(): fire_map, status = fire_manager.update(fire_map)
+ *     simfire/game/managers/fire.py:293   RothermelFireManager.__init__
+ *     simfire/game/managers/fire.py:616   RothermelFireManager.update
+ * Every entry point below names the reference interface it stands in for.  All pointers
+ * are plain host pointers unless a comment says "device"; buffers are borrowed for the
+ * duration of the call only.  No CUDA, C++ or torch types cross this boundary.
+ *
+ * One handle = one CUDA device = E independent simulations ("envs") of one H x W grid,
+ * or (slab mode, sfb_params.slab_*) one horizontal slab of a larger grid whose other
+ * slabs live in other handles / processes / GPUs.
+ *
+ * Error convention: every function returns 0 on success or a negative sfb_error; the
+ * message of the last failure on the calling thread is sfb_last_error().  Nothing throws.
+ * Threading: calls on one handle must be serialised by the caller (the reference is
+ * single-threaded); different handles are independent.
+ */
+#ifndef SIMFIRE_B200_H
+#define SIMFIRE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+typedef struct sfb_sim sfb_sim; /* opaque handle */
+
+enum sfb_error {
+    SFB_OK = 0,
+    SFB_ERR_INVALID = -1, /* bad argument */
+    SFB_ERR_CUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+    SFB_ERR_NOMEM = -3,   /* device or host allocation failed */
+    SFB_ERR_STATE = -4    /* call not valid in the handle's current state */
+};
+
+/* BurnStatus values as they appear in fire_map (simfire/enums.py:52-69). */
+enum sfb_burn_status {
+    SFB_UNBURNED = 0,
+    SFB_BURNING = 1,
+    SFB_BURNED = 2,
+    SFB_FIRELINE = 3,
+    SFB_SCRATCHLINE = 4,
+    SFB_WETLINE = 5
+};
+
+/* GameStatus values returned by update() (simfire/enums.py:106-115). */
+enum sfb_game_status { SFB_QUIT = 0, SFB_RUNNING = 1 };
+
+/* sfb_params.flags */
+enum sfb_flags {
+    SFB_DIAGONAL_SPREAD = 1,   /* fire.py:211-221 (8 neighbours) vs :223-228 (4)            */
+    SFB_ATTENUATE_LINE_ROS = 2,/* fire.py:271-278 vs :280-282                                */
+    SFB_SHARED_STATIC = 4,     /* all envs read one set of static planes (one terrain)       */
+    SFB_KEEP_ROS = 8,          /* materialise the dense rate_of_spread plane (fire.py:704-708);
+                                  costs a dense 8 B/cell pass per step -- parity tests only  */
+    SFB_HAS_MAX_TIME = 16,     /* max_time is not None (fire.py:641)                         */
+    SFB_WIDE_CELLS = 32        /* use the 16-bit cell layout even when max_fire_duration <= 30
+                                  (it is selected automatically above that); tests only      */
+};
+
+/* The eight static per-cell inputs of the Rothermel evaluation, in the order of the
+ * reference's parameter list (fire.py:481-497, rothermel.py:4-22).  Values are float32:
+ * the reference casts them at fire.py:537 / :546 before any arithmetic. */
+enum sfb_static_plane {
+    SFB_W_0 = 0,
+    SFB_DELTA = 1,
+    SFB_M_X = 2,
+    SFB_SIGMA = 3,
+    SFB_U = 4,
+    SFB_U_DIR = 5,
+    SFB_SLOPE_MAG = 6,
+    SFB_SLOPE_DIR = 7,
+    SFB_N_STATIC = 8
+};
+
+/* Planes readable with sfb_get_plane (parity tests, RothermelFireManager attributes). */
+enum sfb_state_plane {
+    SFB_PLANE_BURN = 0, /* float64 burn_amounts (fire.py:370, :710)                     */
+    SFB_PLANE_ROS = 1,  /* float64 rate_of_spread of the last step (needs SFB_KEEP_ROS) */
+    SFB_PLANE_AGE = 2,  /* int32: -1 no sprite, else the sprite's duration (fire.py:633) */
+    SFB_PLANE_STATUS = 3/* int8 BurnStatus -- same as sfb_get_fire_map                  */
+};
+
+/* Constructor arguments: RothermelFireManager.__init__ (fire.py:293-307) plus the
+ * FuelParticle constants (simfire/world/parameters.py:8-27) and Environment.M_f (:53). */
+typedef struct sfb_params {
+    int32_t abi_version;       /* SFB_ABI_VERSION */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t H, W;              /* screen_size = (H, W); arrays are indexed [y][x] */
+    int32_t E;                 /* number of independent simulations in this handle */
+    int32_t max_fire_duration; /* fire.py:116-161; 1..8189 */
+    int32_t flags;             /* sfb_flags */
+    int32_t rows_per_chunk;    /* 0 = auto; tuning knob of the sweep kernel */
+    double pixel_scale;        /* ft per pixel, ignition threshold (fire.py:568) */
+    double update_rate;        /* minutes per step (fire.py:696, :717) */
+    double max_time;           /* minutes; used when SFB_HAS_MAX_TIME */
+    float h, S_T, S_e, p_p;    /* FuelParticle */
+    float M_f;                 /* Environment.M_f */
+    int32_t reserved0;
+    int64_t queue_capacity;    /* 0 = auto; work-queue entries (8 B each) */
+    /* Slab mode (single huge grid split in rows across handles): this handle holds rows
+     * [slab_y0, slab_y0 + H) of a grid with slab_total_H rows.  0/0 = whole grid. */
+    int32_t slab_y0, slab_total_H;
+} sfb_params;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+
+/* RothermelFireManager.__init__ (fire.py:293-380).  Allocates all device state.  Envs
+ * start QUIT with an empty map until sfb_reset() places the initial fire. */
+int sfb_create(const sfb_params* params, sfb_sim** out);
+void sfb_destroy(sfb_sim* sim);
+const char* sfb_last_error(void);
+int sfb_abi_version(void);
+
+/* ---- static inputs --------------------------------------------------------------- */
+
+/* terrain.fuels / U / U_dir / slope planes (fire.py:367-378, :436-449).  `host` is a
+ * float32 [H][W] array for one plane of env `env` (env = -1: every env, or the single
+ * shared set under SFB_SHARED_STATIC). */
+int sfb_set_static(sfb_sim* sim, int32_t env, int32_t plane, const float* host);
+/* All eight planes at once: float32 [8][H][W] in sfb_static_plane order. */
+int sfb_set_static_all(sfb_sim* sim, int32_t env, const float* host);
+
+/* ---- between-step mutations ------------------------------------------------------ */
+
+/* FireSimulation.reset() -> _create_fire_map + _create_fire (simulation.py:202-214,
+ * :273-291, :555-566): map all UNBURNED, burn 0, one BURNING sprite at (x, y), elapsed 0,
+ * status RUNNING.  `envs` lists n env indices (NULL = envs 0..n-1); xy = n pairs (x, y).
+ * In slab mode y is a global row; slabs that do not contain it just clear. */
+int sfb_reset(sfb_sim* sim, const int32_t* envs, int32_t n, const int32_t* xy);
+
+/* ControlLineManager.update (mitigation.py:60-80) batched: points are (env, x, y, kind)
+ * int32 quadruples, kind = BurnStatus value; fire_map[y, x] = kind unconditionally. */
+int sfb_apply_points(sfb_sim* sim, const int32_t* points, int64_t n);
+
+/* FireSimulation.load_mitigation (simulation.py:425-447) / the fire_map argument of
+ * update(): replace the BurnStatus of every cell of envs [env0, env0+n) from int8
+ * [n][H][W]; sprites (burning durations) are kept, as in the reference where the sprite
+ * list is independent of fire_map (fire.py:101-103). */
+int sfb_set_fire_map(sfb_sim* sim, int32_t env0, int32_t n, const int8_t* maps);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+
+/* n_steps x RothermelFireManager.update (fire.py:616-719) on every RUNNING env.  Work is
+ * enqueued on the handle's stream; returns after enqueueing unless sync != 0. */
+int sfb_step(sfb_sim* sim, int32_t n_steps, int32_t sync);
+
+/* Same, bracketed by CUDA events on the handle's stream; *ms = device time of the n steps. */
+int sfb_step_timed(sfb_sim* sim, int32_t n_steps, float* ms);
+
+/* Drop-in for `fire_map, status = manager.update(fire_map)` (simulation.py:535) with
+ * HOST buffers: uploads int8 maps [n][H][W] of envs [env0, env0+n) (the caller may have
+ * edited them, mitigation.py:77), runs one step, downloads the maps in place and writes
+ * GameStatus per env to status[n] (may be NULL). */
+int sfb_update(sfb_sim* sim, int32_t env0, int32_t n, int8_t* maps_inout, int32_t* status);
+
+int sfb_synchronize(sfb_sim* sim);
+
+/* ---- results --------------------------------------------------------------------- */
+
+/* fire_map of envs [env0, env0+n) as int8 BurnStatus [n][H][W]. */
+int sfb_get_fire_map(sfb_sim* sim, int32_t env0, int32_t n, int8_t* out);
+/* One [H][W] plane of one env; element type per sfb_state_plane. */
+int sfb_get_plane(sfb_sim* sim, int32_t env, int32_t plane, void* out);
+/* Per-env GameStatus (int32), elapsed_time (float64, fire.py:717) and number of update()
+ * calls made (int32); any pointer may be NULL. */
+int sfb_get_status(sfb_sim* sim, int32_t* status, double* elapsed, int32_t* steps);
+
+/* Zero-copy observation: after this call *dev points at DEVICE memory holding int8
+ * BurnStatus [E][H][W], refreshed from the packed state on the handle's stream (the call
+ * synchronises the stream before returning). */
+int sfb_fire_map_device(sfb_sim* sim, void** dev);
+
+/* ---- introspection (bench / profiling) -------------------------------------------- */
+
+/* cudaStream_t of the handle, as void*. */
+int sfb_get_stream(sfb_sim* sim, void** stream);
+/* Kernel launches issued by this handle so far (all kernels / hot-path kernels only). */
+int sfb_get_launch_counts(sfb_sim* sim, int64_t* all_kernels, int64_t* step_kernels);
+/* Per-kernel device time: while enabled every step records events around the sweep and
+ * the evaluate kernel.  sfb_get_kernel_ms returns the accumulated milliseconds and launch
+ * counts since enabling and resets them. */
+int sfb_set_kernel_timing(sfb_sim* sim, int32_t enabled);
+int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* eval_ms, int64_t* n_steps);
+/* Work-queue statistics of the last completed step: entries pushed, capacity, and
+ * whether the step overflowed the queue and ran the dense fallback. */
+int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32_t* overflowed);
+/* Bytes of device memory held by the handle. */
+int sfb_device_bytes(sfb_sim* sim, int64_t* bytes);
+
+/* Rate of spread for n (direction, cell) pairs evaluated ON THE DEVICE with exactly the
+ * code the step kernel uses -- the drop-in for compute_rate_of_spread
+ * (simfire/world/rothermel.py:4-136).  dir[i] in 0..7 indexes the neighbour order of
+ * fire.py:211-221; rec is float32 [n][8] in sfb_static_plane order; particle = h, S_T,
+ * S_e, p_p, M_f; out is float64 [n] (ft/min, not yet scaled by update_rate). */
+int sfb_rate_of_spread(int32_t device, const int8_t* dir, const float* rec, const float* particle,
+                       int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMFIRE_B200_H */

@@ -1,0 +1,57 @@
+"""Build libsimfire_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(PKG, "csrc", "sfb.cu")
+DEPS = [
+    SRC,
+    os.path.join(PKG, "csrc", "sfb_kernels.cuh"),
+    os.path.join(PKG, "csrc", "sfb_rothermel.cuh"),
+    os.path.join(os.path.dirname(PKG), "include", "simfire_b200.h"),
+]
+LIB = os.path.join(PKG, "libsimfire_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    # NumPy never contracts a*b+c; the Rothermel arithmetic must round after every operation
+    "--fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]  # fmt: skip
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/sfb.cu -> simfire_b200/libsimfire_b200.so; returns the path."""
+    if not force and not is_stale():
+        return LIB
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

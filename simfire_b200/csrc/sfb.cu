@@ -1,0 +1,759 @@
+// libsimfire_b200.so -- host side of the C ABI declared in include/simfire_b200.h.
+// Plain CUDA runtime; no torch, no CPU fallback: every entry point that computes launches
+// kernels on the handle's device and fails with SFB_ERR_CUDA if it cannot.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/simfire_b200.h"
+#include "sfb_kernels.cuh"
+
+using namespace sfb;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(_e == cudaErrorMemoryAllocation ? SFB_ERR_NOMEM : SFB_ERR_CUDA,           \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct sfb_sim {
+    sfb_params prm;
+    DevParams d;
+    int cell_bytes;   // 1 or 2
+    int parity;       // which half of meta / qcount the NEXT step reads
+    int n_sm;
+    cudaStream_t stream;
+    cudaEvent_t ev[3];
+    // scratch
+    void* stage;          // device staging for host <-> device plane traffic
+    size_t stage_bytes;
+    void* obs;            // int8 [E][H][W] observation buffer (sfb_fire_map_device)
+    int32_t* small;       // device scratch for env lists / points
+    size_t small_bytes;
+    // accounting
+    int64_t launches_all, launches_step;
+    int64_t dev_bytes;
+    int timing;
+    double sweep_ms, eval_ms;
+    int64_t timed_steps;
+    int64_t last_entries;
+    int last_overflow;
+};
+
+static int use(sfb_sim* s) {
+    CU(cudaSetDevice(s->prm.device));
+    return 0;
+}
+
+template <typename T>
+static int dmalloc(sfb_sim* s, T** p, size_t bytes) {
+    CU(cudaMalloc((void**)p, bytes));
+    s->dev_bytes += (int64_t)bytes;
+    return 0;
+}
+
+static int ensure_stage(sfb_sim* s, size_t bytes) {
+    if (s->stage_bytes >= bytes) return 0;
+    if (s->stage) {
+        CU(cudaFree(s->stage));
+        s->dev_bytes -= (int64_t)s->stage_bytes;
+        s->stage = nullptr;
+        s->stage_bytes = 0;
+    }
+    int rc = dmalloc(s, &s->stage, bytes);
+    if (rc) return rc;
+    s->stage_bytes = bytes;
+    return 0;
+}
+
+static int ensure_small(sfb_sim* s, size_t bytes) {
+    if (s->small_bytes >= bytes) return 0;
+    if (s->small) {
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaFree(s->small));
+        s->dev_bytes -= (int64_t)s->small_bytes;
+        s->small = nullptr;
+        s->small_bytes = 0;
+    }
+    bytes = std::max(bytes, (size_t)1 << 16);
+    int rc = dmalloc(s, &s->small, bytes);
+    if (rc) return rc;
+    s->small_bytes = bytes;
+    return 0;
+}
+
+static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------
+// setup / conversion kernels (not on the per-step path)
+// ---------------------------------------------------------------------------------------
+template <typename CellT>
+__global__ void k_clear_envs(DevParams p, const int32_t* envs, int n, int clear_burn) {
+    const long long total = (long long)n * p.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / p.plane);
+        const long long cell = i - (long long)k * p.plane;
+        const int env = envs ? envs[k] : k;
+        const int x = (int)(cell % p.pitch);
+        const long long idx = (long long)env * p.plane + cell;
+        reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(x < p.W ? ST_UNBURNED : ST_BURNED);
+        if (clear_burn) {
+            p.burn[idx] = 0.0;
+            if (p.ros) p.ros[idx] = 0.0;
+        }
+    }
+}
+
+// FireSimulation._create_fire_map + FireManager.__init__ (simulation.py:561-566, fire.py:101-103)
+template <typename CellT>
+__global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const int32_t* xy, int n, int y_off) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int env = envs ? envs[k] : k;
+    const int x = xy[2 * k], y = xy[2 * k + 1] - y_off;
+    if (y >= 0 && y < p.H)
+        reinterpret_cast<CellT*>(p.state)[(long long)env * p.plane + (long long)y * p.pitch + x] =
+            (CellT)(ST_BURNING | (1 << 3));  // sprite created before update() call 1: ign = 0
+    EnvMeta m;
+    m.t = 1;
+    m.running = 1;
+    m.elapsed = 0.0;
+    m.any_live = m.any_cand = m.pad = 0;
+    m.time_quit = p.has_max_time && (p.dt > p.max_time || 0.0 > p.max_time);
+    p.meta[(long long)par * p.E + env] = m;
+}
+
+// ControlLineManager.update (mitigation.py:77): fire_map[y, x] = kind, sprite untouched
+template <typename CellT>
+__global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int kind, int y_off) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int env = pts[4 * i], x = pts[4 * i + 1], y = pts[4 * i + 2] - y_off, k = pts[4 * i + 3];
+    if (k != kind || y < 0 || y >= p.H) return;
+    CellT* c = reinterpret_cast<CellT*>(p.state) + (long long)env * p.plane + (long long)y * p.pitch + x;
+    *c = (CellT)((*c & ~7) | to_internal(k));
+}
+
+template <typename CellT>
+__global__ void k_set_map(DevParams p, int env0, int n, const int8_t* maps) {
+    const long long hw = (long long)p.H * p.W, total = (long long)n * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / hw);
+        const long long r = i - (long long)k * hw;
+        const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
+        CellT* c = reinterpret_cast<CellT*>(p.state) + (long long)(env0 + k) * p.plane + (long long)y * p.pitch + x;
+        *c = (CellT)((*c & ~7) | to_internal(maps[i] & 7));
+    }
+}
+
+template <typename CellT>
+__global__ void k_get_map(DevParams p, int env0, int n, int8_t* maps) {
+    const long long hw = (long long)p.H * p.W, total = (long long)n * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / hw);
+        const long long r = i - (long long)k * hw;
+        const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
+        const CellT c = reinterpret_cast<const CellT*>(p.state)[(long long)(env0 + k) * p.plane + (long long)y * p.pitch + x];
+        maps[i] = (int8_t)to_burn_status(c & 7);
+    }
+}
+
+template <typename CellT>
+__global__ void k_get_plane(DevParams p, int par, int env, int plane, void* out) {
+    const long long hw = (long long)p.H * p.W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hw) return;
+    const int y = (int)(i / p.W), x = (int)(i - (long long)y * p.W);
+    const long long idx = (long long)env * p.plane + (long long)y * p.pitch + x;
+    if (plane == SFB_PLANE_BURN) {
+        ((double*)out)[i] = p.burn[idx];
+    } else if (plane == SFB_PLANE_ROS) {
+        ((double*)out)[i] = p.ros[idx];
+    } else {
+        const int c = reinterpret_cast<const CellT*>(p.state)[idx];
+        if (plane == SFB_PLANE_STATUS) {
+            ((int8_t*)out)[i] = (int8_t)to_burn_status(c & 7);
+        } else {
+            // duration as the NEXT update() call will see it before pruning
+            const int t = p.meta[(long long)par * p.E + env].t;
+            ((int32_t*)out)[i] = (c >> 3) ? sprite_age<CellT>(c >> 3, (t - 1) % Cell<CellT>::M) : -1;
+        }
+    }
+}
+
+__global__ void k_set_static(DevParams p, int env_first, int n_env, int plane, const float* src) {
+    const long long hw = (long long)p.H * p.W, total = (long long)n_env * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / hw);
+        const long long r = i - (long long)k * hw;
+        const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
+        float* rec = (float*)(p.stat + (long long)(env_first + k) * p.plane + (long long)y * p.pitch + x);
+        rec[plane] = src[r];  // the same host plane for every env of the range
+    }
+}
+
+// the dense rate_of_spread plane of the reference is rebuilt from zeros each step that gets
+// past the early return (fire.py:703-708)
+__global__ void k_clear_ros(DevParams p, int par) {
+    const long long total = (long long)p.E * p.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int env = (int)(i / p.plane);
+        const EnvMeta& m = p.meta[(long long)par * p.E + env];
+        if (m.running && !m.time_quit && m.any_cand) p.ros[i] = 0.0;
+    }
+}
+
+__global__ void k_rate_of_spread(const int8_t* dir, const float* rec, SfbParticle fp, long long n, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sfb_rate_of_spread_pair(dir[i], rec + 8 * i, fp);
+}
+
+// ---------------------------------------------------------------------------------------
+// dispatch on the cell width
+// ---------------------------------------------------------------------------------------
+#define DISPATCH(s, KERNEL, grid, block, ...)                                              \
+    do {                                                                                   \
+        if ((s)->cell_bytes == 1) KERNEL<uint8_t><<<(grid), (block), 0, (s)->stream>>>(__VA_ARGS__); \
+        else KERNEL<uint16_t><<<(grid), (block), 0, (s)->stream>>>(__VA_ARGS__);          \
+        (s)->launches_all++;                                                               \
+    } while (0)
+
+static unsigned cap_grid(sfb_sim* s, long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    long long cap = (long long)s->n_sm * 32;
+    return (unsigned)std::max(1LL, std::min(b, cap));
+}
+
+// ---------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------
+extern "C" const char* sfb_last_error(void) { return g_err; }
+extern "C" int sfb_abi_version(void) { return SFB_ABI_VERSION; }
+
+extern "C" void sfb_destroy(sfb_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->prm.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d.state);
+    cudaFree(s->d.burn);
+    cudaFree(s->d.ros);
+    cudaFree((void*)s->d.stat);
+    cudaFree(s->d.meta);
+    cudaFree(s->d.queue);
+    cudaFree(s->d.qcount);
+    cudaFree(s->d.overflow);
+    cudaFree(s->stage);
+    cudaFree(s->obs);
+    cudaFree(s->small);
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int create_impl(const sfb_params* prm, sfb_sim* s) {
+    s->prm = *prm;
+    CU(cudaSetDevice(prm->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, prm->device));
+    s->n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) CU(cudaEventCreate(&e));
+
+    DevParams& d = s->d;
+    memset(&d, 0, sizeof(d));
+    d.H = prm->H;
+    d.W = prm->W;
+    d.E = prm->E;
+    d.pitch = (prm->W + 15) / 16 * 16;
+    d.plane = (int64_t)d.H * d.pitch;
+    d.max_dur = prm->max_fire_duration;
+    d.diagonal = (prm->flags & SFB_DIAGONAL_SPREAD) != 0;
+    d.attenuate = (prm->flags & SFB_ATTENUATE_LINE_ROS) != 0;
+    d.shared_static = (prm->flags & SFB_SHARED_STATIC) != 0;
+    d.keep_ros = (prm->flags & SFB_KEEP_ROS) != 0;
+    d.has_max_time = (prm->flags & SFB_HAS_MAX_TIME) != 0;
+    d.ps = prm->pixel_scale;
+    d.dt = prm->update_rate;
+    d.max_time = prm->max_time;
+    d.part = SfbParticle{prm->h, prm->S_T, prm->S_e, prm->p_p, prm->M_f};
+    s->cell_bytes = (prm->max_fire_duration <= Cell<uint8_t>::M - 1 && !(prm->flags & SFB_WIDE_CELLS)) ? 1 : 2;
+
+    const int wr = 32 * (16 / s->cell_bytes);  // cells per warp row
+    d.strips = (d.pitch + wr - 1) / wr;
+    int R = prm->rows_per_chunk;
+    if (R <= 0) {
+        // enough warps to fill the machine a few times over, as few halo rows as possible
+        R = 32;
+        const long long want = (long long)s->n_sm * 64;
+        while (R > 4 && (long long)d.E * d.strips * ((d.H + R - 1) / R) < want) R /= 2;
+    }
+    R = std::max(4, (R + 3) / 4 * 4);
+    d.rows_per_chunk = R;
+    d.chunks = (d.H + R - 1) / R;
+    d.n_units = (int64_t)d.E * d.chunks * d.strips;
+
+    const int64_t total = (int64_t)d.E * d.plane;
+    int64_t qcap = prm->queue_capacity;
+    if (qcap <= 0) qcap = total <= (8 << 20) ? total : std::max<int64_t>(8 << 20, total / 8);
+    d.qcap = qcap;
+
+    int rc;
+    if ((rc = dmalloc(s, (char**)&d.state, (size_t)total * s->cell_bytes))) return rc;
+    if ((rc = dmalloc(s, &d.burn, (size_t)total * 8))) return rc;
+    if (d.keep_ros && (rc = dmalloc(s, &d.ros, (size_t)total * 8))) return rc;
+    const int64_t stat_cells = d.shared_static ? d.plane : total;
+    if ((rc = dmalloc(s, (StaticRec**)&d.stat, (size_t)stat_cells * sizeof(StaticRec)))) return rc;
+    if ((rc = dmalloc(s, &d.meta, (size_t)2 * d.E * sizeof(EnvMeta)))) return rc;
+    if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
+    if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
+    if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
+
+    CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
+    CU(cudaMemsetAsync(d.meta, 0, (size_t)2 * d.E * sizeof(EnvMeta), s->stream));  // running = 0
+    CU(cudaMemsetAsync(d.qcount, 0, 2 * sizeof(unsigned long long), s->stream));
+    CU(cudaMemsetAsync(d.overflow, 0, 2 * sizeof(int32_t), s->stream));
+    DISPATCH(s, k_clear_envs, cap_grid(s, total, 256), 256, d, (const int32_t*)nullptr, d.E, 1);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_create(const sfb_params* prm, sfb_sim** out) {
+    if (!prm || !out) return fail(SFB_ERR_INVALID, "sfb_create: null argument");
+    *out = nullptr;
+    if (prm->abi_version != SFB_ABI_VERSION)
+        return fail(SFB_ERR_INVALID, "sfb_create: abi_version %d, library is %d", prm->abi_version, SFB_ABI_VERSION);
+    if (prm->H < 1 || prm->W < 1 || prm->E < 1) return fail(SFB_ERR_INVALID, "sfb_create: H, W, E must be >= 1");
+    if (prm->max_fire_duration < 1 || prm->max_fire_duration > Cell<uint16_t>::M - 1)
+        return fail(SFB_ERR_INVALID, "sfb_create: max_fire_duration %d outside 1..%d", prm->max_fire_duration,
+                    Cell<uint16_t>::M - 1);
+    if (!(prm->update_rate == prm->update_rate) || !(prm->pixel_scale == prm->pixel_scale))
+        return fail(SFB_ERR_INVALID, "sfb_create: NaN pixel_scale / update_rate");
+    if ((int64_t)prm->E * prm->H * ((prm->W + 15) / 16 * 16) >= ((int64_t)1 << 47))
+        return fail(SFB_ERR_INVALID, "sfb_create: more than 2^47 cells");
+    if (prm->slab_total_H != 0 &&
+        (prm->slab_y0 < 0 || prm->slab_y0 + prm->H > prm->slab_total_H))
+        return fail(SFB_ERR_INVALID, "sfb_create: slab rows [%d, %d) outside grid of %d rows", prm->slab_y0,
+                    prm->slab_y0 + prm->H, prm->slab_total_H);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SFB_ERR_CUDA, "sfb_create: no CUDA device (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (prm->device < 0 || prm->device >= ndev) return fail(SFB_ERR_INVALID, "sfb_create: device %d of %d", prm->device, ndev);
+    sfb_sim* s = new (std::nothrow) sfb_sim();
+    if (!s) return fail(SFB_ERR_NOMEM, "sfb_create: host allocation failed");
+    int rc = create_impl(prm, s);
+    if (rc) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        sfb_destroy(s);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// static inputs
+// ---------------------------------------------------------------------------------------
+static int set_static_range(sfb_sim* s, int env, int plane, const float* dev_src) {
+    const DevParams& d = s->d;
+    int first = env, n = 1;
+    if (d.shared_static) {
+        first = 0;
+        n = 1;
+    } else if (env < 0) {
+        first = 0;
+        n = d.E;
+    }
+    const long long total = (long long)n * d.H * d.W;
+    k_set_static<<<cap_grid(s, total, 256), 256, 0, s->stream>>>(d, first, n, plane, dev_src);
+    s->launches_all++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sfb_set_static(sfb_sim* s, int32_t env, int32_t plane, const float* host) {
+    if (!s || !host) return fail(SFB_ERR_INVALID, "sfb_set_static: null argument");
+    if (plane < 0 || plane >= SFB_N_STATIC) return fail(SFB_ERR_INVALID, "sfb_set_static: plane %d", plane);
+    if (env < -1 || env >= s->d.E) return fail(SFB_ERR_INVALID, "sfb_set_static: env %d of %d", env, s->d.E);
+    int rc;
+    if ((rc = use(s))) return rc;
+    const size_t bytes = (size_t)s->d.H * s->d.W * sizeof(float);
+    if ((rc = ensure_stage(s, bytes))) return rc;
+    CU(cudaMemcpyAsync(s->stage, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    if ((rc = set_static_range(s, env, plane, (const float*)s->stage))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_set_static_all(sfb_sim* s, int32_t env, const float* host) {
+    if (!s || !host) return fail(SFB_ERR_INVALID, "sfb_set_static_all: null argument");
+    if (env < -1 || env >= s->d.E) return fail(SFB_ERR_INVALID, "sfb_set_static_all: env %d of %d", env, s->d.E);
+    int rc;
+    if ((rc = use(s))) return rc;
+    const size_t hw = (size_t)s->d.H * s->d.W;
+    if ((rc = ensure_stage(s, hw * sizeof(float) * SFB_N_STATIC))) return rc;
+    CU(cudaMemcpyAsync(s->stage, host, hw * sizeof(float) * SFB_N_STATIC, cudaMemcpyHostToDevice, s->stream));
+    for (int pl = 0; pl < SFB_N_STATIC; ++pl)
+        if ((rc = set_static_range(s, env, pl, (const float*)s->stage + pl * hw))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// between-step mutations
+// ---------------------------------------------------------------------------------------
+extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32_t* xy) {
+    if (!s || !xy) return fail(SFB_ERR_INVALID, "sfb_reset: null argument");
+    const DevParams& d = s->d;
+    if (n < 1 || n > d.E) return fail(SFB_ERR_INVALID, "sfb_reset: n = %d of %d envs", n, d.E);
+    const int total_H = s->prm.slab_total_H ? s->prm.slab_total_H : d.H;
+    for (int k = 0; k < n; ++k) {
+        if (envs && (envs[k] < 0 || envs[k] >= d.E)) return fail(SFB_ERR_INVALID, "sfb_reset: env %d of %d", envs[k], d.E);
+        const int x = xy[2 * k], y = xy[2 * k + 1];
+        if (x < 0 || x >= d.W || y < 0 || y >= total_H)
+            return fail(SFB_ERR_INVALID, "sfb_reset: initial fire (%d, %d) outside %d x %d grid", x, y, d.W, total_H);
+    }
+    int rc;
+    if ((rc = use(s))) return rc;
+    const size_t need = (size_t)n * 3 * sizeof(int32_t);
+    if ((rc = ensure_small(s, need))) return rc;
+    int32_t* d_xy = s->small;
+    int32_t* d_envs = envs ? s->small + 2 * (size_t)n : nullptr;
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    if (envs) CU(cudaMemcpyAsync(d_envs, envs, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    DISPATCH(s, k_clear_envs, cap_grid(s, (long long)n * d.plane, 256), 256, d, (const int32_t*)d_envs, n, 1);
+    DISPATCH(s, k_reset_meta, nblocks(n, 128), 128, d, s->parity, (const int32_t*)d_envs, (const int32_t*)d_xy, n,
+             s->prm.slab_y0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));  // host buffers are borrowed for the call only
+    return 0;
+}
+
+extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
+    if (!s || (n > 0 && !pts)) return fail(SFB_ERR_INVALID, "sfb_apply_points: null argument");
+    if (n <= 0) return 0;
+    const DevParams& d = s->d;
+    const int total_H = s->prm.slab_total_H ? s->prm.slab_total_H : d.H;
+    bool present[6] = {false, false, false, false, false, false};
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t* q = pts + 4 * i;
+        if (q[0] < 0 || q[0] >= d.E || q[1] < 0 || q[1] >= d.W || q[2] < 0 || q[2] >= total_H || q[3] < 0 || q[3] > 5)
+            return fail(SFB_ERR_INVALID, "sfb_apply_points: point %lld = (env %d, x %d, y %d, kind %d) out of range",
+                        (long long)i, q[0], q[1], q[2], q[3]);
+        present[q[3]] = true;
+    }
+    int rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = ensure_small(s, (size_t)n * 4 * sizeof(int32_t)))) return rc;
+    CU(cudaMemcpyAsync(s->small, pts, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    // one launch per kind in BurnStatus order: FireSimulation.update_mitigation applies the
+    // fireline, scratchline and wetline managers in that order (simulation.py:468-478), so
+    // when two points name one cell the later kind wins, as it does there
+    for (int kind = 0; kind <= 5; ++kind) {
+        if (!present[kind]) continue;
+        DISPATCH(s, k_apply_points, nblocks(n, 256), 256, d, (const int32_t*)s->small, (long long)n, kind,
+                 s->prm.slab_y0);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int check_env_range(sfb_sim* s, const char* who, int env0, int n) {
+    if (env0 < 0 || n < 1 || env0 + n > s->d.E)
+        return fail(SFB_ERR_INVALID, "%s: envs [%d, %d) of %d", who, env0, env0 + n, s->d.E);
+    return 0;
+}
+
+static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
+    const DevParams& d = s->d;
+    const size_t bytes = (size_t)n * d.H * d.W;
+    int rc;
+    if ((rc = ensure_stage(s, bytes))) return rc;
+    CU(cudaMemcpyAsync(s->stage, maps, bytes, cudaMemcpyHostToDevice, s->stream));
+    DISPATCH(s, k_set_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (const int8_t*)s->stage);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int download_maps(sfb_sim* s, int env0, int n, int8_t* out) {
+    const DevParams& d = s->d;
+    const size_t bytes = (size_t)n * d.H * d.W;
+    int rc;
+    if ((rc = ensure_stage(s, bytes))) return rc;
+    DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (int8_t*)s->stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+extern "C" int sfb_set_fire_map(sfb_sim* s, int32_t env0, int32_t n, const int8_t* maps) {
+    if (!s || !maps) return fail(SFB_ERR_INVALID, "sfb_set_fire_map: null argument");
+    int rc;
+    if ((rc = check_env_range(s, "sfb_set_fire_map", env0, n))) return rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = upload_maps(s, env0, n, maps))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------
+static int enqueue_step(sfb_sim* s) {
+    const DevParams& d = s->d;
+    const int par = s->parity;
+    if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
+    DISPATCH(s, k_sweep, nblocks(d.n_units, SWEEP_WARPS), SWEEP_WARPS * 32, d, par);
+    if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
+    if (d.keep_ros) {
+        k_clear_ros<<<cap_grid(s, (long long)d.E * d.plane, 256), 256, 0, s->stream>>>(d, par);
+        s->launches_all++;
+    }
+    DISPATCH(s, k_eval, (unsigned)(s->n_sm * 8), 256, d, par);
+    s->launches_step += 2;
+    s->parity ^= 1;
+    if (s->timing) {
+        CU(cudaEventRecord(s->ev[2], s->stream));
+        CU(cudaEventSynchronize(s->ev[2]));
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+        CU(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+        s->sweep_ms += a;
+        s->eval_ms += b;
+        s->timed_steps++;
+    }
+    return 0;
+}
+
+extern "C" int sfb_step(sfb_sim* s, int32_t n_steps, int32_t sync) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_step: null handle");
+    if (n_steps < 0) return fail(SFB_ERR_INVALID, "sfb_step: n_steps %d", n_steps);
+    int rc;
+    if ((rc = use(s))) return rc;
+    for (int i = 0; i < n_steps; ++i)
+        if ((rc = enqueue_step(s))) return rc;
+    CU(cudaGetLastError());
+    if (sync) CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_step_timed(sfb_sim* s, int32_t n_steps, float* ms) {
+    if (!s || !ms) return fail(SFB_ERR_INVALID, "sfb_step_timed: null argument");
+    int rc;
+    if ((rc = use(s))) return rc;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, s->stream));
+    for (int i = 0; i < n_steps; ++i)
+        if ((rc = enqueue_step(s))) return rc;
+    CU(cudaEventRecord(b, s->stream));
+    CU(cudaEventSynchronize(b));
+    CU(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int read_status(sfb_sim* s, int env0, int n, int32_t* status, double* elapsed, int32_t* steps) {
+    std::vector<EnvMeta> m((size_t)n);
+    CU(cudaMemcpyAsync(m.data(), s->d.meta + (size_t)s->parity * s->d.E + env0, (size_t)n * sizeof(EnvMeta),
+                       cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < n; ++i) {
+        if (status) status[i] = m[i].running ? SFB_RUNNING : SFB_QUIT;
+        if (elapsed) elapsed[i] = m[i].elapsed;
+        if (steps) steps[i] = m[i].t > 0 ? m[i].t - 1 : 0;
+    }
+    return 0;
+}
+
+extern "C" int sfb_update(sfb_sim* s, int32_t env0, int32_t n, int8_t* maps, int32_t* status) {
+    if (!s || !maps) return fail(SFB_ERR_INVALID, "sfb_update: null argument");
+    int rc;
+    if ((rc = check_env_range(s, "sfb_update", env0, n))) return rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = upload_maps(s, env0, n, maps))) return rc;
+    if ((rc = enqueue_step(s))) return rc;
+    if ((rc = download_maps(s, env0, n, maps))) return rc;
+    if (status) return read_status(s, env0, n, status, nullptr, nullptr);
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_synchronize(sfb_sim* s) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_synchronize: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------
+extern "C" int sfb_get_fire_map(sfb_sim* s, int32_t env0, int32_t n, int8_t* out) {
+    if (!s || !out) return fail(SFB_ERR_INVALID, "sfb_get_fire_map: null argument");
+    int rc;
+    if ((rc = check_env_range(s, "sfb_get_fire_map", env0, n))) return rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = download_maps(s, env0, n, out))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_get_plane(sfb_sim* s, int32_t env, int32_t plane, void* out) {
+    if (!s || !out) return fail(SFB_ERR_INVALID, "sfb_get_plane: null argument");
+    if (env < 0 || env >= s->d.E) return fail(SFB_ERR_INVALID, "sfb_get_plane: env %d of %d", env, s->d.E);
+    if (plane < 0 || plane > SFB_PLANE_STATUS) return fail(SFB_ERR_INVALID, "sfb_get_plane: plane %d", plane);
+    if (plane == SFB_PLANE_ROS && !s->d.keep_ros)
+        return fail(SFB_ERR_STATE, "sfb_get_plane: rate_of_spread is only kept with SFB_KEEP_ROS");
+    int rc;
+    if ((rc = use(s))) return rc;
+    const size_t hw = (size_t)s->d.H * s->d.W;
+    const size_t esz = plane <= SFB_PLANE_ROS ? 8 : (plane == SFB_PLANE_AGE ? 4 : 1);
+    if ((rc = ensure_stage(s, hw * esz))) return rc;
+    DISPATCH(s, k_get_plane, nblocks((long long)hw, 256), 256, s->d, s->parity, env, plane, s->stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->stage, hw * esz, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_get_status(sfb_sim* s, int32_t* status, double* elapsed, int32_t* steps) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_status: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    return read_status(s, 0, s->d.E, status, elapsed, steps);
+}
+
+extern "C" int sfb_fire_map_device(sfb_sim* s, void** dev) {
+    if (!s || !dev) return fail(SFB_ERR_INVALID, "sfb_fire_map_device: null argument");
+    int rc;
+    if ((rc = use(s))) return rc;
+    const size_t bytes = (size_t)s->d.E * s->d.H * s->d.W;
+    if (!s->obs && (rc = dmalloc(s, (char**)&s->obs, bytes))) return rc;
+    DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, s->d, 0, s->d.E, (int8_t*)s->obs);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    *dev = s->obs;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------
+extern "C" int sfb_get_stream(sfb_sim* s, void** stream) {
+    if (!s || !stream) return fail(SFB_ERR_INVALID, "sfb_get_stream: null argument");
+    *stream = (void*)s->stream;
+    return 0;
+}
+
+extern "C" int sfb_get_launch_counts(sfb_sim* s, int64_t* all_kernels, int64_t* step_kernels) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_launch_counts: null handle");
+    if (all_kernels) *all_kernels = s->launches_all;
+    if (step_kernels) *step_kernels = s->launches_step;
+    return 0;
+}
+
+extern "C" int sfb_set_kernel_timing(sfb_sim* s, int32_t enabled) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_set_kernel_timing: null handle");
+    s->timing = enabled != 0;
+    s->sweep_ms = s->eval_ms = 0;
+    s->timed_steps = 0;
+    return 0;
+}
+
+extern "C" int sfb_get_kernel_ms(sfb_sim* s, double* sweep_ms, double* eval_ms, int64_t* n_steps) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_kernel_ms: null handle");
+    if (sweep_ms) *sweep_ms = s->sweep_ms;
+    if (eval_ms) *eval_ms = s->eval_ms;
+    if (n_steps) *n_steps = s->timed_steps;
+    s->sweep_ms = s->eval_ms = 0;
+    s->timed_steps = 0;
+    return 0;
+}
+
+extern "C" int sfb_get_queue_stats(sfb_sim* s, int64_t* entries, int64_t* capacity, int32_t* overflowed) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_queue_stats: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    // the step that ran last used parity^1; k_eval leaves its count in place until the
+    // step after next resets it
+    const int par = s->parity ^ 1;
+    unsigned long long cnt = 0;
+    int32_t ovf = 0;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(&cnt, s->d.qcount + par, sizeof(cnt), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&ovf, s->d.overflow + par, sizeof(ovf), cudaMemcpyDeviceToHost));
+    if (entries) *entries = (int64_t)cnt;
+    if (capacity) *capacity = s->d.qcap;
+    if (overflowed) *overflowed = ovf;
+    return 0;
+}
+
+extern "C" int sfb_device_bytes(sfb_sim* s, int64_t* bytes) {
+    if (!s || !bytes) return fail(SFB_ERR_INVALID, "sfb_device_bytes: null argument");
+    *bytes = s->dev_bytes;
+    return 0;
+}
+
+extern "C" int sfb_rate_of_spread(int32_t device, const int8_t* dir, const float* rec, const float* particle,
+                                  int64_t n, double* out) {
+    if (!dir || !rec || !particle || !out || n < 0) return fail(SFB_ERR_INVALID, "sfb_rate_of_spread: bad argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(device));
+    int8_t* d_dir = nullptr;
+    float* d_rec = nullptr;
+    double* d_out = nullptr;
+    CU(cudaMalloc((void**)&d_dir, (size_t)n));
+    CU(cudaMalloc((void**)&d_rec, (size_t)n * 8 * sizeof(float)));
+    CU(cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)));
+    CU(cudaMemcpy(d_dir, dir, (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_rec, rec, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    SfbParticle fp{particle[0], particle[1], particle[2], particle[3], particle[4]};
+    k_rate_of_spread<<<nblocks(n, 128), 128>>>(d_dir, d_rec, fp, (long long)n, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_dir);
+    cudaFree(d_rec);
+    cudaFree(d_out);
+    return 0;
+}

@@ -1,0 +1,214 @@
+"""
+GPU parity tests: the CUDA stepper, driven through the C ABI (simfire_b200.FireEngine is a
+one-to-one ctypes wrapper), against the golden trajectories recorded from the unmodified
+reference and against the NumPy oracle on seeded inputs.
+
+Tolerances.  fire_map / GameStatus / elapsed_time: bit-exact.  Rate of spread and the
+float64 burn accumulator: 1e-5 relative (BASELINE.json north_star), plus an absolute term
+for pairs where 1 + phi_w + phi_s cancels ("Mixed precision"): the
+error of a float32 transcendental is relative to the un-cancelled magnitude, so the
+absolute term is 3e-6 of the rate the same pair would have on flat ground.
+"""
+import numpy as np
+import pytest
+from scenario_io import GOLDEN, check_trajectory, dense_params, load_scenario, scenario_names
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def engine_for(sc, **kw):
+    from simfire_b200 import FireEngine
+
+    eng = FireEngine(
+        sc["H"], sc["W"], kw.pop("E", 1), pixel_scale=float(sc["ps"]), update_rate=float(sc["dt"]),
+        max_fire_duration=int(sc["max_dur"]), max_time=sc["max_time"], attenuate_line_ros=bool(sc["attenuate"]),
+        diagonal_spread=bool(sc["diagonal"]), M_f=float(sc["M_f"]), keep_ros=True, **kw,
+    )  # fmt: skip
+    eng.set_static(sc["planes"])
+    return eng
+
+
+class EngineAdapter:
+    """Adapts FireEngine (env `env`) to scenario_io.check_trajectory."""
+
+    def __init__(self, eng, env=0):
+        self.eng, self.env = eng, env
+
+    def apply_points(self, pts):
+        if pts:
+            self.eng.apply_points([(self.env, x, y, k) for x, y, k in pts])
+
+    def step(self):
+        self.eng.step(1)
+        return int(self.eng.status()[0][self.env])
+
+    def get_map(self):
+        return self.eng.fire_map(self.env, 1)[0]
+
+    def get_burn(self):
+        return self.eng.plane("burn", self.env)
+
+    def get_ros(self):
+        return self.eng.plane("ros", self.env)
+
+    def elapsed(self):
+        return float(self.eng.status()[1][self.env])
+
+
+def test_rate_of_spread_golden_pairs():
+    """compute_rate_of_spread (rothermel.py:4-136) on the device vs the reference's output."""
+    from simfire_b200 import rate_of_spread
+
+    z = np.load(f"{GOLDEN}/rothermel_pairs.npz")
+    h, S_T, S_e, p_p, M_f = z["consts"]
+    args = [z[k] for k in ("w_0", "delta", "M_x", "sigma", "U", "U_dir")]
+    R = rate_of_spread(z["direction"], *args, z["slope_mag"], z["slope_dir"], h=h, S_T=S_T, S_e=S_e, p_p=p_p, M_f=M_f)
+    R_flat = rate_of_spread(z["direction"], *args, 0.0, 0.0, h=h, S_T=S_T, S_e=S_e, p_p=p_p, M_f=M_f)
+    want = z["R"]
+    assert np.array_equal(R == 0, want == 0)
+    err = np.abs(R - want)
+    tol = RTOL * np.abs(want) + 3e-6 * np.maximum(R_flat, np.abs(want))
+    assert np.all(err <= tol), f"max excess {np.max(err - tol)} at {np.argmax(err - tol)}"
+    # and without the cancellation allowance almost everywhere
+    assert np.mean(err <= RTOL * np.abs(want)) > 0.999
+
+
+def test_rate_of_spread_known_answer():
+    """simfire/world/_tests/test_rothermel.py:10-100 (src == dst there, so theta = 0 = direction 0)."""
+    from simfire_b200 import rate_of_spread
+
+    z = np.load(f"{GOLDEN}/rothermel_pairs.npz")
+    R = rate_of_spread(np.zeros(8, np.int8), z["kat_w_0"], z["kat_delta"], z["kat_M_x"], z["kat_sigma"],
+                       z["kat_U"], z["kat_U_dir"], 0.0, 0.0, M_f=0.03)  # fmt: skip
+    np.testing.assert_array_almost_equal(R, z["kat_literal"], decimal=2)
+    np.testing.assert_allclose(R, z["kat_R"], rtol=RTOL)
+
+
+def _burn_tol(sc):
+    # burn is a running sum of R*dt - attenuation: errors scale with the largest addend
+    scale = max(float(np.max(np.abs(sc["burns"]))), float(np.max(np.abs(sc["ross"]))), 1.0)
+    return dict(burn_exact=False, burn_rtol=RTOL, burn_atol=RTOL * scale)
+
+
+@pytest.mark.parametrize("name", scenario_names())
+def test_golden_trajectory(name):
+    """fire_map bit-exact every step; burn / ros within tolerance; status and elapsed exact."""
+    sc = load_scenario(name)
+    with engine_for(sc) as eng:
+        eng.reset([sc["init"]])
+        check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
+
+
+@pytest.mark.parametrize("name", ["scenario_a_models_diag_att", "scenario_d_midrun_mitigation",
+                                  "scenario_b_models_4nbr_noatt", "scenario_f_max_time"])  # fmt: skip
+@pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64"])
+def test_golden_trajectory_variants(name, variant):
+    """The 16-bit cell layout, the dense fallback taken on queue overflow and other chunk
+    heights must give the same trajectories."""
+    sc = load_scenario(name)
+    kw = {"wide_cells": dict(wide_cells=True), "queue_overflow": dict(queue_capacity=3),
+          "rows4": dict(rows_per_chunk=4), "rows64": dict(rows_per_chunk=64)}[variant]  # fmt: skip
+    with engine_for(sc, **kw) as eng:
+        eng.reset([sc["init"]])
+        check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
+        if variant == "queue_overflow":
+            assert eng.queue_stats()[1] == 3
+
+
+def test_batched_envs_are_independent():
+    """E copies of one terrain (shared static planes), different ignition points, each
+    checked against its own NumPy-oracle run; env 2 is reset half way."""
+    from oracle.dense_numpy import DenseFire
+
+    sc = load_scenario("scenario_a_models_diag_att")
+    H, W = sc["H"], sc["W"]
+    rng = np.random.default_rng(7)
+    burnable = np.argwhere(sc["planes"]["w_0"] > 0)
+    starts = [tuple(int(v) for v in burnable[i][::-1]) for i in rng.choice(len(burnable), 5, replace=False)]
+    E = len(starts)
+    pre = [(e, x, y, k) for e in range(E) for x, y, k in sc["pre"] if (x, y) != starts[e]]
+    with engine_for(sc, E=E, shared_static=True) as eng:
+        eng.reset(starts)
+        eng.apply_points(pre)
+        oracles = []
+        for e in range(E):
+            o = DenseFire(sc["planes"], dense_params(sc), starts[e])
+            o.apply_points([(x, y, k) for ee, x, y, k in pre if ee == e])
+            oracles.append(o)
+        for step in range(1, 41):
+            if step == 15:  # RL-style reset of one env while the others keep running
+                eng.reset([starts[0]], envs=[2])
+                oracles[2] = DenseFire(sc["planes"], dense_params(sc), starts[0])
+            eng.step(1)
+            st, el, n = eng.status()
+            maps = eng.fire_map()
+            for e, o in enumerate(oracles):
+                want_st = o.step()
+                assert st[e] == want_st, (step, e)
+                assert el[e] == o.elapsed_time, (step, e)
+                assert n[e] == o.step_count, (step, e)
+                assert np.array_equal(maps[e], o.status), f"env {e} step {step}"
+
+
+def test_multi_step_launch_equals_single_steps():
+    sc = load_scenario("scenario_c_random_fuel_hills")
+    with engine_for(sc) as a, engine_for(sc) as b:
+        for eng in (a, b):
+            eng.reset([sc["init"]])
+            eng.apply_points([(0, x, y, k) for x, y, k in sc["pre"]])
+        for _ in range(12):
+            a.step(1)
+        b.step(12, sync=False)
+        b.synchronize()
+        assert np.array_equal(a.fire_map(), b.fire_map())
+        assert np.array_equal(a.plane("burn"), b.plane("burn"))
+        assert a.status()[1][0] == b.status()[1][0]
+
+
+def test_update_with_host_maps():
+    """sfb_update: the manager.update(fire_map) drop-in with host buffers."""
+    sc = load_scenario("scenario_d_midrun_mitigation")
+    with engine_for(sc) as eng:
+        eng.reset([sc["init"]])
+        fm = np.zeros((sc["H"], sc["W"]), dtype=np.int8)
+        fm[sc["init"][1], sc["init"][0]] = 1
+        for x, y, k in sc["pre"]:
+            fm[y, x] = k
+        map_at = {int(s): i for i, s in enumerate(sc["map_steps"])}
+        for step in range(1, int(sc["n_steps"]) + 1):
+            for x, y, k in sc["schedule"].get(step, ()):
+                fm[y, x] = k  # the caller edits its own array, as mitigation.py:77 does
+            st = eng.update(fm)
+            assert st[0] == int(sc["status"][step - 1])
+            if step in map_at:
+                assert np.array_equal(fm, sc["maps"][map_at[step]]), f"step {step}"
+
+
+def test_observation_tensor_matches_host_map():
+    import torch
+
+    sc = load_scenario("scenario_chaparral_64")
+    with engine_for(sc) as eng:
+        eng.reset([sc["init"]])
+        eng.step(10)
+        t = eng.fire_map_device()
+        assert t.is_cuda and t.dtype == torch.int8 and tuple(t.shape) == (1, sc["H"], sc["W"])
+        assert np.array_equal(t.cpu().numpy(), eng.fire_map())
+
+
+def test_errors_are_reported():
+    from simfire_b200 import FireEngine, SfbError
+
+    with pytest.raises(SfbError):
+        FireEngine(8, 8, 1, pixel_scale=50.0, update_rate=1.0, max_fire_duration=0)
+    with FireEngine(8, 8, 1, pixel_scale=50.0, update_rate=1.0, max_fire_duration=4) as eng:
+        with pytest.raises(SfbError):
+            eng.reset([(8, 0)])
+        with pytest.raises(SfbError):
+            eng.apply_points([(0, 1, 1, 9)])
+        with pytest.raises(SfbError):
+            eng.plane("ros")
+        with pytest.raises(ValueError):
+            eng.set_static({k: np.zeros((3, 3)) for k in ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")})
