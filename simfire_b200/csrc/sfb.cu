@@ -271,6 +271,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.queue);
     cudaFree(s->d.qcount);
     cudaFree(s->d.overflow);
+    cudaFree((void*)s->d.filler);
     cudaFree(s->stage);
     cudaFree(s->obs);
     cudaFree(s->small);
@@ -337,6 +338,13 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
     if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
     if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
+    {
+        const size_t n = (size_t)d.pitch + 32;
+        std::vector<uint8_t> fill(n * s->cell_bytes, 0);
+        for (size_t i = 0; i < n; ++i) fill[i * s->cell_bytes] = (uint8_t)ST_BURNED;  // little endian
+        if ((rc = dmalloc(s, (char**)&d.filler, fill.size()))) return rc;
+        CU(cudaMemcpy((void*)d.filler, fill.data(), fill.size(), cudaMemcpyHostToDevice));
+    }
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
     CU(cudaMemsetAsync(d.meta, 0, (size_t)2 * d.E * sizeof(EnvMeta), s->stream));  // running = 0

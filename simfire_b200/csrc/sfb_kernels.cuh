@@ -75,6 +75,7 @@ struct DevParams {
     // slab mode: rows -1 and H of this slab live in a neighbour slab (peer device memory)
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
+    const void* filler;       // (pitch + 2 * 16) BURNED cells: stands in for rows outside the grid
 };
 
 template <typename CellT>
@@ -154,15 +155,18 @@ __device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& 
 // three-row window in registers.  A row is examined cell by cell only if the window holds
 // a sprite code (or, with attenuation, a control line): the window is then staged in
 // shared memory so that the eight neighbours of every cell are plain byte reads.
+//
+// The streaming part is straight-line code: rows outside the grid are read from a row of
+// BURNED filler cells (p.filler) instead of being branched around, and the cells left and
+// right of the strip come from one predicated byte load by lanes 0 and 31.
 // ---------------------------------------------------------------------------------------
 constexpr int SWEEP_WARPS = 4;
 constexpr int WQ_CAP = 96;  // >= 64: a flush is forced whenever fewer than 32 slots are free
 
-template <typename CellT>
 struct RowRegs {
-    uint4 v;    // this lane's CPL cells
-    CellT h;    // lane 0: cell left of the strip, lane 31: cell right of it
-    uint32_t b; // ballot: lanes whose segment needs a look
+    uint4 v;     // this lane's CPL cells
+    uint32_t h;  // lane 0: cell left of the strip, lane 31: cell right of it
+    uint32_t b;  // ballot: lanes whose segment needs a look
 };
 
 template <typename CellT>
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
     constexpr int CPL = C::CPL;
     constexpr int WR = 32 * CPL;        // cells per warp row
     constexpr int RS = WR + 2 * CPL;    // staged row: CPL pad | WR cells | CPL pad (16-B aligned)
-    constexpr int GROUPS = WR / 32;     // 32-cell groups per warp row
     constexpr int SEG_PER_GROUP = 32 / CPL;
+    constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
     __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
     __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
 
@@ -188,17 +192,43 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
     const bool spread = !mp->time_quit;
     const int tm1 = (mp->t - 1) % C::M;
     const int max_dur = p.max_dur;
+    const int H = p.H, pitch = p.pitch;
+    const bool diagonal = p.diagonal != 0, attenuate = p.attenuate != 0;
 
-    CellT* const envbase = reinterpret_cast<CellT*>(p.state) + (long long)env * p.plane;
+    CellT* const state = reinterpret_cast<CellT*>(p.state);
+    const long long env_off = (long long)env * p.plane;
+    const CellT* const envbase = state + env_off;
+    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
     const int x0 = strip * WR;
     const int xl = x0 + lane * CPL;
     const int y_begin = chunk * p.rows_per_chunk;
-    const int y_end = min(y_begin + p.rows_per_chunk, p.H);
-    const uint32_t look_mask = p.attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
-    const bool has_left = strip > 0, has_right = x0 + WR < p.pitch;
+    const int y_end = min(y_begin + p.rows_per_chunk, H);
+    const uint32_t look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
+    const uint32_t hmask = look_mask & CELL_ALL;
+    const bool in_x = xl < pitch;
+    // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
+    const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
+    const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
     CellT(*sm)[RS] = sm_all[warp];
     unsigned long long* const wq = wq_all[warp];
     int wcount = 0;  // warp-uniform
+
+    // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
+    auto edge_row = [&](int y) -> const CellT* {
+        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + env_off;
+        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + env_off;
+        return filler;
+    };
+    auto issue = [&](const CellT* rowp, RowRegs& r) {
+        r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+        r.h = ST_BURNED;
+        if (in_x) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
+        if (hpred) r.h = rowp[hoff];
+    };
+    auto finish = [&](RowRegs& r) {
+        const uint32_t a = ((r.v.x | r.v.y | r.v.z | r.v.w) & look_mask) | (r.h & hmask);
+        r.b = __ballot_sync(0xffffffffu, a != 0);
+    };
 
     // one global atomic per flush instead of one per push: the queue tail is a single
     // address and L2 serialises atomics on it
@@ -217,51 +247,36 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
         __syncwarp();
     };
 
-    auto load_row = [&](int y, RowRegs<CellT>& r) {
-        r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
-        r.h = (CellT)ST_BURNED;
-        const CellT* rowp = nullptr;
-        if (y >= 0 && y < p.H) rowp = envbase + (long long)y * p.pitch;
-        else if (y == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.plane;
-        else if (y == p.H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.plane;
-        if (rowp) {
-            if (xl < p.pitch) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
-            if (lane == 0 && has_left) r.h = rowp[x0 - 1];
-            if (lane == 31 && has_right) r.h = rowp[x0 + WR];
-        }
-        uint32_t a = (r.v.x | r.v.y | r.v.z | r.v.w) & look_mask;
-        const uint32_t hm = (sizeof(CellT) == 1) ? (look_mask & 0xFFu) : (look_mask & 0xFFFFu);
-        a |= (uint32_t)r.h & hm;
-        r.b = __ballot_sync(0xffffffffu, a != 0);
-    };
-
     int f_live = 0, f_cand = 0;
 
-    auto process_row = [&](int y, const RowRegs<CellT>& rp, const RowRegs<CellT>& rc, const RowRegs<CellT>& rn) {
+    auto process_row = [&](int y, const RowRegs& rp, const RowRegs& rc, const RowRegs& rn) {
         const uint32_t act = rp.b | rc.b | rn.b;
         if (act == 0 || y >= y_end) return;  // warp-uniform
         __syncwarp();
         *reinterpret_cast<uint4*>(&sm[0][CPL + lane * CPL]) = rp.v;
         *reinterpret_cast<uint4*>(&sm[1][CPL + lane * CPL]) = rc.v;
         *reinterpret_cast<uint4*>(&sm[2][CPL + lane * CPL]) = rn.v;
-        if (lane == 0) { sm[0][CPL - 1] = rp.h; sm[1][CPL - 1] = rc.h; sm[2][CPL - 1] = rn.h; }
-        if (lane == 31) { sm[0][CPL + WR] = rp.h; sm[1][CPL + WR] = rc.h; sm[2][CPL + WR] = rn.h; }
+        if (lane == 0) { sm[0][CPL - 1] = (CellT)rp.h; sm[1][CPL - 1] = (CellT)rc.h; sm[2][CPL - 1] = (CellT)rn.h; }
+        if (lane == 31) { sm[0][CPL + WR] = (CellT)rp.h; sm[1][CPL + WR] = (CellT)rc.h; sm[2][CPL + WR] = (CellT)rn.h; }
         __syncwarp();
-        // lanes whose own or adjacent segment needs a look
+        // segments whose own or adjacent segment needs a look -> 32-cell groups to visit
         const uint32_t near = act | (act << 1) | (act >> 1);
-#pragma unroll 1
-        for (int g = 0; g < GROUPS; ++g) {
-            const uint32_t gm = ((SEG_PER_GROUP == 2) ? 0x3u : 0xFu) << (g * SEG_PER_GROUP);
-            if (!(near & gm)) continue;  // warp-uniform
+        uint32_t groups = 0;
+#pragma unroll
+        for (int g = 0; g < WR / 32; ++g)
+            if (near & (((1u << SEG_PER_GROUP) - 1u) << (g * SEG_PER_GROUP))) groups |= 1u << g;
+        while (groups) {  // warp-uniform
+            const int g = __ffs(groups) - 1;
+            groups &= groups - 1;
             const int xi = CPL + g * 32 + lane;  // index in the staged row
             const int x = x0 + g * 32 + lane;
             const int c = sm[1][xi];
             int s = c & 7;
             const int code = c >> 3;
-            const long long idx = (long long)env * p.plane + (long long)y * p.pitch + x;
+            const long long idx = env_off + (long long)y * pitch + x;
             if (code) {
                 if (sprite_age<CellT>(code, tm1) >= max_dur) {  // fire.py:116-161
-                    reinterpret_cast<CellT*>(p.state)[idx] = (CellT)ST_BURNED;
+                    state[idx] = (CellT)ST_BURNED;
                     s = ST_BURNED;
                 } else {
                     f_live = 1;
@@ -280,18 +295,18 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
                         if (a < best) { best = a; dir = k; }
                     }
                 };
-                if (p.diagonal) look(2, +1, 5);
+                if (diagonal) look(2, +1, 5);
                 look(2, 0, 6);
-                if (p.diagonal) look(2, -1, 7);
+                if (diagonal) look(2, -1, 7);
                 look(1, +1, 4);
                 look(1, -1, 0);
-                if (p.diagonal) look(0, +1, 3);
+                if (diagonal) look(0, +1, 3);
                 look(0, 0, 2);
-                if (p.diagonal) look(0, -1, 1);
+                if (diagonal) look(0, -1, 1);
                 if (dir != DIR_NONE) {
                     f_cand = 1;
                     push = true;
-                } else if ((s & ST_LINE_BIT) && p.attenuate) {
+                } else if ((s & ST_LINE_BIT) && attenuate) {
                     push = true;
                 }
             }
@@ -304,21 +319,39 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
         }
     };
 
-    // rolling three-row window, four loads in flight
-    RowRegs<CellT> r0, r1, r2, r3, r4, r5;
-    load_row(y_begin - 1, r0);
-    load_row(y_begin, r1);
+    // rolling three-row window; the four loads of a batch are issued before any is used
+    RowRegs r0, r1, r2, r3, r4, r5;
+    const CellT* rowp = envbase + (long long)y_begin * pitch;  // row y of the loop below
+    issue(y_begin > 0 ? rowp - pitch : edge_row(-1), r0);
+    issue(rowp, r1);
+    finish(r0);
+    finish(r1);
     for (int y = y_begin; y < y_end; y += 4) {
-        load_row(y + 1, r2);
-        load_row(y + 2, r3);
-        load_row(y + 3, r4);
-        load_row(y + 4, r5);
+        const CellT* q1 = rowp + pitch;
+        const CellT* q2 = q1 + pitch;
+        const CellT* q3 = q2 + pitch;
+        const CellT* q4 = q3 + pitch;
+        if (y + 4 >= H) {  // warp-uniform, last batch of the grid only
+            if (y + 1 >= H) q1 = edge_row(y + 1);
+            if (y + 2 >= H) q2 = edge_row(y + 2);
+            if (y + 3 >= H) q3 = edge_row(y + 3);
+            q4 = edge_row(y + 4);
+        }
+        issue(q1, r2);
+        issue(q2, r3);
+        issue(q3, r4);
+        issue(q4, r5);
+        finish(r2);
+        finish(r3);
+        finish(r4);
+        finish(r5);
         process_row(y, r0, r1, r2);
         process_row(y + 1, r1, r2, r3);
         process_row(y + 2, r2, r3, r4);
         process_row(y + 3, r3, r4, r5);
         r0 = r4;
         r1 = r5;
+        rowp = q4;
     }
     flush();
     f_live = __any_sync(0xffffffffu, f_live);
