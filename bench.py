@@ -260,7 +260,7 @@ def gpu_arm(args):
         E = args.envs
     H, W = wl.H, wl.W
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
-                     **wl.engine_kwargs())  # fmt: skip
+                     sweep_ldg=(args.sweep == "ldg"), **wl.engine_kwargs())  # fmt: skip
     eng.set_static(wl.planes)
     starts = wl.burnable_starts(E, seed=1000 + rank)
     eng.reset(starts)
@@ -367,7 +367,7 @@ def gpu_arm(args):
                 "api": "FireEngine.apply_points + step + fire_map (pinned host buffers)"},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "traffic": load_traffic_note(args.workload),
             "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--burn-in", type=int, default=60)
     ap.add_argument("--rows-per-chunk", type=int, default=0)
+    ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
     ap.add_argument("--roofline-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget", type=float, default=12.0)

@@ -62,8 +62,10 @@ enum sfb_flags {
     SFB_KEEP_ROS = 8,          /* materialise the dense rate_of_spread plane (fire.py:704-708);
                                   costs a dense 8 B/cell pass per step -- parity tests only  */
     SFB_HAS_MAX_TIME = 16,     /* max_time is not None (fire.py:641)                         */
-    SFB_WIDE_CELLS = 32        /* use the 16-bit cell layout even when max_fire_duration <= 30
+    SFB_WIDE_CELLS = 32,       /* use the 16-bit cell layout even when max_fire_duration <= 30
                                   (it is selected automatically above that); tests only      */
+    SFB_SWEEP_LDG = 64         /* stream the state with 128-bit global loads instead of the TMA
+                                  ring (A/B measurements; slab mode always uses it)          */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the

@@ -10,7 +10,7 @@ from .build import LIB
 ABI_VERSION = 1
 
 # sfb_flags
-DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS = 1, 2, 4, 8, 16, 32
+DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS = 0, 1, 2, 3
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")

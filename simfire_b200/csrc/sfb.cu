@@ -44,6 +44,8 @@ struct sfb_sim {
     sfb_params prm;
     DevParams d;
     int cell_bytes;   // 1 or 2
+    int use_tma;      // sweep front end
+    CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int n_sm;
     cudaStream_t stream;
@@ -311,14 +313,19 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
 
     const int wr = 32 * (16 / s->cell_bytes);  // cells per warp row
     d.strips = (d.pitch + wr - 1) / wr;
+    const bool tma = !(prm->flags & SFB_SWEEP_LDG) && prm->slab_total_H == 0;
     int R = prm->rows_per_chunk;
     if (R <= 0) {
         // enough warps to fill the machine a few times over, as few halo rows as possible
-        R = 32;
+        R = tma ? 64 : 32;
         const long long want = (long long)s->n_sm * 64;
-        while (R > 4 && (long long)d.E * d.strips * ((d.H + R - 1) / R) < want) R /= 2;
+        while (R > 8 && (long long)d.E * d.strips * ((d.H + R - 1) / R) < want) R /= 2;
+        if (tma) R -= 2;  // rows_per_chunk + 2 halo rows = whole TMA boxes
     }
-    R = std::max(4, (R + 3) / 4 * 4);
+    if (tma)
+        R = std::max(TMA_BOX_ROWS - 2, (R + 2 + TMA_BOX_ROWS - 1) / TMA_BOX_ROWS * TMA_BOX_ROWS - 2);
+    else
+        R = std::max(4, (R + 3) / 4 * 4);
     d.rows_per_chunk = R;
     d.chunks = (d.H + R - 1) / R;
     d.n_units = (int64_t)d.E * d.chunks * d.strips;
@@ -344,6 +351,30 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         for (size_t i = 0; i < n; ++i) fill[i * s->cell_bytes] = (uint8_t)ST_BURNED;  // little endian
         if ((rc = dmalloc(s, (char**)&d.filler, fill.size()))) return rc;
         CU(cudaMemcpy((void*)d.filler, fill.data(), fill.size(), cudaMemcpyHostToDevice));
+    }
+
+    s->use_tma = !(prm->flags & SFB_SWEEP_LDG) && prm->slab_total_H == 0;
+    if (s->use_tma) {
+        // driver entry point through the runtime: no link-time dependency on libcuda
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled is not available in this driver");
+        const cuuint64_t row_bytes = (cuuint64_t)d.pitch * s->cell_bytes;
+        const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)d.H, (cuuint64_t)d.E};
+        const cuuint64_t strides[2] = {row_bytes, row_bytes * (cuuint64_t)d.H};  // bytes, dims 1 and 2
+        const cuuint32_t box[3] = {TMA_ROW_BYTES / 4, TMA_BOX_ROWS, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d.state, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        CU(cudaFuncSetAttribute(k_sweep_tma<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
+        CU(cudaFuncSetAttribute(k_sweep_tma<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
     }
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
@@ -546,7 +577,14 @@ static int enqueue_step(sfb_sim* s) {
     const DevParams& d = s->d;
     const int par = s->parity;
     if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
-    DISPATCH(s, k_sweep, nblocks(d.n_units, SWEEP_WARPS), SWEEP_WARPS * 32, d, par);
+    if (s->use_tma) {
+        const unsigned grid = nblocks(d.n_units, SWEEP_WARPS);
+        if (s->cell_bytes == 1) k_sweep_tma<uint8_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
+        else k_sweep_tma<uint16_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
+        s->launches_all++;
+    } else {
+        DISPATCH(s, k_sweep_ldg, nblocks(d.n_units, SWEEP_WARPS), SWEEP_WARPS * 32, d, par);
+    }
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
     if (d.keep_ros) {
         k_clear_ros<<<cap_grid(s, (long long)d.E * d.plane, 256), 256, 0, s->stream>>>(d, par);

@@ -30,6 +30,7 @@
 // (fire.py:633) is recovered as (t - 1 - ign) mod M, so the code never has to be
 // rewritten while the sprite burns, and a cell's byte changes exactly twice in its life.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -150,89 +151,63 @@ __device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& 
 }
 
 // ---------------------------------------------------------------------------------------
-// k_sweep: one warp per (env, chunk of rows, strip of 32 x CPL columns).  Each lane streams
-// its CPL-cell segment of every row with one 128-bit load, four rows in flight, keeping a
-// three-row window in registers.  A row is examined cell by cell only if the window holds
-// a sprite code (or, with attenuation, a control line): the window is then staged in
-// shared memory so that the eight neighbours of every cell are plain byte reads.
+// k_sweep: one warp per (env, chunk of rows, strip of 32 x CPL columns).
 //
-// The streaming part is straight-line code: rows outside the grid are read from a row of
-// BURNED filler cells (p.filler) instead of being branched around, and the cells left and
-// right of the strip come from one predicated byte load by lanes 0 and 31.
+// Common part (SweepWarp): the cell-by-cell examination of one row, entered only if the
+// three-row window around it holds a sprite code (or, with attenuation, a control line).
+// The window lives in shared memory as rows of RS cells: CPL pad | 32*CPL cells | CPL pad,
+// so the eight neighbours of every cell are plain byte reads.
+//
+// Two streaming front ends feed it:
+//   k_sweep_tma  TMA (cp.async.bulk.tensor) boxes of 8 rows x 544 B land in a per-warp
+//                shared-memory ring, completion on mbarriers, 2 boxes in flight per warp;
+//                out-of-grid cells are zero-filled by the TMA unit.  Default.
+//   k_sweep_ldg  128-bit global loads into a register window, four rows in flight; rows
+//                outside the grid are read from a row of BURNED filler cells.
 // ---------------------------------------------------------------------------------------
 constexpr int SWEEP_WARPS = 4;
 constexpr int WQ_CAP = 96;  // >= 64: a flush is forced whenever fewer than 32 slots are free
 
-struct RowRegs {
-    uint4 v;     // this lane's CPL cells
-    uint32_t h;  // lane 0: cell left of the strip, lane 31: cell right of it
-    uint32_t b;  // ballot: lanes whose segment needs a look
-};
-
 template <typename CellT>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, const int par) {
+struct SweepWarp {
     using C = Cell<CellT>;
-    constexpr int CPL = C::CPL;
-    constexpr int WR = 32 * CPL;        // cells per warp row
-    constexpr int RS = WR + 2 * CPL;    // staged row: CPL pad | WR cells | CPL pad (16-B aligned)
-    constexpr int SEG_PER_GROUP = 32 / CPL;
-    constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
-    __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
-    __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
+    static constexpr int CPL = C::CPL;
+    static constexpr int WR = 32 * CPL;      // cells per warp row
+    static constexpr int RS = WR + 2 * CPL;  // staged row, in cells (544 bytes)
+    static constexpr int SEG_PER_GROUP = 32 / CPL;
+    static constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long unit = (long long)blockIdx.x * SWEEP_WARPS + warp;
-    if (unit >= p.n_units) return;
-    const int strip = (int)(unit % p.strips);
-    const long long u2 = unit / p.strips;
-    const int chunk = (int)(u2 % p.chunks);
-    const int env = (int)(u2 / p.chunks);
-    EnvMeta* const mp = p.meta + (long long)par * p.E + env;
-    if (!mp->running) return;
-    const bool spread = !mp->time_quit;
-    const int tm1 = (mp->t - 1) % C::M;
-    const int max_dur = p.max_dur;
-    const int H = p.H, pitch = p.pitch;
-    const bool diagonal = p.diagonal != 0, attenuate = p.attenuate != 0;
-
-    CellT* const state = reinterpret_cast<CellT*>(p.state);
-    const long long env_off = (long long)env * p.plane;
-    const CellT* const envbase = state + env_off;
-    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
-    const int x0 = strip * WR;
-    const int xl = x0 + lane * CPL;
-    const int y_begin = chunk * p.rows_per_chunk;
-    const int y_end = min(y_begin + p.rows_per_chunk, H);
-    const uint32_t look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
-    const uint32_t hmask = look_mask & CELL_ALL;
-    const bool in_x = xl < pitch;
-    // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
-    const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
-    const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
-    CellT(*sm)[RS] = sm_all[warp];
-    unsigned long long* const wq = wq_all[warp];
+    const DevParams& p;
+    int par, lane, env, x0, y_end, tm1, max_dur;
+    bool spread, diagonal, attenuate;
+    long long env_off;
+    uint32_t look_mask;
+    unsigned long long* wq;
     int wcount = 0;  // warp-uniform
+    int f_live = 0, f_cand = 0;
 
-    // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
-    auto edge_row = [&](int y) -> const CellT* {
-        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + env_off;
-        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + env_off;
-        return filler;
-    };
-    auto issue = [&](const CellT* rowp, RowRegs& r) {
-        r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
-        r.h = ST_BURNED;
-        if (in_x) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
-        if (hpred) r.h = rowp[hoff];
-    };
-    auto finish = [&](RowRegs& r) {
-        const uint32_t a = ((r.v.x | r.v.y | r.v.z | r.v.w) & look_mask) | (r.h & hmask);
-        r.b = __ballot_sync(0xffffffffu, a != 0);
-    };
+    __device__ __forceinline__ SweepWarp(const DevParams& p_, int par_, int lane_, int env_, int strip, int chunk,
+                                         const EnvMeta& m, unsigned long long* wq_)
+        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_) {
+        x0 = strip * WR;
+        y_end = min((chunk + 1) * p.rows_per_chunk, p.H);
+        tm1 = (m.t - 1) % C::M;
+        max_dur = p.max_dur;
+        spread = !m.time_quit;
+        diagonal = p.diagonal != 0;
+        attenuate = p.attenuate != 0;
+        env_off = (long long)env * p.plane;
+        look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
+    }
+
+    // does this lane's segment (plus, for lanes 0 / 31, the cell outside the strip) need a look?
+    __device__ __forceinline__ bool seg_needs_look(const uint4& v, uint32_t halo_cell) const {
+        return ((((v.x | v.y) | (v.z | v.w)) & look_mask) | (halo_cell & look_mask & CELL_ALL)) != 0;
+    }
 
     // one global atomic per flush instead of one per push: the queue tail is a single
     // address and L2 serialises atomics on it
-    auto flush = [&]() {
+    __device__ __forceinline__ void flush() {
         if (wcount == 0) return;
         __syncwarp();
         unsigned long long base = 0;
@@ -245,37 +220,58 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
         }
         wcount = 0;
         __syncwarp();
-    };
+    }
 
-    int f_live = 0, f_cand = 0;
+    // sort key of a cell as a fire source: duration * 8 if it carries a live sprite, else NO_SRC
+    static constexpr int NO_SRC = 1 << 20;
+    __device__ __forceinline__ int source_key(int c) const {
+        const int code = c >> 3;
+        const int a = sprite_age<CellT>(code, tm1);
+        return (code != 0 && a < max_dur) ? a * 8 : NO_SRC;
+    }
 
-    auto process_row = [&](int y, const RowRegs& rp, const RowRegs& rc, const RowRegs& rn) {
-        const uint32_t act = rp.b | rc.b | rn.b;
-        if (act == 0 || y >= y_end) return;  // warp-uniform
-        __syncwarp();
-        *reinterpret_cast<uint4*>(&sm[0][CPL + lane * CPL]) = rp.v;
-        *reinterpret_cast<uint4*>(&sm[1][CPL + lane * CPL]) = rc.v;
-        *reinterpret_cast<uint4*>(&sm[2][CPL + lane * CPL]) = rn.v;
-        if (lane == 0) { sm[0][CPL - 1] = (CellT)rp.h; sm[1][CPL - 1] = (CellT)rc.h; sm[2][CPL - 1] = (CellT)rn.h; }
-        if (lane == 31) { sm[0][CPL + WR] = (CellT)rp.h; sm[1][CPL + WR] = (CellT)rc.h; sm[2][CPL + WR] = (CellT)rn.h; }
-        __syncwarp();
-        // segments whose own or adjacent segment needs a look -> 32-cell groups to visit
-        const uint32_t near = act | (act << 1) | (act >> 1);
+    // rp / rc / rn: rows y-1, y, y+1 in shared memory (RS cells each); act: ballot of the
+    // lanes whose segment needs a look in any of the three rows.
+    //
+    // The row is visited in groups of 30 cells: lane l of group g holds column 30g + l - 1 of
+    // the three rows, so lanes 1..30 find all eight neighbours in the adjacent lanes (lanes 0
+    // and 31 only lend their cells).  The pair the reference writes last is the one whose
+    // source has the largest (ignition step, y, x) (fire.py:704-705 + sprite-list order):
+    // smallest duration first, then south before north and east before west.  Folding that
+    // rank into the low bits of the key turns the selection into a warp-shuffle min.
+    __device__ __forceinline__ void detail_row(int y, const CellT* rp, const CellT* rc, const CellT* rn, uint32_t act) {
+        constexpr int GW = 30, NG = (WR + GW - 1) / GW;
+        CellT* const state = reinterpret_cast<CellT*>(p.state);
         uint32_t groups = 0;
 #pragma unroll
-        for (int g = 0; g < WR / 32; ++g)
-            if (near & (((1u << SEG_PER_GROUP) - 1u) << (g * SEG_PER_GROUP))) groups |= 1u << g;
+        for (int g = 0; g < NG; ++g) {
+            // segments overlapped by columns [30g - 1, 30g + 30]; the pads count as segments 0 / 31
+            const int lo = (GW * g - 1) < 0 ? 0 : (GW * g - 1) / CPL;
+            const int hi = (GW * g + GW) / CPL > 31 ? 31 : (GW * g + GW) / CPL;
+            const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            if (act & m) groups |= 1u << g;
+        }
         while (groups) {  // warp-uniform
             const int g = __ffs(groups) - 1;
             groups &= groups - 1;
-            const int xi = CPL + g * 32 + lane;  // index in the staged row
-            const int x = x0 + g * 32 + lane;
-            const int c = sm[1][xi];
-            int s = c & 7;
-            const int code = c >> 3;
-            const long long idx = env_off + (long long)y * pitch + x;
-            if (code) {
-                if (sprite_age<CellT>(code, tm1) >= max_dur) {  // fire.py:116-161
+            const int col = min(g * GW + lane - 1, WR);  // staged column -1 .. WR (pads included)
+            const int xi = CPL + col;
+            const int cp = rp[xi], cc = rc[xi], cn = rn[xi];
+            if (!__any_sync(0xffffffffu, ((cp | cc | cn) & (int)(look_mask & CELL_ALL)) != 0)) continue;
+            const int kp = source_key(cp), kc = source_key(cc), kn = source_key(cn);
+            // keys of the eight neighbours, rank in the low three bits (0 = written last)
+            int best = min(__shfl_down_sync(0xffffffffu, kc, 1) + 3, __shfl_up_sync(0xffffffffu, kc, 1) + 4);
+            best = min(best, min(kn + 1, kp + 6));
+            if (diagonal) {
+                best = min(best, min(__shfl_down_sync(0xffffffffu, kn, 1) + 0, __shfl_up_sync(0xffffffffu, kn, 1) + 2));
+                best = min(best, min(__shfl_down_sync(0xffffffffu, kp, 1) + 5, __shfl_up_sync(0xffffffffu, kp, 1) + 7));
+            }
+            const int x = x0 + col;
+            const bool owner = lane >= 1 && lane <= GW && col < WR && x < p.W;
+            int s = cc & 7;
+            const long long idx = env_off + (long long)y * p.pitch + x;
+            if (owner && (cc >> 3) != 0) {
+                if (kc == NO_SRC) {  // duration reached max_fire_duration (fire.py:116-161)
                     state[idx] = (CellT)ST_BURNED;
                     s = ST_BURNED;
                 } else {
@@ -284,26 +280,9 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
             }
             bool push = false;
             int dir = DIR_NONE;
-            if (spread && ignitable(s)) {
-                // the pair written last is the one whose source has the largest
-                // (ignition step, y, x): smallest age, then the order below
-                int best = max_dur;
-                auto look = [&](int row, int dx, int k) {
-                    const int nc = (int)sm[row][xi + dx] >> 3;
-                    if (nc) {
-                        const int a = sprite_age<CellT>(nc, tm1);
-                        if (a < best) { best = a; dir = k; }
-                    }
-                };
-                if (diagonal) look(2, +1, 5);
-                look(2, 0, 6);
-                if (diagonal) look(2, -1, 7);
-                look(1, +1, 4);
-                look(1, -1, 0);
-                if (diagonal) look(0, +1, 3);
-                look(0, 0, 2);
-                if (diagonal) look(0, -1, 1);
-                if (dir != DIR_NONE) {
+            if (owner && spread && ignitable(s)) {
+                if (best < NO_SRC) {
+                    dir = (0x12304765u >> ((best & 7) * 4)) & 0xF;  // rank -> direction of fire.py:211-221
                     f_cand = 1;
                     push = true;
                 } else if ((s & ST_LINE_BIT) && attenuate) {
@@ -317,6 +296,220 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
                 if (wcount > WQ_CAP - 32) flush();
             }
         }
+    }
+
+    __device__ __forceinline__ void finish(EnvMeta* mp) {
+        flush();
+        f_live = __any_sync(0xffffffffu, f_live);
+        f_cand = __any_sync(0xffffffffu, f_cand);
+        if (lane == 0) {
+            if (f_live) mp->any_live = 1;
+            if (f_cand) mp->any_cand = 1;
+        }
+    }
+};
+
+__device__ __forceinline__ bool decode_unit(const DevParams& p, long long unit, int& strip, int& chunk, int& env) {
+    if (unit >= p.n_units) return false;
+    strip = (int)(unit % p.strips);
+    const long long u2 = unit / p.strips;
+    chunk = (int)(u2 % p.chunks);
+    env = (int)(u2 / p.chunks);
+    return true;
+}
+
+// ---- front end 1: TMA ring --------------------------------------------------------------
+constexpr int TMA_BOX_ROWS = 8;                      // rows per TMA box
+constexpr int TMA_STAGES = 4;                        // boxes in the per-warp ring
+constexpr int TMA_ROW_BYTES = 544;                   // 16 B pad | 512 B | 16 B pad
+constexpr int TMA_BOX_BYTES = TMA_BOX_ROWS * TMA_ROW_BYTES;
+constexpr int TMA_RING_ROWS = TMA_BOX_ROWS * TMA_STAGES;
+constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128;  // ring | work items | mbarriers
+static_assert(TMA_WARP_SMEM % 128 == 0 && TMA_BOX_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+constexpr int TMA_BLOCK_SMEM = SWEEP_WARPS * TMA_WARP_SMEM + 128;              // + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+// The tensor map describes the state plane as uint32 [E][H][pitch_bytes / 4]; a box is
+// 136 x 8 x 1 elements = 8 rows of 544 bytes starting 16 bytes left of the strip.
+template <typename CellT>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const int par) {
+    using SW = SweepWarp<CellT>;
+    constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
+    constexpr int B = TMA_BOX_ROWS, NR = TMA_RING_ROWS;
+    static_assert(RS * sizeof(CellT) == TMA_ROW_BYTES, "row bytes");
+    extern __shared__ unsigned char smem_raw[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int strip, chunk, env;
+    if (!decode_unit(p, (long long)blockIdx.x * SWEEP_WARPS + warp, strip, chunk, env)) return;
+    EnvMeta* const mp = p.meta + (long long)par * p.E + env;
+    const EnvMeta m = *mp;
+    if (!m.running) return;
+
+    unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127) + warp * TMA_WARP_SMEM;
+    CellT* const ring = reinterpret_cast<CellT*>(base);
+    unsigned long long* const wq = reinterpret_cast<unsigned long long*>(base + NR * TMA_ROW_BYTES);
+    const uint32_t bar0 = smem_u32(base + NR * TMA_ROW_BYTES + WQ_CAP * 8);
+    const uint32_t ring_u32 = smem_u32(ring);
+
+    SW sw(p, par, lane, env, strip, chunk, m, wq);
+    const int y_begin = chunk * p.rows_per_chunk;
+    const int n_rows = sw.y_end - y_begin;           // rows this unit owns
+    const int n_box = (n_rows + 2 + B - 1) / B;      // local row j <-> grid row y_begin - 1 + j
+    const int c0 = (sw.x0 - CPL) * (int)sizeof(CellT) / 4;
+
+    if (lane == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue_box = [&](int k) {  // lane 0 only
+        const uint32_t bar = bar0 + 8 * (k % TMA_STAGES);
+        mbar_expect_tx(bar, TMA_BOX_BYTES);
+        tma_load_3d(ring_u32 + (k % TMA_STAGES) * TMA_BOX_BYTES, &tmap, c0, y_begin - 1 + k * B, env, bar);
+    };
+    if (lane == 0)
+        for (int k = 0; k < min(n_box, TMA_STAGES - 1); ++k) issue_box(k);
+
+    // bit i of `nz`: local row (k*B - 2 + i) holds something to look at; two rows carried over
+    uint32_t carry = 0;
+    for (int k = 0; k < n_box; ++k) {
+        mbar_wait(bar0 + 8 * (k % TMA_STAGES), (k / TMA_STAGES) & 1);
+        const CellT* box = ring + (k % TMA_STAGES) * (B * RS);
+        uint32_t nz = carry;
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(box + i * RS + CPL + lane * CPL);
+            const bool a = (((v.x | v.y) | (v.z | v.w)) & sw.look_mask) != 0;
+            if (__any_sync(0xffffffffu, a)) nz |= 4u << i;
+        }
+        {   // cells just outside the strip: lanes 0-7 the left pad of row `lane`, 8-15 the right pad of row lane-8
+            uint32_t hw = 0;
+            if (lane < 2 * B) {
+                const unsigned char* rowb = reinterpret_cast<const unsigned char*>(box + (lane & (B - 1)) * RS);
+                hw = *reinterpret_cast<const uint32_t*>(rowb + (lane < B ? 12 : TMA_ROW_BYTES - 16));
+                // only the adjacent cell counts: the last cell of the left pad, the first of the right pad
+                hw = lane < B ? (hw >> (32 - 8 * (int)sizeof(CellT))) : (hw & SW::CELL_ALL);
+            }
+            const uint32_t hb = __ballot_sync(0xffffffffu, (hw & sw.look_mask & SW::CELL_ALL) != 0);
+            nz |= ((hb | (hb >> B)) & ((1u << B) - 1u)) << 2;
+        }
+        carry = nz >> B;
+        // local row j = k*B - 1 + i is complete once box k is here (its row j+1 = k*B + i), i = 0..B-1
+        uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
+        while (rows) {  // warp-uniform
+            const int i = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int j = k * B - 1 + i;
+            if (j < 1 || j > n_rows) continue;
+            const CellT* rp = ring + ((j - 1) % NR) * RS;
+            const CellT* rc = ring + (j % NR) * RS;
+            const CellT* rn = ring + ((j + 1) % NR) * RS;
+            const uint4 vp = *reinterpret_cast<const uint4*>(rp + CPL + lane * CPL);
+            const uint4 vc = *reinterpret_cast<const uint4*>(rc + CPL + lane * CPL);
+            const uint4 vn = *reinterpret_cast<const uint4*>(rn + CPL + lane * CPL);
+            uint32_t hcell = 0;
+            if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
+            if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
+            const uint4 vo = make_uint4(vp.x | vc.x | vn.x, vp.y | vc.y | vn.y, vp.z | vc.z | vn.z, vp.w | vc.w | vn.w);
+            const uint32_t act = __ballot_sync(0xffffffffu, sw.seg_needs_look(vo, hcell));
+            sw.detail_row(y_begin - 1 + j, rp, rc, rn, act);
+        }
+        // box k-1 is dead now (its last row was the `prev` of this box's first row): refill its slot
+        __syncwarp();
+        if (lane == 0 && k + TMA_STAGES - 1 < n_box) issue_box(k + TMA_STAGES - 1);
+    }
+    sw.finish(mp);
+}
+
+// ---- front end 2: register window -------------------------------------------------------
+struct RowRegs {
+    uint4 v;     // this lane's CPL cells
+    uint32_t h;  // lane 0: cell left of the strip, lane 31: cell right of it
+    uint32_t b;  // ballot: lanes whose segment needs a look
+};
+
+template <typename CellT>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_ldg(const DevParams p, const int par) {
+    using SW = SweepWarp<CellT>;
+    using C = Cell<CellT>;
+    constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
+    __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
+    __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int strip, chunk, env;
+    if (!decode_unit(p, (long long)blockIdx.x * SWEEP_WARPS + warp, strip, chunk, env)) return;
+    EnvMeta* const mp = p.meta + (long long)par * p.E + env;
+    const EnvMeta m = *mp;
+    if (!m.running) return;
+    SW sw(p, par, lane, env, strip, chunk, m, wq_all[warp]);
+    const int H = p.H, pitch = p.pitch;
+
+    const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + sw.env_off;
+    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
+    const int x0 = sw.x0;
+    const int xl = x0 + lane * CPL;
+    const int y_begin = chunk * p.rows_per_chunk;
+    const int y_end = sw.y_end;
+    const bool in_x = xl < pitch;
+    // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
+    const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
+    const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
+    CellT(*sm)[RS] = sm_all[warp];
+
+    // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
+    auto edge_row = [&](int y) -> const CellT* {
+        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + sw.env_off;
+        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + sw.env_off;
+        return filler;
+    };
+    auto issue = [&](const CellT* rowp, RowRegs& r) {
+        r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+        r.h = ST_BURNED;
+        if (in_x) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
+        if (hpred) r.h = rowp[hoff];
+    };
+    auto finish = [&](RowRegs& r) { r.b = __ballot_sync(0xffffffffu, sw.seg_needs_look(r.v, r.h)); };
+
+    auto process_row = [&](int y, const RowRegs& rp, const RowRegs& rc, const RowRegs& rn) {
+        const uint32_t act = rp.b | rc.b | rn.b;
+        if (act == 0 || y >= y_end) return;  // warp-uniform
+        __syncwarp();
+        *reinterpret_cast<uint4*>(&sm[0][CPL + lane * CPL]) = rp.v;
+        *reinterpret_cast<uint4*>(&sm[1][CPL + lane * CPL]) = rc.v;
+        *reinterpret_cast<uint4*>(&sm[2][CPL + lane * CPL]) = rn.v;
+        if (lane == 0) { sm[0][CPL - 1] = (CellT)rp.h; sm[1][CPL - 1] = (CellT)rc.h; sm[2][CPL - 1] = (CellT)rn.h; }
+        if (lane == 31) { sm[0][CPL + WR] = (CellT)rp.h; sm[1][CPL + WR] = (CellT)rc.h; sm[2][CPL + WR] = (CellT)rn.h; }
+        __syncwarp();
+        sw.detail_row(y, sm[0], sm[1], sm[2], act);
     };
 
     // rolling three-row window; the four loads of a batch are issued before any is used
@@ -353,13 +546,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevParams p, c
         r1 = r5;
         rowp = q4;
     }
-    flush();
-    f_live = __any_sync(0xffffffffu, f_live);
-    f_cand = __any_sync(0xffffffffu, f_cand);
-    if (lane == 0) {
-        if (f_live) mp->any_live = 1;
-        if (f_cand) mp->any_cand = 1;
-    }
+    sw.finish(mp);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ class FireEngine:
         rows_per_chunk: int = 0,
         queue_capacity: int = 0,
         wide_cells: bool = False,
+        sweep_ldg: bool = False,
     ) -> None:
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -67,6 +68,7 @@ class FireEngine:
         flags |= _lib.KEEP_ROS if keep_ros else 0
         flags |= _lib.HAS_MAX_TIME if max_time is not None else 0
         flags |= _lib.WIDE_CELLS if wide_cells else 0
+        flags |= _lib.SWEEP_LDG if sweep_ldg else 0
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,

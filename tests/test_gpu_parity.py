@@ -103,13 +103,15 @@ def test_golden_trajectory(name):
 
 @pytest.mark.parametrize("name", ["scenario_a_models_diag_att", "scenario_d_midrun_mitigation",
                                   "scenario_b_models_4nbr_noatt", "scenario_f_max_time"])  # fmt: skip
-@pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64"])
+@pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8"])
 def test_golden_trajectory_variants(name, variant):
-    """The 16-bit cell layout, the dense fallback taken on queue overflow and other chunk
-    heights must give the same trajectories."""
+    """The 16-bit cell layout, the dense fallback taken on queue overflow, other chunk
+    heights and the non-TMA streaming front end must give the same trajectories."""
     sc = load_scenario(name)
     kw = {"wide_cells": dict(wide_cells=True), "queue_overflow": dict(queue_capacity=3),
-          "rows4": dict(rows_per_chunk=4), "rows64": dict(rows_per_chunk=64)}[variant]  # fmt: skip
+          "rows4": dict(rows_per_chunk=4), "rows64": dict(rows_per_chunk=64), "ldg": dict(sweep_ldg=True),
+          "ldg_wide": dict(sweep_ldg=True, wide_cells=True),
+          "ldg_rows8": dict(sweep_ldg=True, rows_per_chunk=8)}[variant]  # fmt: skip
     with engine_for(sc, **kw) as eng:
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
