@@ -13,7 +13,7 @@ DEPS = [
     os.path.join(PKG, "csrc", "sfb_rothermel.cuh"),
     os.path.join(os.path.dirname(PKG), "include", "simfire_b200.h"),
 ]
-LIB = os.path.join(PKG, "libsimfire_b200.so")
+LIB = os.environ.get("SFB_LIB") or os.path.join(PKG, "libsimfire_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,7 +42,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/sfb.cu -> simfire_b200/libsimfire_b200.so; returns the path."""
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *os.environ.get("SFB_NVCC_EXTRA", "").split(), "-o", LIB, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

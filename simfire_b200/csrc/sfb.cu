@@ -45,6 +45,7 @@ struct sfb_sim {
     DevParams d;
     int cell_bytes;   // 1 or 2
     int use_tma;      // sweep front end
+    int sweep_blocks; // persistent grid of the sweep kernel
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int n_sm;
@@ -273,6 +274,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.queue);
     cudaFree(s->d.qcount);
     cudaFree(s->d.overflow);
+    cudaFree(s->d.unit_next);
     cudaFree((void*)s->d.filler);
     cudaFree(s->stage);
     cudaFree(s->obs);
@@ -345,6 +347,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
     if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
     if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
+    if ((rc = dmalloc(s, &d.unit_next, 2 * sizeof(unsigned long long)))) return rc;
+    CU(cudaMemsetAsync(d.unit_next, 0, 2 * sizeof(unsigned long long), s->stream));
     {
         const size_t n = (size_t)d.pitch + 32;
         std::vector<uint8_t> fill(n * s->cell_bytes, 0);
@@ -375,6 +379,24 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
         CU(cudaFuncSetAttribute(k_sweep_tma<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
         CU(cudaFuncSetAttribute(k_sweep_tma<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
+    }
+
+    {   // persistent sweep grid: as many blocks as fit on the device, never more than there are units
+        int per_sm = 0;
+        if (s->use_tma) {
+            if (s->cell_bytes == 1)
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_tma<uint8_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
+            else
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_tma<uint16_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
+        } else {
+            if (s->cell_bytes == 1)
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ldg<uint8_t>, SWEEP_WARPS * 32, 0));
+            else
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ldg<uint16_t>, SWEEP_WARPS * 32, 0));
+        }
+        if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: sweep kernel does not fit on an SM");
+        const long long need = (d.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
+        s->sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
     }
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
@@ -578,12 +600,12 @@ static int enqueue_step(sfb_sim* s) {
     const int par = s->parity;
     if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
     if (s->use_tma) {
-        const unsigned grid = nblocks(d.n_units, SWEEP_WARPS);
+        const unsigned grid = (unsigned)s->sweep_blocks;
         if (s->cell_bytes == 1) k_sweep_tma<uint8_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
         else k_sweep_tma<uint16_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
         s->launches_all++;
     } else {
-        DISPATCH(s, k_sweep_ldg, nblocks(d.n_units, SWEEP_WARPS), SWEEP_WARPS * 32, d, par);
+        DISPATCH(s, k_sweep_ldg, (unsigned)s->sweep_blocks, SWEEP_WARPS * 32, d, par);
     }
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
     if (d.keep_ros) {

@@ -73,6 +73,7 @@ struct DevParams {
     unsigned long long* queue;  // [qcap] work items
     unsigned long long* qcount; // [2]
     int32_t* overflow;          // [2]
+    unsigned long long* unit_next;  // [2] next sweep unit to hand out (dynamic scheduling)
     // slab mode: rows -1 and H of this slab live in a neighbour slab (peer device memory)
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
@@ -165,7 +166,13 @@ __device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& 
 //   k_sweep_ldg  128-bit global loads into a register window, four rows in flight; rows
 //                outside the grid are read from a row of BURNED filler cells.
 // ---------------------------------------------------------------------------------------
-constexpr int SWEEP_WARPS = 4;
+#ifndef SFB_SWEEP_WARPS
+#define SFB_SWEEP_WARPS 4
+#endif
+#ifndef SFB_LDG_MIN_BLOCKS
+#define SFB_LDG_MIN_BLOCKS 6
+#endif
+constexpr int SWEEP_WARPS = SFB_SWEEP_WARPS;
 constexpr int WQ_CAP = 96;  // >= 64: a flush is forced whenever fewer than 32 slots are free
 
 template <typename CellT>
@@ -309,8 +316,14 @@ struct SweepWarp {
     }
 };
 
-__device__ __forceinline__ bool decode_unit(const DevParams& p, long long unit, int& strip, int& chunk, int& env) {
-    if (unit >= p.n_units) return false;
+// Warps are persistent: each pulls the next (env, chunk, strip) unit from a device counter,
+// so a warp that drew a quiet piece of map immediately takes another one instead of idling
+// until its block retires.
+__device__ __forceinline__ bool next_unit(const DevParams& p, int par, int lane, int& strip, int& chunk, int& env) {
+    unsigned long long unit = 0;
+    if (lane == 0) unit = atomicAdd(p.unit_next + par, 1ULL);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= (unsigned long long)p.n_units) return false;
     strip = (int)(unit % p.strips);
     const long long u2 = unit / p.strips;
     chunk = (int)(u2 % p.chunks);
@@ -320,7 +333,10 @@ __device__ __forceinline__ bool decode_unit(const DevParams& p, long long unit, 
 
 // ---- front end 1: TMA ring --------------------------------------------------------------
 constexpr int TMA_BOX_ROWS = 8;                      // rows per TMA box
-constexpr int TMA_STAGES = 4;                        // boxes in the per-warp ring
+#ifndef SFB_TMA_STAGES
+#define SFB_TMA_STAGES 3
+#endif
+constexpr int TMA_STAGES = SFB_TMA_STAGES;           // boxes in the per-warp ring
 constexpr int TMA_ROW_BYTES = 544;                   // 16 B pad | 512 B | 16 B pad
 constexpr int TMA_BOX_BYTES = TMA_BOX_ROWS * TMA_ROW_BYTES;
 constexpr int TMA_RING_ROWS = TMA_BOX_ROWS * TMA_STAGES;
@@ -366,23 +382,11 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
     extern __shared__ unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int strip, chunk, env;
-    if (!decode_unit(p, (long long)blockIdx.x * SWEEP_WARPS + warp, strip, chunk, env)) return;
-    EnvMeta* const mp = p.meta + (long long)par * p.E + env;
-    const EnvMeta m = *mp;
-    if (!m.running) return;
-
     unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127) + warp * TMA_WARP_SMEM;
     CellT* const ring = reinterpret_cast<CellT*>(base);
     unsigned long long* const wq = reinterpret_cast<unsigned long long*>(base + NR * TMA_ROW_BYTES);
     const uint32_t bar0 = smem_u32(base + NR * TMA_ROW_BYTES + WQ_CAP * 8);
     const uint32_t ring_u32 = smem_u32(ring);
-
-    SW sw(p, par, lane, env, strip, chunk, m, wq);
-    const int y_begin = chunk * p.rows_per_chunk;
-    const int n_rows = sw.y_end - y_begin;           // rows this unit owns
-    const int n_box = (n_rows + 2 + B - 1) / B;      // local row j <-> grid row y_begin - 1 + j
-    const int c0 = (sw.x0 - CPL) * (int)sizeof(CellT) / 4;
 
     if (lane == 0) {
         for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -390,63 +394,82 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    auto issue_box = [&](int k) {  // lane 0 only
-        const uint32_t bar = bar0 + 8 * (k % TMA_STAGES);
-        mbar_expect_tx(bar, TMA_BOX_BYTES);
-        tma_load_3d(ring_u32 + (k % TMA_STAGES) * TMA_BOX_BYTES, &tmap, c0, y_begin - 1 + k * B, env, bar);
-    };
-    if (lane == 0)
-        for (int k = 0; k < min(n_box, TMA_STAGES - 1); ++k) issue_box(k);
+    uint32_t boxes_done = 0;  // boxes consumed by this warp so far: fixes ring slot and mbarrier phase
 
-    // bit i of `nz`: local row (k*B - 2 + i) holds something to look at; two rows carried over
-    uint32_t carry = 0;
-    for (int k = 0; k < n_box; ++k) {
-        mbar_wait(bar0 + 8 * (k % TMA_STAGES), (k / TMA_STAGES) & 1);
-        const CellT* box = ring + (k % TMA_STAGES) * (B * RS);
-        uint32_t nz = carry;
+    int strip, chunk, env;
+    while (next_unit(p, par, lane, strip, chunk, env)) {
+        EnvMeta* const mp = p.meta + (long long)par * p.E + env;
+        const EnvMeta m = *mp;
+        if (!m.running) continue;
+        SW sw(p, par, lane, env, strip, chunk, m, wq);
+        const int y_begin = chunk * p.rows_per_chunk;
+        const int n_rows = sw.y_end - y_begin;           // rows this unit owns
+        const int n_box = (n_rows + 2 + B - 1) / B;      // local row j <-> grid row y_begin - 1 + j
+        const int c0 = (sw.x0 - CPL) * (int)sizeof(CellT) / 4;
+        const uint32_t kb = boxes_done;                  // global index of this unit's box 0
+        auto slot_of_row = [&](int j) { return (int)((kb * B + (uint32_t)j) % NR); };
+
+        auto issue_box = [&](int k) {  // lane 0 only
+            const uint32_t st = (kb + k) % TMA_STAGES;
+            mbar_expect_tx(bar0 + 8 * st, TMA_BOX_BYTES);
+            tma_load_3d(ring_u32 + st * TMA_BOX_BYTES, &tmap, c0, y_begin - 1 + k * B, env, bar0 + 8 * st);
+        };
+        __syncwarp();  // every lane is done with the previous unit's rows
+        if (lane == 0)
+            for (int k = 0; k < min(n_box, TMA_STAGES - 1); ++k) issue_box(k);
+
+        // bit i of `nz`: local row (k*B - 2 + i) holds something to look at; two rows carried over
+        uint32_t carry = 0;
+        for (int k = 0; k < n_box; ++k) {
+            const uint32_t K = kb + k;
+            mbar_wait(bar0 + 8 * (K % TMA_STAGES), (K / TMA_STAGES) & 1);
+            const CellT* box = ring + (K % TMA_STAGES) * (B * RS);
+            uint32_t nz = carry;
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const uint4 v = *reinterpret_cast<const uint4*>(box + i * RS + CPL + lane * CPL);
-            const bool a = (((v.x | v.y) | (v.z | v.w)) & sw.look_mask) != 0;
-            if (__any_sync(0xffffffffu, a)) nz |= 4u << i;
-        }
-        {   // cells just outside the strip: lanes 0-7 the left pad of row `lane`, 8-15 the right pad of row lane-8
-            uint32_t hw = 0;
-            if (lane < 2 * B) {
-                const unsigned char* rowb = reinterpret_cast<const unsigned char*>(box + (lane & (B - 1)) * RS);
-                hw = *reinterpret_cast<const uint32_t*>(rowb + (lane < B ? 12 : TMA_ROW_BYTES - 16));
-                // only the adjacent cell counts: the last cell of the left pad, the first of the right pad
-                hw = lane < B ? (hw >> (32 - 8 * (int)sizeof(CellT))) : (hw & SW::CELL_ALL);
+            for (int i = 0; i < B; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(box + i * RS + CPL + lane * CPL);
+                const bool a = (((v.x | v.y) | (v.z | v.w)) & sw.look_mask) != 0;
+                if (__any_sync(0xffffffffu, a)) nz |= 4u << i;
             }
-            const uint32_t hb = __ballot_sync(0xffffffffu, (hw & sw.look_mask & SW::CELL_ALL) != 0);
-            nz |= ((hb | (hb >> B)) & ((1u << B) - 1u)) << 2;
+            {   // cells just outside the strip: lanes 0-7 the left pad of row `lane`, 8-15 the right pad of row lane-8
+                uint32_t hw = 0;
+                if (lane < 2 * B) {
+                    const unsigned char* rowb = reinterpret_cast<const unsigned char*>(box + (lane & (B - 1)) * RS);
+                    hw = *reinterpret_cast<const uint32_t*>(rowb + (lane < B ? 12 : TMA_ROW_BYTES - 16));
+                    // only the adjacent cell counts: the last cell of the left pad, the first of the right pad
+                    hw = lane < B ? (hw >> (32 - 8 * (int)sizeof(CellT))) : (hw & SW::CELL_ALL);
+                }
+                const uint32_t hb = __ballot_sync(0xffffffffu, (hw & sw.look_mask & SW::CELL_ALL) != 0);
+                nz |= ((hb | (hb >> B)) & ((1u << B) - 1u)) << 2;
+            }
+            carry = nz >> B;
+            // local row j = k*B - 1 + i is complete once box k is here (its row j+1 = k*B + i), i = 0..B-1
+            uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
+            while (rows) {  // warp-uniform
+                const int i = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int j = k * B - 1 + i;
+                if (j < 1 || j > n_rows) continue;
+                const CellT* rp = ring + slot_of_row(j - 1) * RS;
+                const CellT* rc = ring + slot_of_row(j) * RS;
+                const CellT* rn = ring + slot_of_row(j + 1) * RS;
+                const uint4 vp = *reinterpret_cast<const uint4*>(rp + CPL + lane * CPL);
+                const uint4 vc = *reinterpret_cast<const uint4*>(rc + CPL + lane * CPL);
+                const uint4 vn = *reinterpret_cast<const uint4*>(rn + CPL + lane * CPL);
+                uint32_t hcell = 0;
+                if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
+                if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
+                const uint4 vo = make_uint4(vp.x | vc.x | vn.x, vp.y | vc.y | vn.y, vp.z | vc.z | vn.z, vp.w | vc.w | vn.w);
+                const uint32_t act = __ballot_sync(0xffffffffu, sw.seg_needs_look(vo, hcell));
+                sw.detail_row(y_begin - 1 + j, rp, rc, rn, act);
+            }
+            // box k-1 is dead now (its last row was the `prev` of this box's first row): refill its slot
+            __syncwarp();
+            if (lane == 0 && k + TMA_STAGES - 1 < n_box) issue_box(k + TMA_STAGES - 1);
         }
-        carry = nz >> B;
-        // local row j = k*B - 1 + i is complete once box k is here (its row j+1 = k*B + i), i = 0..B-1
-        uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
-        while (rows) {  // warp-uniform
-            const int i = __ffs(rows) - 1;
-            rows &= rows - 1;
-            const int j = k * B - 1 + i;
-            if (j < 1 || j > n_rows) continue;
-            const CellT* rp = ring + ((j - 1) % NR) * RS;
-            const CellT* rc = ring + (j % NR) * RS;
-            const CellT* rn = ring + ((j + 1) % NR) * RS;
-            const uint4 vp = *reinterpret_cast<const uint4*>(rp + CPL + lane * CPL);
-            const uint4 vc = *reinterpret_cast<const uint4*>(rc + CPL + lane * CPL);
-            const uint4 vn = *reinterpret_cast<const uint4*>(rn + CPL + lane * CPL);
-            uint32_t hcell = 0;
-            if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
-            if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
-            const uint4 vo = make_uint4(vp.x | vc.x | vn.x, vp.y | vc.y | vn.y, vp.z | vc.z | vn.z, vp.w | vc.w | vn.w);
-            const uint32_t act = __ballot_sync(0xffffffffu, sw.seg_needs_look(vo, hcell));
-            sw.detail_row(y_begin - 1 + j, rp, rc, rn, act);
-        }
-        // box k-1 is dead now (its last row was the `prev` of this box's first row): refill its slot
-        __syncwarp();
-        if (lane == 0 && k + TMA_STAGES - 1 < n_box) issue_box(k + TMA_STAGES - 1);
+        boxes_done += (uint32_t)n_box;
+        sw.finish(mp);
     }
-    sw.finish(mp);
 }
 
 // ---- front end 2: register window -------------------------------------------------------
@@ -457,7 +480,7 @@ struct RowRegs {
 };
 
 template <typename CellT>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_ldg(const DevParams p, const int par) {
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_ldg(const DevParams p, const int par) {
     using SW = SweepWarp<CellT>;
     using C = Cell<CellT>;
     constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
@@ -465,16 +488,17 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_ldg(const DevParams 
     __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = p.H, pitch = p.pitch;
+    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
+    CellT(*sm)[RS] = sm_all[warp];
+
     int strip, chunk, env;
-    if (!decode_unit(p, (long long)blockIdx.x * SWEEP_WARPS + warp, strip, chunk, env)) return;
+    while (next_unit(p, par, lane, strip, chunk, env)) {
     EnvMeta* const mp = p.meta + (long long)par * p.E + env;
     const EnvMeta m = *mp;
-    if (!m.running) return;
+    if (!m.running) continue;
     SW sw(p, par, lane, env, strip, chunk, m, wq_all[warp]);
-    const int H = p.H, pitch = p.pitch;
-
     const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + sw.env_off;
-    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
     const int x0 = sw.x0;
     const int xl = x0 + lane * CPL;
     const int y_begin = chunk * p.rows_per_chunk;
@@ -483,7 +507,6 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_ldg(const DevParams 
     // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
     const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
     const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
-    CellT(*sm)[RS] = sm_all[warp];
 
     // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
     auto edge_row = [&](int y) -> const CellT* {
@@ -547,6 +570,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_ldg(const DevParams 
         rowp = q4;
     }
     sw.finish(mp);
+    }  // units
 }
 
 // ---------------------------------------------------------------------------------------
@@ -631,6 +655,7 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
     if (gid == 0) {
         p.qcount[par ^ 1] = 0;
         p.overflow[par ^ 1] = 0;
+        p.unit_next[par ^ 1] = 0;
     }
 }
 
