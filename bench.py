@@ -241,19 +241,15 @@ def load_traffic_note(workload: str):
 def gpu_arm(args):
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from simfire_b200 import FireEngine
+    from simfire_b200.sharding import RankContext
+
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the stepper has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    from simfire_b200 import FireEngine
+    ctx = RankContext.from_env(backend="nccl", device_id=torch.device("cuda", local))
+    rank, world = ctx.rank, ctx.world
 
     wl, E, shared = make_workload(args.workload)
     if args.envs:
@@ -268,8 +264,7 @@ def gpu_arm(args):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        ctx.barrier()
         torch.cuda.synchronize()
 
     eng.step(args.warmup)
@@ -279,10 +274,7 @@ def gpu_arm(args):
         ms = eng.step_timed(args.steps)
         barrier()
     launches = eng.launch_counts()[1] - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = ctx.max(ms)
     cells_per_step = H * W * E * world
     value = cells_per_step * args.steps / (ms_max * 1e-3)
 
@@ -319,10 +311,7 @@ def gpu_arm(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = cells_per_step * e2e_steps / float(t.item())
+    e2e_value = cells_per_step * e2e_steps / ctx.max(e2e_s)
 
     # ---- sanity: the timed steps really advanced fires
     st, el, nsteps = eng.status()
@@ -330,8 +319,7 @@ def gpu_arm(args):
     running = int(st.sum())
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        ctx.close()
         return
 
     peaks = {}
@@ -385,8 +373,7 @@ def gpu_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_budget)
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def main():

@@ -1,0 +1,261 @@
+"""
+`FireSimulation`: the SimHarness-facing surface of simfire/sim/simulation.py:184-553 --
+`run()`, `fire_map`, `update_mitigation()`, `update_agent_positions()`, `load_mitigation()`,
+`reset()`, `get_actions()`, `get_attribute_data()` ... -- on top of the device-resident
+stepper, plus `BatchedFireSimulation`, the same surface vectorised over E independent envs
+(one engine, one kernel launch per step for all of them).
+
+Always headless: rendering, GIF recording, spread-graph drawing and `save_data` are display /
+IO features outside the hot-path scope.
+
+Unlike the drop-in manager (`fire_manager.RothermelFireManager.update`, which round-trips the
+caller's fire_map every call exactly like the reference), the simulation classes keep the map
+on the device: mitigation goes down as a few (x, y, kind) points, `run(n)` issues n steps in
+one call, and the int64 host `fire_map` is materialised lazily when it is read.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .config import Config, str_to_minutes
+from .engine import FireEngine
+from .enums import BurnStatus, ElevationConstants, FuelConstants, GameStatus, WindConstants
+from .fire_manager import fuel_planes
+from .parameters import Environment, FuelParticle
+from .workloads import compute_slopes
+
+
+def _static_planes(config: Config):
+    H, W = config.area.screen_size
+    fdata = np.asarray(config.terrain.fuel_layer.data)
+    fuels = fdata[..., 0] if fdata.dtype == object else fdata
+    w_0, delta, M_x, sigma = fuel_planes(fuels)
+    elev = np.asarray(config.terrain.topography_layer.data, dtype=np.float64).reshape(H, W)
+    slope_mag, slope_dir = compute_slopes(elev, config.area.pixel_scale)
+    return dict(w_0=w_0, delta=delta, M_x=M_x, sigma=sigma, U=config.wind.speed, U_dir=config.wind.direction,
+                slope_mag=slope_mag, slope_dir=slope_dir), elev  # fmt: skip
+
+
+def _engine_from_config(config: Config, E: int, device: int, shared_static: bool, **kw) -> FireEngine:
+    fp = FuelParticle()
+    H, W = config.area.screen_size
+    return FireEngine(
+        H, W, E, pixel_scale=config.area.pixel_scale, update_rate=config.simulation.update_rate,
+        max_fire_duration=config.fire.max_fire_duration, max_time=config.simulation.runtime,
+        attenuate_line_ros=config.mitigation.ros_attenuation, diagonal_spread=config.fire.diagonal_spread,
+        fuel_particle=(fp.h, fp.S_T, fp.S_e, fp.p_p), M_f=config.environment.moisture,
+        shared_static=shared_static, device=device, **kw,
+    )  # fmt: skip
+
+
+class FireSimulation:
+    def __init__(self, config: Config, *, device: int = 0) -> None:
+        self.config = config
+        self.device = device
+        self._rendering = False
+        self.agents: Dict[int, Tuple[int, int]] = {}
+        self._engine: Optional[FireEngine] = None
+        self.reset()
+
+    # -- lifecycle (simulation.py:202-214) ----------------------------------------------------
+    def reset(self) -> None:
+        H, W = self.config.area.screen_size
+        if self._engine is None or (self._engine.H, self._engine.W) != (H, W):
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = _engine_from_config(self.config, 1, self.device, shared_static=True)
+        self._planes, self._elevations = _static_planes(self.config)
+        self._engine.set_static(self._planes)
+        self._engine.reset([self.config.fire.fire_initial_position])
+        self.fuel_particle = FuelParticle()
+        self.environment = Environment(self.config.environment.moisture, self.config.wind.speed,
+                                       self.config.wind.direction)  # fmt: skip
+        self.agents.clear()
+        self.agent_positions = np.zeros((H, W), dtype=np.int64)
+        self._fire_map: Optional[np.ndarray] = None
+        self.elapsed_steps = 0
+        self.elapsed_time = 0.0
+        self.fire_status = GameStatus.RUNNING
+        self.game_status = GameStatus.RUNNING
+        self.active = True
+
+    def close(self) -> None:
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    # -- fire_map: int64 (H, W) like the reference (simulation.py:561-564), fetched lazily -----
+    @property
+    def fire_map(self) -> np.ndarray:
+        if self._fire_map is None:
+            self._fire_map = self._engine.fire_map(0, 1)[0].astype(np.int64)
+        return self._fire_map
+
+    @fire_map.setter
+    def fire_map(self, value: np.ndarray) -> None:
+        value = np.asarray(value)
+        if value.shape != tuple(self.config.area.screen_size):
+            raise ValueError(f"fire_map of shape {value.shape} does not match {self.config.area.screen_size}")
+        self._engine.set_fire_map(value.astype(np.int8))
+        self._fire_map = None
+
+    def fire_map_device(self):
+        """Zero-copy int8 (H, W) BurnStatus tensor on the GPU (observation for RL)."""
+        return self._engine.fire_map_device()[0]
+
+    # -- descriptive API ------------------------------------------------------------------------
+    def get_actions(self) -> Dict[str, int]:
+        return {"fireline": BurnStatus.FIRELINE, "scratchline": BurnStatus.SCRATCHLINE, "wetline": BurnStatus.WETLINE}
+
+    @property
+    def disaster_categories(self):
+        return BurnStatus
+
+    def get_disaster_categories(self) -> Dict[str, int]:
+        return {i.name: i.value for i in BurnStatus}
+
+    @staticmethod
+    def supported_attributes() -> List[str]:
+        return ["w_0", "sigma", "delta", "M_x", "elevation", "wind_speed", "wind_direction"]
+
+    def get_attribute_bounds(self) -> Dict[str, object]:
+        return {
+            "w_0": {"min": FuelConstants.W_0_MIN, "max": FuelConstants.W_0_MAX},
+            "sigma": {"min": FuelConstants.SIGMA_MIN, "max": FuelConstants.SIGMA_MAX},
+            "delta": {"min": FuelConstants.DELTA_MIN, "max": FuelConstants.DELTA_MAX},
+            "M_x": {"min": FuelConstants.M_X_MIN, "max": FuelConstants.M_X_MAX},
+            "elevation": {"min": ElevationConstants.MIN_ELEVATION, "max": ElevationConstants.MAX_ELEVATION},
+            "wind_speed": {"min": WindConstants.MIN_SPEED, "max": WindConstants.MAX_SPEED},
+            "wind_direction": {"min": 0.0, "max": 360.0},
+        }
+
+    def get_attribute_data(self) -> Dict[str, np.ndarray]:
+        """Same dtypes as simulation.py:395-403 (sigma is uint32 there)."""
+        p = self._planes
+        return {"w_0": p["w_0"].astype(np.float32), "sigma": p["sigma"].astype(np.uint32),
+                "delta": p["delta"].astype(np.float32), "M_x": p["M_x"].astype(np.float32),
+                "elevation": self._elevations, "wind_speed": self.config.wind.speed,
+                "wind_direction": self.config.wind.direction}  # fmt: skip
+
+    # -- between-step mutations -------------------------------------------------------------------
+    def load_mitigation(self, mitigation_map: np.ndarray) -> None:
+        """simulation.py:425-447"""
+        category_values = [status.value for status in BurnStatus]
+        if np.isin(mitigation_map, category_values).all():
+            message = ("You are overwriting the current fire map with the given mitigation map - the current "
+                       "fire map data will be erased.")  # fmt: skip
+            self.fire_map = mitigation_map
+        else:
+            message = f"Invalid values in {mitigation_map} - values need to be within {category_values}... Skipping"
+        warnings.warn(message)
+
+    def update_mitigation(self, points: Iterable[Tuple[int, int, int]]) -> None:
+        """(column, row, mitigation) tuples (simulation.py:449-478); unknown kinds are skipped."""
+        keep = [(0, int(c), int(r), int(m)) for c, r, m in points
+                if m in (BurnStatus.FIRELINE, BurnStatus.SCRATCHLINE, BurnStatus.WETLINE)]  # fmt: skip
+        if keep:
+            self._engine.apply_points(keep)
+            self._fire_map = None
+
+    def update_agent_positions(self, points: Iterable[Tuple[int, int, int]]) -> None:
+        """(column, row, agent_id) tuples (simulation.py:480-499); the fire never reads this."""
+        for column, row, agent_id in points:
+            self.agent_positions[self.agent_positions == agent_id] = 0
+            self.agent_positions[row][column] = agent_id
+            self.agents[agent_id] = (column, row)
+
+    # -- run (simulation.py:501-553) -----------------------------------------------------------------
+    def run(self, time: Union[str, int]) -> Tuple[np.ndarray, bool]:
+        if isinstance(time, str):
+            total_updates = round(str_to_minutes(time) / self.config.simulation.update_rate)
+        else:
+            total_updates = int(time)
+        if self.fire_status == GameStatus.RUNNING and total_updates > 0:
+            # envs that return QUIT stop advancing on the device, like the `while` loop of the reference
+            self._engine.step(total_updates)
+            st, el, n = self._engine.status()
+            self.fire_status = GameStatus(int(st[0]))
+            self.elapsed_time = float(el[0])
+            self.elapsed_steps = int(n[0])
+            self._fire_map = None
+        self.active = self.fire_status == GameStatus.RUNNING
+        return self.fire_map, self.active
+
+    # -- config mutation helpers the harness uses -------------------------------------------------------
+    def set_fire_initial_position(self, pos: Tuple[int, int]) -> None:
+        self.config.reset_fire(pos)
+        self.reset()
+
+    def rendering(self) -> bool:
+        return False
+
+
+class BatchedFireSimulation:
+    """
+    E independent `FireSimulation`s of one terrain on one GPU.  Methods mirror
+    `FireSimulation` with a leading env axis: `run(n)` -> (fire_maps[E, H, W] int8, active[E]),
+    `update_mitigation(points)` takes (env, column, row, mitigation) rows, `reset(envs=...)`
+    restarts a subset (the RL "done" handling).  Across GPUs, run one instance per process /
+    device on a disjoint slice of envs: envs never interact, so there is no collective.
+    """
+
+    def __init__(self, config: Config, num_envs: int, *, device: int = 0,
+                 initial_positions: Optional[Sequence[Tuple[int, int]]] = None) -> None:  # fmt: skip
+        self.config = config
+        self.num_envs = int(num_envs)
+        self._engine = _engine_from_config(config, self.num_envs, device, shared_static=True)
+        self._planes, self._elevations = _static_planes(config)
+        self._engine.set_static(self._planes)
+        pos = initial_positions if initial_positions is not None else [config.fire.fire_initial_position] * self.num_envs
+        self._engine.reset(pos)
+        H, W = config.area.screen_size
+        self.agent_positions = np.zeros((self.num_envs, H, W), dtype=np.int64)
+
+    @property
+    def engine(self) -> FireEngine:
+        return self._engine
+
+    def reset(self, positions=None, envs: Optional[Sequence[int]] = None) -> None:
+        envs = list(range(self.num_envs)) if envs is None else list(envs)
+        if positions is None:
+            positions = [self.config.fire.fire_initial_position] * len(envs)
+        self._engine.reset(positions, envs=envs)
+        self.agent_positions[envs] = 0
+
+    def update_mitigation(self, points) -> None:
+        pts = np.asarray(points, dtype=np.int32).reshape(-1, 4)
+        ok = (pts[:, 3] >= BurnStatus.FIRELINE) & (pts[:, 3] <= BurnStatus.WETLINE)
+        self._engine.apply_points(pts[ok])
+
+    def update_agent_positions(self, points) -> None:
+        for env, column, row, agent_id in points:
+            a = self.agent_positions[env]
+            a[a == agent_id] = 0
+            a[row, column] = agent_id
+
+    def run(self, time: Union[str, int], out: Optional[np.ndarray] = None):
+        if isinstance(time, str):
+            total_updates = round(str_to_minutes(time) / self.config.simulation.update_rate)
+        else:
+            total_updates = int(time)
+        self._engine.step(total_updates, sync=False)
+        maps = self._engine.fire_map(0, self.num_envs, out=out)
+        st, _, _ = self._engine.status()
+        return maps, st == GameStatus.RUNNING
+
+    def fire_maps_device(self):
+        return self._engine.fire_map_device()
+
+    @property
+    def elapsed_time(self) -> np.ndarray:
+        return self._engine.status()[1]
+
+    @property
+    def elapsed_steps(self) -> np.ndarray:
+        return self._engine.status()[2]
+
+    def close(self) -> None:
+        self._engine.close()

@@ -1,0 +1,241 @@
+"""
+GPU tests of the reference-shaped Python surface: the `RothermelFireManager` drop-in
+(simfire/game/managers/fire.py) and `FireSimulation` (simfire/sim/simulation.py), replayed
+against vectors recorded from the unmodified reference (tests/golden/gen_golden.py,
+tests/golden/gen_api_golden.py) and against re-statements of the reference's own unit tests
+(simfire/game/managers/_tests/test_fire.py, simfire/sim/_tests/test_simulation.py).
+"""
+import ast
+import types
+
+import numpy as np
+import pytest
+import yaml
+from scenario_io import GOLDEN, load_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _terrain(H, W, fuels, elevations):
+    return types.SimpleNamespace(fuels=fuels, elevations=elevations, screen_size=(H, W))
+
+
+def _manager_for(sc, **kw):
+    from simfire_b200.fire_manager import RothermelFireManager
+    from simfire_b200.parameters import Environment, FuelParticle
+
+    p = sc["planes"]
+    fuels = np.stack([p["w_0"], p["delta"], p["M_x"], p["sigma"]], axis=-1)
+    return RothermelFireManager(
+        sc["init"], 2, int(sc["max_dur"]), float(sc["ps"]), float(sc["dt"]), FuelParticle(),
+        _terrain(sc["H"], sc["W"], fuels, sc["elevations"]), Environment(float(sc["M_f"]), p["U"], p["U_dir"]),
+        max_time=sc["max_time"], attenuate_line_ros=bool(sc["attenuate"]), headless=True,
+        diagonal_spread=bool(sc["diagonal"]), **kw,
+    )  # fmt: skip
+
+
+@pytest.mark.parametrize("name", ["scenario_c_random_fuel_hills", "scenario_d_midrun_mitigation",
+                                  "scenario_f_max_time"])  # fmt: skip
+def test_manager_dropin_replays_reference(name):
+    """`fire_map, status = manager.update(fire_map)` with the caller's int64 map, edited in
+    place between calls exactly as `ControlLineManager.update` does (mitigation.py:77)."""
+    from simfire_b200.enums import BurnStatus, GameStatus
+
+    sc = load_scenario(name)
+    mgr = _manager_for(sc, keep_rate_of_spread=True)
+    # slopes are computed by the manager from the elevations, as fire.py:436-449 does
+    assert np.array_equal(mgr.slope_mag, sc["planes"]["slope_mag"])
+    assert np.array_equal(mgr.slope_dir, sc["planes"]["slope_dir"])
+    fire_map = np.full((sc["H"], sc["W"]), BurnStatus.UNBURNED)
+    assert fire_map.dtype == np.int64
+    fire_map[sc["init"][1], sc["init"][0]] = BurnStatus.BURNING
+    for x, y, k in sc["pre"]:
+        fire_map[y, x] = k
+    map_at = {int(s): i for i, s in enumerate(sc["map_steps"])}
+    for step in range(1, int(sc["n_steps"]) + 1):
+        for x, y, k in sc["schedule"].get(step, ()):
+            fire_map[y, x] = k
+        out, status = mgr.update(fire_map)
+        assert out is fire_map and isinstance(status, GameStatus)
+        assert int(status) == int(sc["status"][step - 1]), step
+        assert mgr.elapsed_time == float(sc["elapsed"][step - 1]), step
+        if step in map_at:
+            assert np.array_equal(fire_map, sc["maps"][map_at[step]]), f"{name} step {step}"
+    np.testing.assert_allclose(mgr.burn_amounts, sc["burns"][-1], rtol=1e-5,
+                               atol=1e-5 * float(np.max(np.abs(sc["burns"]))))  # fmt: skip
+    mgr.close()
+
+
+def _simple_manager(size=11, pixel_scale=0.0, max_fire_duration=4, **kw):
+    from simfire_b200.config import chaparral
+    from simfire_b200.fire_manager import RothermelFireManager
+    from simfire_b200.parameters import Environment, FuelParticle
+
+    fuels = np.empty((size, size), dtype=object)
+    fuels.fill(chaparral(1113))
+    terrain = _terrain(size, size, fuels, np.zeros((size, size)))
+    env = Environment(0.03, kw.pop("U", 88.0), kw.pop("U_dir", 135.0))
+    return RothermelFireManager((size // 2, size // 2), 2, max_fire_duration, pixel_scale, 1.0, FuelParticle(),
+                                terrain, env, headless=True, **kw)  # fmt: skip
+
+
+def test_update_ignites_all_neighbours_when_pixel_scale_is_zero():
+    """test_fire.py:326-392: after one update every in-bounds neighbour burns (8 or 4)."""
+    for diagonal, want in ((True, 9), (False, 5)):
+        mgr = _simple_manager(diagonal_spread=diagonal)
+        fm = np.zeros((11, 11), dtype=np.int64)
+        fm[5, 5] = 1
+        fm, status = mgr.update(fm)
+        assert int(status) == 1
+        assert (fm == 1).sum() == want
+        assert sorted(mgr.sprites) == sorted((int(x), int(y)) for y, x in np.argwhere(fm == 1))
+        assert mgr.elapsed_time == 1.0
+        mgr.close()
+
+
+def test_prune_after_max_fire_duration():
+    """fire.py:116-161 timeline: the initial fire turns BURNED at the start of update max_dur + 1."""
+    mgr = _simple_manager(pixel_scale=1e9, max_fire_duration=3)  # nothing else ever ignites
+    fm = np.zeros((11, 11), dtype=np.int64)
+    fm[5, 5] = 1
+    for step in range(1, 4):
+        fm, status = mgr.update(fm)
+        assert fm[5, 5] == 1 and int(status) == 1, step
+        assert mgr.durations == [step]
+    fm, status = mgr.update(fm)  # sprite pruned, none left -> QUIT
+    assert fm[5, 5] == 2 and int(status) == 0
+    assert mgr.sprites == []
+    mgr.close()
+
+
+def test_attenuation_on_and_off():
+    """test_fire.py:124-162: with attenuation every control line loses 980/490/245 per step,
+    without it the lines' rate of spread is exactly zero."""
+    lines = {(1, 1): 3, (2, 1): 4, (3, 1): 5, (6, 5): 3}  # (x, y) -> kind; (6, 5) touches the fire
+    for attenuate in (True, False):
+        mgr = _simple_manager(pixel_scale=50.0, attenuate_line_ros=attenuate, keep_rate_of_spread=True)
+        fm = np.zeros((11, 11), dtype=np.int64)
+        fm[5, 5] = 1
+        for (x, y), k in lines.items():
+            fm[y, x] = k
+        fm, _ = mgr.update(fm)
+        ros = mgr.rate_of_spread
+        if attenuate:
+            assert ros[1, 1] == -980 and ros[1, 2] == -490 and ros[1, 3] == -245
+            assert ros[5, 6] == pytest.approx(mgr.rate_of_spread[5, 6]) and ros[5, 6] > -980
+        else:
+            assert ros[1, 1] == 0 and ros[1, 2] == 0 and ros[1, 3] == 0 and ros[5, 6] == 0
+        assert np.array_equal(mgr.burn_amounts, ros)  # first step: burn == ros
+        mgr.close()
+
+
+def test_manager_errors_match_reference():
+    with pytest.raises(ValueError, match="should match the terrain shape"):
+        _simple_manager(U=np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="should be one of"):
+        _simple_manager(U=[1.0, 2.0])
+    mgr = _simple_manager()
+    with pytest.raises(AssertionError):
+        mgr.update(np.zeros((4, 4), dtype=np.int64))
+    mgr.close()
+
+
+@pytest.mark.parametrize("name", ["flat64", "gauss48"])
+def test_fire_simulation_replays_reference_call_sequence(name):
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_{name}.npz")
+    sim = FireSimulation(Config(config_dict=yaml.safe_load(str(z["config_yaml"]))))
+    script = ast.literal_eval(str(z["script"]))
+    k = 0
+    for op, arg in script:
+        if op == "run":
+            fm, active = sim.run(arg)
+            assert fm.dtype == np.int64 and fm.shape == z["maps"][k].shape
+            assert np.array_equal(fm, z["maps"][k]), f"{name}: fire_map after call {k} ({op} {arg})"
+            et, es, act = z["meta"][k]
+            assert sim.elapsed_time == et and sim.elapsed_steps == int(es) and bool(active) == bool(act), k
+            assert sim.active == bool(act)
+            k += 1
+        elif op == "mitigate":
+            sim.update_mitigation(arg)
+        elif op == "agents":
+            sim.update_agent_positions(arg)
+        elif op == "reset":
+            sim.reset()
+    assert np.array_equal(sim.agent_positions, z["agent_positions"])
+    attr = sim.get_attribute_data()
+    for key in ("w_0", "sigma", "delta", "M_x", "wind_speed", "wind_direction"):
+        assert attr[key].dtype == z["attr_" + key].dtype, key
+        assert np.array_equal(attr[key], z["attr_" + key]), key
+    assert np.array_equal(np.asarray(attr["elevation"], dtype=np.float64).reshape(z["attr_elevation"].shape[:2]),
+                          z["attr_elevation"].reshape(z["attr_elevation"].shape[:2]))  # fmt: skip
+    assert sim.get_actions() == {"fireline": 3, "scratchline": 4, "wetline": 5}
+    assert set(sim.get_attribute_bounds()) == set(sim.supported_attributes())
+    sim.close()
+
+
+def test_simulation_run_until_burned_out():
+    """test_simulation.py:84-121: run('1h') on a 9x9 flat map ends with BURNED cells;
+    run(1) advances elapsed_time by update_rate."""
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    y = yaml.safe_load(str(z["config_yaml"]))
+    y["area"]["screen_size"] = [9, 9]
+    y["fire"]["fire_initial_position"]["static"]["position"] = "(4, 4)"
+    sim = FireSimulation(Config(config_dict=y))
+    fm, active = sim.run(1)
+    assert sim.elapsed_time == y["simulation"]["update_rate"] and active
+    fm, active = sim.run("1h")
+    assert fm.max() == 2 and not active
+    sim.close()
+
+
+def test_load_mitigation_and_device_view():
+    import torch
+
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    sim = FireSimulation(Config(config_dict=yaml.safe_load(str(z["config_yaml"]))))
+    m = np.zeros((64, 64), dtype=np.int64)
+    m[10, :] = 3
+    with pytest.warns(UserWarning, match="overwriting"):
+        sim.load_mitigation(m)
+    assert np.array_equal(sim.fire_map, m)
+    bad = m.copy()
+    bad[0, 0] = 17
+    with pytest.warns(UserWarning, match="Invalid values"):
+        sim.load_mitigation(bad)
+    assert np.array_equal(sim.fire_map, m)
+    t = sim.fire_map_device()
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), m.astype(np.int8))
+    assert torch.count_nonzero(t == 3).item() == 64
+    sim.close()
+
+
+def test_batched_simulation_matches_single_envs():
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import BatchedFireSimulation, FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    y = yaml.safe_load(str(z["config_yaml"]))
+    starts = [(20, 24), (40, 10), (5, 50)]
+    batch = BatchedFireSimulation(Config(config_dict=y), 3, initial_positions=starts)
+    batch.update_mitigation([(e, x, 30, 3) for e in range(3) for x in range(0, 64)] + [(1, 2, 2, 9)])
+    maps, active = batch.run(25)
+    for e, pos in enumerate(starts):
+        cfg = Config(config_dict=yaml.safe_load(str(z["config_yaml"])))
+        cfg.reset_fire(pos)
+        single = FireSimulation(cfg)
+        single.update_mitigation([(x, 30, 3) for x in range(0, 64)])
+        fm, act = single.run(25)
+        assert np.array_equal(maps[e], fm), e
+        assert bool(active[e]) == act
+        assert batch.elapsed_time[e] == single.elapsed_time and batch.elapsed_steps[e] == single.elapsed_steps
+        single.close()
+    batch.close()
