@@ -66,7 +66,7 @@ def test_manager_dropin_replays_reference(name):
     mgr.close()
 
 
-def _simple_manager(size=11, pixel_scale=0.0, max_fire_duration=4, **kw):
+def _simple_manager(size=11, pixel_scale=1e-3, max_fire_duration=4, **kw):
     from simfire_b200.config import chaparral
     from simfire_b200.fire_manager import RothermelFireManager
     from simfire_b200.parameters import Environment, FuelParticle
@@ -79,8 +79,9 @@ def _simple_manager(size=11, pixel_scale=0.0, max_fire_duration=4, **kw):
                                 terrain, env, headless=True, **kw)  # fmt: skip
 
 
-def test_update_ignites_all_neighbours_when_pixel_scale_is_zero():
-    """test_fire.py:326-392: after one update every in-bounds neighbour burns (8 or 4)."""
+def test_update_ignites_all_neighbours_when_pixel_scale_is_tiny():
+    """test_fire.py:326-392 (which zeroes pixel_scale after construction): after one update
+    every in-bounds neighbour burns (8 or 4)."""
     for diagonal, want in ((True, 9), (False, 5)):
         mgr = _simple_manager(diagonal_spread=diagonal)
         fm = np.zeros((11, 11), dtype=np.int64)
