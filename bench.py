@@ -256,7 +256,7 @@ def gpu_arm(args):
         E = args.envs
     H, W = wl.H, wl.W
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
-                     sweep_ldg=(args.sweep == "ldg"), **wl.engine_kwargs())  # fmt: skip
+                     sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, **wl.engine_kwargs())  # fmt: skip
     eng.set_static(wl.planes)
     starts = wl.burnable_starts(E, seed=1000 + rank)
     eng.reset(starts)
@@ -302,15 +302,19 @@ def gpu_arm(args):
         pts_np[:, 3] = 3  # BurnStatus.FIRELINE
         eng.apply_points(pts_np)          # host -> device
         eng.step(1, sync=False)
-        eng.fire_map(0, E, out=maps_np)   # device -> host (synchronises)
+        return eng.sync_fire_maps(maps_np)  # device -> host: changed cells only, patched into the mirror
 
+    e2e_step()  # first call downloads every map once
     e2e_step()
     barrier()
     t0 = time.perf_counter()
+    e2e_changes = 0
     for _ in range(e2e_steps):
-        e2e_step()
+        e2e_changes += max(0, e2e_step())
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the patched mirror must equal a full download (checked outside the timed region)
+    e2e_ok = bool(np.array_equal(maps_np[: min(E, 16)], eng.fire_map(0, min(E, 16))))
     e2e_value = cells_per_step * e2e_steps / ctx.max(e2e_s)
 
     # ---- sanity: the timed steps really advanced fires
@@ -351,8 +355,11 @@ def gpu_arm(args):
         },
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes) * world,
-                "d2h_bytes_per_step": int(maps_np.nbytes) * world, "steps": e2e_steps,
-                "api": "FireEngine.apply_points + step + fire_map (pinned host buffers)"},
+                "d2h_bytes_per_step": (int(8 * e2e_changes / e2e_steps) + 12 if not args.no_track else int(maps_np.nbytes)) * world,
+                "steps": e2e_steps, "host_mirror_bytes": int(maps_np.nbytes) * world, "mirror_matches_download": e2e_ok,
+                "api": "FireEngine.apply_points (pinned H2D) + step + sync_fire_maps: every env's int8 fire_map is "
+                       "brought up to date in host memory each step" + (" by patching the cells the device logged "
+                       "as changed (8 B each)" if not args.no_track else " by a full download")},
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -388,9 +395,10 @@ def main():
     ap.add_argument("--rows-per-chunk", type=int, default=0)
     ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
     ap.add_argument("--roofline-steps", type=int, default=20)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -64,8 +64,10 @@ enum sfb_flags {
     SFB_HAS_MAX_TIME = 16,     /* max_time is not None (fire.py:641)                         */
     SFB_WIDE_CELLS = 32,       /* use the 16-bit cell layout even when max_fire_duration <= 30
                                   (it is selected automatically above that); tests only      */
-    SFB_SWEEP_LDG = 64         /* stream the state with 128-bit global loads instead of the TMA
+    SFB_SWEEP_LDG = 64,        /* stream the state with 128-bit global loads instead of the TMA
                                   ring (A/B measurements; slab mode always uses it)          */
+    SFB_TRACK_CHANGES = 128    /* keep a device log of every BurnStatus change so that
+                                  sfb_sync_fire_maps can patch a host mirror incrementally   */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the
@@ -170,6 +172,15 @@ int sfb_synchronize(sfb_sim* sim);
 
 /* fire_map of envs [env0, env0+n) as int8 BurnStatus [n][H][W]. */
 int sfb_get_fire_map(sfb_sim* sim, int32_t env0, int32_t n, int8_t* out);
+/* Bring a HOST mirror of every env's fire_map (int8 BurnStatus [E][H][W]) up to date.  The
+ * first call, a call with a different buffer, or a call after sfb_set_fire_map / a log
+ * overflow downloads everything (like sfb_get_fire_map); otherwise, with SFB_TRACK_CHANGES,
+ * only the cells that changed since the previous call travel over PCIe and are patched into
+ * `mirror` by host threads -- what `sim.fire_map` needs after each `run()` without copying
+ * E*H*W bytes per step.  The caller must not modify `mirror` between calls.  *n_changes (may be
+ * NULL) receives the number of patched cells, or -1 for a full download. */
+int sfb_sync_fire_maps(sfb_sim* sim, int8_t* mirror, int64_t* n_changes);
+
 /* One [H][W] plane of one env; element type per sfb_state_plane. */
 int sfb_get_plane(sfb_sim* sim, int32_t env, int32_t plane, void* out);
 /* Per-env GameStatus (int32), elapsed_time (float64, fire.py:717) and number of update()

@@ -11,6 +11,7 @@ ABI_VERSION = 1
 
 # sfb_flags
 DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
+TRACK_CHANGES = 128
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS = 0, 1, 2, 3
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")
@@ -22,7 +23,7 @@ EXPORTS = (
     "sfb_step_timed", "sfb_update", "sfb_synchronize", "sfb_get_fire_map", "sfb_get_plane",
     "sfb_get_status", "sfb_fire_map_device", "sfb_get_stream", "sfb_get_launch_counts",
     "sfb_set_kernel_timing", "sfb_get_kernel_ms", "sfb_get_queue_stats", "sfb_device_bytes",
-    "sfb_rate_of_spread",
+    "sfb_rate_of_spread", "sfb_sync_fire_maps",
 )  # fmt: skip
 
 
@@ -74,6 +75,7 @@ def load() -> C.CDLL:
         "sfb_synchronize": (C.c_int, [vp]),
         "sfb_get_fire_map": (C.c_int, [vp, i32, i32, vp]),
         "sfb_get_plane": (C.c_int, [vp, i32, i32, vp]),
+        "sfb_sync_fire_maps": (C.c_int, [vp, vp, C.POINTER(i64)]),
         "sfb_get_status": (C.c_int, [vp, vp, vp, vp]),
         "sfb_fire_map_device": (C.c_int, [vp, C.POINTER(vp)]),
         "sfb_get_stream": (C.c_int, [vp, C.POINTER(vp)]),

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/simfire_b200.h"
@@ -65,6 +66,11 @@ struct sfb_sim {
     int64_t timed_steps;
     int64_t last_entries;
     int last_overflow;
+    // host mirror bookkeeping (sfb_sync_fire_maps)
+    const int8_t* mirror;      // buffer the last sync wrote, nullptr = none valid
+    int full_resync;           // something changed that the log does not describe
+    unsigned long long* log_host;  // pinned staging for the change log
+    size_t log_host_entries;
 };
 
 static int use(sfb_sim* s) {
@@ -149,6 +155,19 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
     m.any_live = m.any_cand = m.pad = 0;
     m.time_quit = p.has_max_time && (p.dt > p.max_time || 0.0 > p.max_time);
     p.meta[(long long)par * p.E + env] = m;
+    if (p.track) {  // "env was cleared", then its first burning cell, in this order
+        const unsigned long long slot = atomicAdd(p.chg_count, 2ULL);
+        if (slot + 1 < (unsigned long long)p.chg_cap) {
+            p.chg[slot] = (unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48);
+            const bool inside = y >= 0 && y < p.H;
+            const long long idx = (long long)env * p.plane + (long long)(inside ? y : 0) * p.pitch + x;
+            // a slab that does not hold the ignition row logs the reset twice (harmless)
+            p.chg[slot + 1] = inside ? ((unsigned long long)idx | (1ULL << 48))
+                                     : ((unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48));
+        } else {
+            *p.chg_overflow = 1;
+        }
+    }
 }
 
 // ControlLineManager.update (mitigation.py:77): fire_map[y, x] = kind, sprite untouched
@@ -158,8 +177,14 @@ __global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int
     if (i >= n) return;
     const int env = pts[4 * i], x = pts[4 * i + 1], y = pts[4 * i + 2] - y_off, k = pts[4 * i + 3];
     if (k != kind || y < 0 || y >= p.H) return;
-    CellT* c = reinterpret_cast<CellT*>(p.state) + (long long)env * p.plane + (long long)y * p.pitch + x;
+    const long long idx = (long long)env * p.plane + (long long)y * p.pitch + x;
+    CellT* c = reinterpret_cast<CellT*>(p.state) + idx;
     *c = (CellT)((*c & ~7) | to_internal(k));
+    if (p.track) {
+        const unsigned long long slot = atomicAdd(p.chg_count, 1ULL);
+        if (slot < (unsigned long long)p.chg_cap) p.chg[slot] = (unsigned long long)idx | ((unsigned long long)k << 48);
+        else *p.chg_overflow = 1;
+    }
 }
 
 template <typename CellT>
@@ -275,6 +300,10 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.qcount);
     cudaFree(s->d.overflow);
     cudaFree(s->d.unit_next);
+    cudaFree(s->d.chg);
+    cudaFree(s->d.chg_count);
+    cudaFree(s->d.chg_overflow);
+    if (s->log_host) cudaFreeHost(s->log_host);
     cudaFree((void*)s->d.filler);
     cudaFree(s->stage);
     cudaFree(s->obs);
@@ -348,6 +377,15 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
     if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
     if ((rc = dmalloc(s, &d.unit_next, 2 * sizeof(unsigned long long)))) return rc;
+    d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
+    if (d.track) {
+        d.chg_cap = std::max<int64_t>(1 << 20, total / 16);
+        if ((rc = dmalloc(s, &d.chg, (size_t)d.chg_cap * 8))) return rc;
+        if ((rc = dmalloc(s, &d.chg_count, sizeof(unsigned long long)))) return rc;
+        if ((rc = dmalloc(s, &d.chg_overflow, sizeof(int32_t)))) return rc;
+        CU(cudaMemsetAsync(d.chg_count, 0, sizeof(unsigned long long), s->stream));
+        CU(cudaMemsetAsync(d.chg_overflow, 0, sizeof(int32_t), s->stream));
+    }
     CU(cudaMemsetAsync(d.unit_next, 0, 2 * sizeof(unsigned long long), s->stream));
     {
         const size_t n = (size_t)d.pitch + 32;
@@ -562,6 +600,7 @@ static int check_env_range(sfb_sim* s, const char* who, int env0, int n) {
 
 static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     const DevParams& d = s->d;
+    s->full_resync = 1;  // the change log does not describe wholesale map replacement
     const size_t bytes = (size_t)n * d.H * d.W;
     int rc;
     if ((rc = ensure_stage(s, bytes))) return rc;
@@ -704,6 +743,87 @@ extern "C" int sfb_get_fire_map(sfb_sim* s, int32_t env0, int32_t n, int8_t* out
     if ((rc = use(s))) return rc;
     if ((rc = download_maps(s, env0, n, out))) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// Patch entries [0, n) of the change log into the host mirror.  Entries of one cell are in
+// time order in the log; each thread owns a contiguous range of envs and walks the whole log,
+// so the order is preserved without any synchronisation.
+static void apply_log(const sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror) {
+    const DevParams& d = s->d;
+    const long long hw = (long long)d.H * d.W;
+    const bool linear = d.pitch == d.W;
+    unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    nt = (unsigned)std::min<long long>(nt, std::max<long long>(1, n / 4096));
+    nt = std::min<unsigned>(nt, (unsigned)d.E);
+    auto work = [&](unsigned t) {
+        const long long e_lo = (long long)d.E * t / nt, e_hi = (long long)d.E * (t + 1) / nt;
+        const unsigned long long lo = (unsigned long long)(e_lo * d.plane), hi = (unsigned long long)(e_hi * d.plane);
+        for (long long i = 0; i < n; ++i) {
+            const unsigned long long e = log[i];
+            const unsigned long long idx = e & 0xFFFFFFFFFFFFull;
+            const int st = (int)(e >> 48) & 7;
+            if (st == LOG_ENV_RESET) {
+                if ((long long)idx >= e_lo && (long long)idx < e_hi) memset(mirror + idx * hw, 0, (size_t)hw);
+            } else if (idx >= lo && idx < hi) {
+                if (linear) {
+                    mirror[idx] = (int8_t)st;
+                } else {
+                    const long long env = (long long)(idx / d.plane), rem = (long long)(idx - env * d.plane);
+                    mirror[env * hw + (rem / d.pitch) * d.W + rem % d.pitch] = (int8_t)st;
+                }
+            }
+        }
+    };
+    if (nt <= 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes) {
+    if (!s || !mirror) return fail(SFB_ERR_INVALID, "sfb_sync_fire_maps: null argument");
+    int rc;
+    if ((rc = use(s))) return rc;
+    DevParams& d = s->d;
+    unsigned long long cnt = 0;
+    int32_t ovf = 0;
+    if (d.track) {
+        CU(cudaMemcpyAsync(&cnt, d.chg_count, sizeof(cnt), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(&ovf, d.chg_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    const bool full = !d.track || ovf || s->full_resync || s->mirror != mirror || cnt > (unsigned long long)d.chg_cap;
+    if (full) {
+        if ((rc = download_maps(s, 0, d.E, mirror))) return rc;
+        if (n_changes) *n_changes = -1;
+    } else if (cnt > 0) {
+        if (s->log_host_entries < cnt) {
+            if (s->log_host) CU(cudaFreeHost(s->log_host));
+            s->log_host = nullptr;
+            s->log_host_entries = 0;
+            const size_t want = std::max<size_t>((size_t)cnt * 2, (size_t)1 << 20);
+            CU(cudaMallocHost((void**)&s->log_host, want * 8));
+            s->log_host_entries = want;
+        }
+        CU(cudaMemcpyAsync(s->log_host, d.chg, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        apply_log(s, s->log_host, (long long)cnt, mirror);
+        if (n_changes) *n_changes = (int64_t)cnt;
+    } else if (n_changes) {
+        *n_changes = 0;
+    }
+    if (d.track) {
+        CU(cudaMemsetAsync(d.chg_count, 0, sizeof(unsigned long long), s->stream));
+        CU(cudaMemsetAsync(d.chg_overflow, 0, sizeof(int32_t), s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    s->mirror = mirror;
+    s->full_resync = 0;
     return 0;
 }
 

@@ -39,7 +39,8 @@
 namespace sfb {
 
 constexpr int ST_UNBURNED = 0, ST_BURNING = 1, ST_BURNED = 2, ST_LINE_BIT = 4;
-constexpr int DIR_NONE = 8;  // work item of a control-line cell that is not a candidate
+constexpr int DIR_NONE = 8;    // work item of a control-line cell that is not a candidate
+constexpr int DIR_PRUNED = 9;  // not work: a sprite burnt out here (only pushed for the change log)
 
 struct __align__(16) EnvMeta {
     int32_t t;          // 1-based index of the update() call being executed
@@ -78,6 +79,12 @@ struct DevParams {
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
     const void* filler;       // (pitch + 2 * 16) BURNED cells: stands in for rows outside the grid
+    // change log (SFB_TRACK_CHANGES)
+    int32_t track;
+    unsigned long long* chg;        // [chg_cap] idx | BurnStatus << 48
+    unsigned long long* chg_count;  // entries appended since the host last drained the log
+    int32_t* chg_overflow;
+    int64_t chg_cap;
 };
 
 template <typename CellT>
@@ -121,8 +128,27 @@ __device__ __forceinline__ unsigned long long make_item(long long idx, int dir, 
 // Work item: the part of the step that touches float data.  Shared by the queue path and
 // the dense fallback.
 // ---------------------------------------------------------------------------------------
+// Change log (SFB_TRACK_CHANGES): every status change of a cell is appended as
+// idx | BurnStatus << 48 so that a host mirror of fire_map can be patched instead of
+// re-downloaded (sfb_sync_fire_maps).  BurnStatus 7 = "env idx was reset".  Warp-wide call.
+constexpr int LOG_ENV_RESET = 7;
+__device__ __forceinline__ void log_append(const DevParams& p, bool have, long long idx, int burn_status) {
+    const uint32_t m = __ballot_sync(0xffffffffu, have);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(p.chg_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (have) {
+        const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+        if (slot < (unsigned long long)p.chg_cap) p.chg[slot] = (unsigned long long)idx | ((unsigned long long)burn_status << 48);
+        else *p.chg_overflow = 1;
+    }
+}
+
+// returns true if the cell ignited
 template <typename CellT>
-__device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& m, int env, long long idx,
+__device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& m, int env, long long idx,
                                              int dir, int s) {
     double ros;
     if (dir != DIR_NONE) {
@@ -136,7 +162,7 @@ __device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& 
     } else {
         // control line that no fire touches: attenuated only if the step got past the
         // "no new locations" early return (fire.py:651-652)
-        if (!m.any_cand) return;
+        if (!m.any_cand) return false;
         ros = 0.0 - line_attenuation(s);
     }
     if (p.keep_ros) p.ros[idx] = ros;
@@ -148,7 +174,9 @@ __device__ __forceinline__ void process_item(const DevParams& p, const EnvMeta& 
     if (dir != DIR_NONE && b > p.ps) {  // fire.py:568 (strict); tested for every candidate
         const int code = 1 + (m.t % Cell<CellT>::M);
         reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(ST_BURNING | (code << 3));  // fire.py:571-587
+        return true;
     }
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -287,6 +315,10 @@ struct SweepWarp {
             }
             bool push = false;
             int dir = DIR_NONE;
+            if (p.track && owner && (cc >> 3) != 0 && kc == NO_SRC) {
+                push = true;
+                dir = DIR_PRUNED;
+            }
             if (owner && spread && ignitable(s)) {
                 if (best < NO_SRC) {
                     dir = (0x12304765u >> ((best & 7) * 4)) & 0xF;  // rank -> direction of fire.py:211-221
@@ -625,15 +657,27 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
     if (p.overflow[par]) {
         const long long total = (long long)p.E * p.plane;
         for (long long i = gid; i < total; i += gstride) dense_cell<CellT>(p, par, i);
+        if (p.track && gid == 0) *p.chg_overflow = 1;  // the dense pass does not log: force a full resync
     } else {
         const long long n = (long long)p.qcount[par];
-        for (long long i = gid; i < n; i += gstride) {
-            const unsigned long long it = p.queue[i];
-            const long long idx = (long long)(it & 0xFFFFFFFFFFFFull);
-            const int dir = (int)((it >> 48) & 0xF), s = (int)((it >> 52) & 7);
-            const int env = (int)(idx / p.plane);
-            const EnvMeta m = p.meta[(long long)par * p.E + env];
-            process_item<CellT>(p, m, env, idx, dir, s);
+        const int lane = threadIdx.x & 31;
+        for (long long base = gid - lane; base < n; base += gstride) {  // warp-uniform trip count
+            const long long i = base + lane;
+            long long idx = 0;
+            int logged = -1;
+            if (i < n) {
+                const unsigned long long it = p.queue[i];
+                idx = (long long)(it & 0xFFFFFFFFFFFFull);
+                const int dir = (int)((it >> 48) & 0xF), s = (int)((it >> 52) & 7);
+                if (dir == DIR_PRUNED) {
+                    logged = 2;  // BurnStatus.BURNED
+                } else {
+                    const int env = (int)(idx / p.plane);
+                    const EnvMeta m = p.meta[(long long)par * p.E + env];
+                    if (process_item<CellT>(p, m, env, idx, dir, s)) logged = 1;  // BurnStatus.BURNING
+                }
+            }
+            if (p.track) log_append(p, logged >= 0, idx, logged);
         }
     }
 

@@ -54,6 +54,7 @@ class FireEngine:
         queue_capacity: int = 0,
         wide_cells: bool = False,
         sweep_ldg: bool = False,
+        track_changes: bool = False,
     ) -> None:
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -69,6 +70,7 @@ class FireEngine:
         flags |= _lib.HAS_MAX_TIME if max_time is not None else 0
         flags |= _lib.WIDE_CELLS if wide_cells else 0
         flags |= _lib.SWEEP_LDG if sweep_ldg else 0
+        flags |= _lib.TRACK_CHANGES if track_changes else 0
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -175,6 +177,19 @@ class FireEngine:
             out = np.empty((n, self.H, self.W), dtype=np.int8)
         _lib.check(self._lib.sfb_get_fire_map(self._h, int(env0), int(n), _ptr(out)))
         return out
+
+    def sync_fire_maps(self, mirror: np.ndarray) -> int:
+        """
+        Bring the caller's host mirror (int8 [E, H, W], C-contiguous, the same array on every
+        call, not modified in between) up to date.  With `track_changes=True` only the cells
+        that changed since the previous call cross PCIe.  Returns the number of patched cells
+        (-1: everything was downloaded).
+        """
+        if mirror.dtype != np.int8 or not mirror.flags.c_contiguous or mirror.size != self.E * self.H * self.W:
+            raise ValueError("sync_fire_maps: mirror must be a C-contiguous int8 array of E*H*W cells")
+        n = C.c_int64()
+        _lib.check(self._lib.sfb_sync_fire_maps(self._h, _ptr(mirror), C.byref(n)))
+        return int(n.value)
 
     def plane(self, which: str, env: int = 0) -> np.ndarray:
         pid, dt = {"burn": (_lib.PLANE_BURN, np.float64), "ros": (_lib.PLANE_ROS, np.float64),

@@ -206,8 +206,9 @@ class BatchedFireSimulation:
                  initial_positions: Optional[Sequence[Tuple[int, int]]] = None) -> None:  # fmt: skip
         self.config = config
         self.num_envs = int(num_envs)
-        self._engine = _engine_from_config(config, self.num_envs, device, shared_static=True)
+        self._engine = _engine_from_config(config, self.num_envs, device, shared_static=True, track_changes=True)
         self._planes, self._elevations = _static_planes(config)
+        self._mirror: Optional[np.ndarray] = None
         self._engine.set_static(self._planes)
         pos = initial_positions if initial_positions is not None else [config.fire.fire_initial_position] * self.num_envs
         self._engine.reset(pos)
@@ -242,9 +243,16 @@ class BatchedFireSimulation:
         else:
             total_updates = int(time)
         self._engine.step(total_updates, sync=False)
-        maps = self._engine.fire_map(0, self.num_envs, out=out)
+        if out is None:
+            if self._mirror is None:
+                H, W = self.config.area.screen_size
+                self._mirror = np.empty((self.num_envs, H, W), dtype=np.int8)
+            out = self._mirror
+        # the same array is returned (updated in place) on every call, like the reference's
+        # fire_map; only the cells that changed since the previous call cross PCIe
+        self._engine.sync_fire_maps(out)
         st, _, _ = self._engine.status()
-        return maps, st == GameStatus.RUNNING
+        return out, st == GameStatus.RUNNING
 
     def fire_maps_device(self):
         return self._engine.fire_map_device()

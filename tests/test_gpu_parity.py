@@ -188,6 +188,47 @@ def test_update_with_host_maps():
                 assert np.array_equal(fm, sc["maps"][map_at[step]]), f"step {step}"
 
 
+@pytest.mark.parametrize("shape", [(64, 64), (50, 70)])  # pitch == W and pitch > W
+def test_incremental_host_mirror_matches_full_download(shape):
+    """sfb_sync_fire_maps: patching a host mirror from the device change log must give the
+    same maps as downloading them, across steps, mitigation, resets and map replacement."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    H, W = shape
+    wl = synthetic_operational(H, W, seed=5, patch=8)
+    E = 6
+    rng = np.random.default_rng(3)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True)
+    with FireEngine(H, W, E, shared_static=True, track_changes=True, **kw) as eng:
+        eng.set_static(wl.planes)
+        eng.reset(wl.burnable_starts(E, seed=2, margin=4))
+        mirror = np.full((E, H, W), 77, dtype=np.int8)
+        assert eng.sync_fire_maps(mirror) == -1  # first call: full download
+        assert np.array_equal(mirror, eng.fire_map())
+        patched = 0
+        for it in range(40):
+            if it % 3 == 0:
+                pts = np.stack([rng.integers(0, E, 9), rng.integers(0, W, 9), rng.integers(0, H, 9),
+                                rng.integers(3, 6, 9)], axis=1)  # fmt: skip
+                eng.apply_points(pts)
+            if it == 17:
+                eng.reset(wl.burnable_starts(2, seed=9, margin=4), envs=[1, 4])
+            eng.step(int(rng.integers(1, 4)))
+            if it == 25:
+                eng.set_fire_map(eng.fire_map(2, 1), env0=2)  # wholesale replacement -> full resync
+                assert eng.sync_fire_maps(mirror) == -1
+            else:
+                n = eng.sync_fire_maps(mirror)
+                assert n >= 0
+                patched += n
+            assert np.array_equal(mirror, eng.fire_map()), f"iteration {it}"
+        assert patched > 100
+        other = np.zeros_like(mirror)
+        assert eng.sync_fire_maps(other) == -1  # a different buffer cannot be patched
+        assert np.array_equal(other, mirror)
+
+
 def test_observation_tensor_matches_host_map():
     import torch
 
