@@ -192,6 +192,37 @@ int sfb_get_status(sfb_sim* sim, int32_t* status, double* elapsed, int32_t* step
  * synchronises the stream before returning). */
 int sfb_fire_map_device(sfb_sim* sim, void** dev);
 
+/* ---- slab mode: one large grid split in horizontal slabs across handles / GPUs ----------
+ * Each handle is created with slab_y0 / slab_total_H and holds rows [slab_y0, slab_y0 + H).
+ * The sweep kernel reads the row above / below its slab straight from the neighbour slab's
+ * state plane (peer device memory over NVLink when the slabs live on different GPUs), so
+ * there is no halo copy; what must be coordinated per step is
+ *     (all slabs finished step t-1)  ->  sfb_step_sweep on every slab
+ *     OR of the per-env flags across slabs (sfb_flags_device, an all-reduce MAX of int32)
+ *     ->  sfb_step_eval on every slab.
+ * simfire_b200/slab.py does this with torch.distributed (one process per GPU). */
+
+/* Device pointer and geometry of the packed state plane [E][H][pitch] of this handle. */
+int sfb_state_device(sfb_sim* sim, void** state, int64_t* plane_cells, int32_t* pitch_cells, int32_t* cell_bytes);
+/* CUDA IPC handle (64 bytes) of the state plane, to be opened in the neighbours' processes. */
+int sfb_ipc_export(sfb_sim* sim, void* handle64);
+int sfb_ipc_open(int32_t device, const void* handle64, void** dev_ptr);
+int sfb_ipc_close(int32_t device, void* dev_ptr);
+/* top_row: device pointer to row (slab_y0 - 1) of env 0 inside the slab above (NULL: grid
+ * edge); top_plane_cells: per-env stride of that slab's plane; same for the slab below. */
+int sfb_set_halo(sfb_sim* sim, const void* top_row, int64_t top_plane_cells, const void* bottom_row,
+                 int64_t bottom_plane_cells);
+/* The two halves of sfb_step. */
+int sfb_step_sweep(sfb_sim* sim);
+int sfb_step_eval(sfb_sim* sim);
+/* int32 view of the EnvMeta records of the step in flight (valid between sfb_step_sweep and
+ * sfb_step_eval): 8 int32 per env; an element-wise MAX across slabs ORs any_live / any_cand
+ * and leaves the other fields (identical on every slab) unchanged. */
+int sfb_flags_device(sfb_sim* sim, void** flags, int64_t* n_int32);
+/* Run the handle's work on the caller's stream (cudaStream_t as void*), e.g. the stream a
+ * communication library orders its collectives on.  NULL restores the handle's own stream. */
+int sfb_set_stream(sfb_sim* sim, void* stream);
+
 /* ---- introspection (bench / profiling) -------------------------------------------- */
 
 /* cudaStream_t of the handle, as void*. */

@@ -23,7 +23,8 @@ EXPORTS = (
     "sfb_step_timed", "sfb_update", "sfb_synchronize", "sfb_get_fire_map", "sfb_get_plane",
     "sfb_get_status", "sfb_fire_map_device", "sfb_get_stream", "sfb_get_launch_counts",
     "sfb_set_kernel_timing", "sfb_get_kernel_ms", "sfb_get_queue_stats", "sfb_device_bytes",
-    "sfb_rate_of_spread", "sfb_sync_fire_maps",
+    "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
+    "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
 )  # fmt: skip
 
 
@@ -76,6 +77,15 @@ def load() -> C.CDLL:
         "sfb_get_fire_map": (C.c_int, [vp, i32, i32, vp]),
         "sfb_get_plane": (C.c_int, [vp, i32, i32, vp]),
         "sfb_sync_fire_maps": (C.c_int, [vp, vp, C.POINTER(i64)]),
+        "sfb_state_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+        "sfb_ipc_export": (C.c_int, [vp, vp]),
+        "sfb_ipc_open": (C.c_int, [i32, vp, C.POINTER(vp)]),
+        "sfb_ipc_close": (C.c_int, [i32, vp]),
+        "sfb_set_halo": (C.c_int, [vp, vp, i64, vp, i64]),
+        "sfb_step_sweep": (C.c_int, [vp]),
+        "sfb_step_eval": (C.c_int, [vp]),
+        "sfb_flags_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "sfb_set_stream": (C.c_int, [vp, vp]),
         "sfb_get_status": (C.c_int, [vp, vp, vp, vp]),
         "sfb_fire_map_device": (C.c_int, [vp, C.POINTER(vp)]),
         "sfb_get_stream": (C.c_int, [vp, C.POINTER(vp)]),

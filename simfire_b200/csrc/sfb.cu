@@ -49,8 +49,10 @@ struct sfb_sim {
     int sweep_blocks; // persistent grid of the sweep kernel
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
+    int in_step;      // sfb_step_sweep done, sfb_step_eval pending
     int n_sm;
-    cudaStream_t stream;
+    cudaStream_t stream;      // stream in use
+    cudaStream_t own_stream;  // created by the handle
     cudaEvent_t ev[3];
     // scratch
     void* stage;          // device staging for host <-> device plane traffic
@@ -291,6 +293,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     if (!s) return;
     cudaSetDevice(s->prm.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    s->stream = s->own_stream;
     cudaFree(s->d.state);
     cudaFree(s->d.burn);
     cudaFree(s->d.ros);
@@ -320,7 +323,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, prm->device));
     s->n_sm = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
     for (auto& e : s->ev) CU(cudaEventCreate(&e));
 
     DevParams& d = s->d;
@@ -634,7 +638,7 @@ extern "C" int sfb_set_fire_map(sfb_sim* s, int32_t env0, int32_t n, const int8_
 // ---------------------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------------------
-static int enqueue_step(sfb_sim* s) {
+static int enqueue_sweep(sfb_sim* s) {
     const DevParams& d = s->d;
     const int par = s->parity;
     if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
@@ -647,13 +651,22 @@ static int enqueue_step(sfb_sim* s) {
         DISPATCH(s, k_sweep_ldg, (unsigned)s->sweep_blocks, SWEEP_WARPS * 32, d, par);
     }
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
+    s->launches_step += 1;
+    s->in_step = 1;
+    return 0;
+}
+
+static int enqueue_eval(sfb_sim* s) {
+    const DevParams& d = s->d;
+    const int par = s->parity;
     if (d.keep_ros) {
         k_clear_ros<<<cap_grid(s, (long long)d.E * d.plane, 256), 256, 0, s->stream>>>(d, par);
         s->launches_all++;
     }
     DISPATCH(s, k_eval, (unsigned)(s->n_sm * 8), 256, d, par);
-    s->launches_step += 2;
+    s->launches_step += 1;
     s->parity ^= 1;
+    s->in_step = 0;
     if (s->timing) {
         CU(cudaEventRecord(s->ev[2], s->stream));
         CU(cudaEventSynchronize(s->ev[2]));
@@ -664,6 +677,99 @@ static int enqueue_step(sfb_sim* s) {
         s->eval_ms += b;
         s->timed_steps++;
     }
+    return 0;
+}
+
+static int enqueue_step(sfb_sim* s) {
+    if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
+    int rc = enqueue_sweep(s);
+    return rc ? rc : enqueue_eval(s);
+}
+
+extern "C" int sfb_step_sweep(sfb_sim* s) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_step_sweep: null handle");
+    if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_sweep: the previous sweep has not been evaluated");
+    int rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = enqueue_sweep(s))) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sfb_step_eval(sfb_sim* s) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_step_eval: null handle");
+    if (!s->in_step) return fail(SFB_ERR_STATE, "sfb_step_eval: no sweep in flight");
+    int rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = enqueue_eval(s))) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sfb_flags_device(sfb_sim* s, void** flags, int64_t* n_int32) {
+    if (!s || !flags || !n_int32) return fail(SFB_ERR_INVALID, "sfb_flags_device: null argument");
+    *flags = (void*)(s->d.meta + (size_t)s->parity * s->d.E);
+    *n_int32 = (int64_t)s->d.E * (int64_t)(sizeof(EnvMeta) / sizeof(int32_t));
+    return 0;
+}
+
+extern "C" int sfb_set_stream(sfb_sim* s, void* stream) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_set_stream: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    return 0;
+}
+
+extern "C" int sfb_state_device(sfb_sim* s, void** state, int64_t* plane_cells, int32_t* pitch_cells, int32_t* cell_bytes) {
+    if (!s || !state) return fail(SFB_ERR_INVALID, "sfb_state_device: null argument");
+    *state = s->d.state;
+    if (plane_cells) *plane_cells = s->d.plane;
+    if (pitch_cells) *pitch_cells = s->d.pitch;
+    if (cell_bytes) *cell_bytes = s->cell_bytes;
+    return 0;
+}
+
+extern "C" int sfb_ipc_export(sfb_sim* s, void* handle64) {
+    if (!s || !handle64) return fail(SFB_ERR_INVALID, "sfb_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int rc;
+    if ((rc = use(s))) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->d.state));
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int sfb_ipc_open(int32_t device, const void* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return fail(SFB_ERR_INVALID, "sfb_ipc_open: null argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int sfb_ipc_close(int32_t device, void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+extern "C" int sfb_set_halo(sfb_sim* s, const void* top_row, int64_t top_plane_cells, const void* bottom_row,
+                            int64_t bottom_plane_cells) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_set_halo: null handle");
+    if (s->use_tma && (top_row || bottom_row))
+        return fail(SFB_ERR_STATE, "sfb_set_halo: the handle was not created in slab mode (slab_total_H = 0)");
+    int rc;
+    if ((rc = use(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->d.halo_top = top_row;
+    s->d.halo_top_plane = top_plane_cells;
+    s->d.halo_bottom = bottom_row;
+    s->d.halo_bottom_plane = bottom_plane_cells;
     return 0;
 }
 

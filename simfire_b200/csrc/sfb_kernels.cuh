@@ -78,6 +78,7 @@ struct DevParams {
     // slab mode: rows -1 and H of this slab live in a neighbour slab (peer device memory)
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
+    int64_t halo_top_plane, halo_bottom_plane;  // per-env stride (cells) of those neighbour planes
     const void* filler;       // (pitch + 2 * 16) BURNED cells: stands in for rows outside the grid
     // change log (SFB_TRACK_CHANGES)
     int32_t track;
@@ -542,8 +543,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
 
     // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
     auto edge_row = [&](int y) -> const CellT* {
-        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + sw.env_off;
-        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + sw.env_off;
+        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
+        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
         return filler;
     };
     auto issue = [&](const CellT* rowp, RowRegs& r) {
@@ -628,8 +629,8 @@ __device__ void dense_cell(const DevParams& p, const int par, long long idx) {
         if (xx < 0 || xx >= p.W) return;
         const CellT* rowp;
         if (yy >= 0 && yy < p.H) rowp = st + (long long)env * p.plane + (long long)yy * p.pitch;
-        else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.plane;
-        else if (yy == p.H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.plane;
+        else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
+        else if (yy == p.H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
         else return;
         const int nc = (int)rowp[xx] >> 3;
         if (nc) {

@@ -55,6 +55,8 @@ class FireEngine:
         wide_cells: bool = False,
         sweep_ldg: bool = False,
         track_changes: bool = False,
+        slab_y0: int = 0,
+        slab_total_H: int = 0,
     ) -> None:
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -78,7 +80,7 @@ class FireEngine:
             pixel_scale=float(pixel_scale), update_rate=float(update_rate),
             max_time=float(max_time) if max_time is not None else 0.0,
             h=h, S_T=S_T, S_e=S_e, p_p=p_p, M_f=float(M_f), reserved0=0,
-            queue_capacity=int(queue_capacity), slab_y0=0, slab_total_H=0,
+            queue_capacity=int(queue_capacity), slab_y0=int(slab_y0), slab_total_H=int(slab_total_H),
         )  # fmt: skip
         _lib.check(self._lib.sfb_create(C.byref(prm), C.byref(self._h)))
 
@@ -220,6 +222,66 @@ class FireEngine:
             }  # fmt: skip
 
         return torch.as_tensor(_Iface(), device=f"cuda:{self.device}")
+
+    # -- slab mode (one grid split in row slabs across engines / GPUs) ---------------------
+    def state_device(self):
+        """(device pointer, plane cells, pitch cells, bytes per cell) of the packed state plane."""
+        ptr, plane, pitch, cb = C.c_void_p(), C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.sfb_state_device(self._h, C.byref(ptr), C.byref(plane), C.byref(pitch), C.byref(cb)))
+        return int(ptr.value), int(plane.value), int(pitch.value), int(cb.value)
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.sfb_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        _lib.check(self._lib.sfb_ipc_open(self.device, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        _lib.check(self._lib.sfb_ipc_close(self.device, C.c_void_p(ptr)))
+
+    def set_halo(self, top_row: int, top_plane: int, bottom_row: int, bottom_plane: int) -> None:
+        _lib.check(self._lib.sfb_set_halo(self._h, C.c_void_p(top_row or None), int(top_plane),
+                                          C.c_void_p(bottom_row or None), int(bottom_plane)))  # fmt: skip
+
+    def step_sweep(self) -> None:
+        _lib.check(self._lib.sfb_step_sweep(self._h))
+
+    def step_eval(self) -> None:
+        _lib.check(self._lib.sfb_step_eval(self._h))
+
+    def flags_tensors(self):
+        """Two int32 CUDA tensors [E, 8] viewing the double-buffered per-env records; index
+        them with `self.flags_parity()`.  MAX-reducing the one in flight across slabs ORs the
+        any_live / any_cand flags."""
+        import torch
+
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.sfb_flags_device(self._h, C.byref(p), C.byref(n)))
+        cur = int(p.value)
+        nbytes = int(n.value) * 4
+        base = cur - nbytes if self._parity_probe() else cur
+        out = []
+        for k in range(2):
+            class _Iface:
+                __cuda_array_interface__ = {"shape": (self.E, 8), "typestr": "<i4", "data": (base + k * nbytes, False),
+                                            "version": 3, "strides": None}  # fmt: skip
+            out.append(torch.as_tensor(_Iface(), device=f"cuda:{self.device}"))
+        return out
+
+    def _parity_probe(self) -> int:
+        # parity = number of completed steps mod 2 (every handle starts at 0)
+        _, step_kernels = self.launch_counts()
+        return (step_kernels // 2) % 2
+
+    def flags_parity(self) -> int:
+        return self._parity_probe()
+
+    def set_stream(self, stream: int) -> None:
+        _lib.check(self._lib.sfb_set_stream(self._h, C.c_void_p(stream or None)))
 
     # -- introspection --------------------------------------------------------------------
     @property

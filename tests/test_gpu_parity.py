@@ -255,3 +255,38 @@ def test_errors_are_reported():
             eng.plane("ros")
         with pytest.raises(ValueError):
             eng.set_static({k: np.zeros((3, 3)) for k in ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")})
+
+
+@pytest.mark.parametrize("n_slabs,ldg_single", [(2, False), (3, True)])
+def test_row_slabs_equal_single_grid(n_slabs, ldg_single):
+    """Slab mode (cfg5) on one GPU: the grid split in row slabs, each slab an engine that reads
+    its neighbours' edge rows through the halo pointers, must evolve exactly like one engine
+    holding the whole grid -- including the env-wide flags (QUIT, early return, attenuation of
+    untouched control lines) that are OR-ed across slabs every step."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.slab import SlabGrid
+    from simfire_b200.workloads import synthetic_operational
+
+    H, W, E = 101, 160, 2
+    wl = synthetic_operational(H, W, seed=8, patch=8)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True, max_time=70.0)
+    starts = [(80, 49), (30, 52)]  # next to the slab boundaries
+    lines = [(e, x, y, 3 + (x % 3)) for e in range(E) for y in (20, 51, 75) for x in range(10, 150, 2)]
+    grid = SlabGrid(H, W, wl.planes, n_slabs=n_slabs, E=E, **kw)
+    with FireEngine(H, W, E, sweep_ldg=ldg_single, **kw) as ref:
+        ref.set_static(wl.planes, env=-1)
+        ref.reset(starts)
+        ref.apply_points(lines)
+        grid.reset(starts)
+        grid.apply_points(lines)
+        for it in range(30):
+            n = 1 + it % 3
+            ref.step(n)
+            grid.step(n)
+            assert np.array_equal(grid.fire_map(), ref.fire_map()), f"step block {it}"
+            a, b = grid.status(), ref.status()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), it
+        assert (ref.fire_map() == 2).sum() > 500
+        burn = np.concatenate([e.plane("burn", 1) for e in grid.engines], axis=0)
+        assert np.array_equal(burn, ref.plane("burn", 1))
+    grid.close()
