@@ -212,6 +212,20 @@ struct SweepWarp {
     static constexpr int RS = WR + 2 * CPL;  // staged row, in cells (544 bytes)
     static constexpr int SEG_PER_GROUP = 32 / CPL;
     static constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
+    static constexpr int GW = 30, NG = (WR + GW - 1) / GW;  // detail_row visits groups of 30 owned cells
+
+    // seg_lut[L]: the groups whose columns [30g - 1, 30g + 30] overlap lane L's segment (the pad
+    // cells count as part of segments 0 / 31).  Filled once per (persistent) warp.
+    static __device__ __forceinline__ void build_seg_lut(uint32_t* lut, int lane) {
+        uint32_t m = 0;
+        for (int g = 0; g < NG; ++g) {
+            const int lo = (GW * g - 1) < 0 ? 0 : (GW * g - 1) / CPL;
+            const int hi = (GW * g + GW) / CPL > 31 ? 31 : (GW * g + GW) / CPL;
+            if (lane >= lo && lane <= hi) m |= 1u << g;
+        }
+        lut[lane] = m;
+        __syncwarp();
+    }
 
     const DevParams& p;
     int par, lane, env, x0, y_end, tm1, max_dur;
@@ -219,12 +233,13 @@ struct SweepWarp {
     long long env_off;
     uint32_t look_mask;
     unsigned long long* wq;
+    const uint32_t* seg_lut;
     int wcount = 0;  // warp-uniform
     int f_live = 0, f_cand = 0;
 
     __device__ __forceinline__ SweepWarp(const DevParams& p_, int par_, int lane_, int env_, int strip, int chunk,
-                                         const EnvMeta& m, unsigned long long* wq_)
-        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_) {
+                                         const EnvMeta& m, unsigned long long* wq_, const uint32_t* lut_)
+        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_), seg_lut(lut_) {
         x0 = strip * WR;
         y_end = min((chunk + 1) * p.rows_per_chunk, p.H);
         tm1 = (m.t - 1) % C::M;
@@ -276,17 +291,9 @@ struct SweepWarp {
     // smallest duration first, then south before north and east before west.  Folding that
     // rank into the low bits of the key turns the selection into a warp-shuffle min.
     __device__ __forceinline__ void detail_row(int y, const CellT* rp, const CellT* rc, const CellT* rn, uint32_t act) {
-        constexpr int GW = 30, NG = (WR + GW - 1) / GW;
         CellT* const state = reinterpret_cast<CellT*>(p.state);
         uint32_t groups = 0;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            // segments overlapped by columns [30g - 1, 30g + 30]; the pads count as segments 0 / 31
-            const int lo = (GW * g - 1) < 0 ? 0 : (GW * g - 1) / CPL;
-            const int hi = (GW * g + GW) / CPL > 31 ? 31 : (GW * g + GW) / CPL;
-            const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            if (act & m) groups |= 1u << g;
-        }
+        for (uint32_t a = act; a; a &= a - 1) groups |= seg_lut[__ffs(a) - 1];  // warp-uniform
         while (groups) {  // warp-uniform
             const int g = __ffs(groups) - 1;
             groups &= groups - 1;
@@ -365,7 +372,10 @@ __device__ __forceinline__ bool next_unit(const DevParams& p, int par, int lane,
 }
 
 // ---- front end 1: TMA ring --------------------------------------------------------------
-constexpr int TMA_BOX_ROWS = 8;                      // rows per TMA box
+#ifndef SFB_TMA_BOX_ROWS
+#define SFB_TMA_BOX_ROWS 8
+#endif
+constexpr int TMA_BOX_ROWS = SFB_TMA_BOX_ROWS;       // rows per TMA box
 #ifndef SFB_TMA_STAGES
 #define SFB_TMA_STAGES 3
 #endif
@@ -373,7 +383,7 @@ constexpr int TMA_STAGES = SFB_TMA_STAGES;           // boxes in the per-warp ri
 constexpr int TMA_ROW_BYTES = 544;                   // 16 B pad | 512 B | 16 B pad
 constexpr int TMA_BOX_BYTES = TMA_BOX_ROWS * TMA_ROW_BYTES;
 constexpr int TMA_RING_ROWS = TMA_BOX_ROWS * TMA_STAGES;
-constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128;  // ring | work items | mbarriers
+constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128 + 128;  // ring | work items | mbarriers | seg_lut
 static_assert(TMA_WARP_SMEM % 128 == 0 && TMA_BOX_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
 constexpr int TMA_BLOCK_SMEM = SWEEP_WARPS * TMA_WARP_SMEM + 128;              // + alignment slack
 
@@ -419,7 +429,9 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
     CellT* const ring = reinterpret_cast<CellT*>(base);
     unsigned long long* const wq = reinterpret_cast<unsigned long long*>(base + NR * TMA_ROW_BYTES);
     const uint32_t bar0 = smem_u32(base + NR * TMA_ROW_BYTES + WQ_CAP * 8);
+    uint32_t* const seg_lut = reinterpret_cast<uint32_t*>(base + NR * TMA_ROW_BYTES + WQ_CAP * 8 + 128);
     const uint32_t ring_u32 = smem_u32(ring);
+    SW::build_seg_lut(seg_lut, lane);
 
     if (lane == 0) {
         for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -434,7 +446,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
         EnvMeta* const mp = p.meta + (long long)par * p.E + env;
         const EnvMeta m = *mp;
         if (!m.running) continue;
-        SW sw(p, par, lane, env, strip, chunk, m, wq);
+        SW sw(p, par, lane, env, strip, chunk, m, wq, seg_lut);
         const int y_begin = chunk * p.rows_per_chunk;
         const int n_rows = sw.y_end - y_begin;           // rows this unit owns
         const int n_box = (n_rows + 2 + B - 1) / B;      // local row j <-> grid row y_begin - 1 + j
@@ -464,7 +476,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
                 const bool a = (((v.x | v.y) | (v.z | v.w)) & sw.look_mask) != 0;
                 if (__any_sync(0xffffffffu, a)) nz |= 4u << i;
             }
-            {   // cells just outside the strip: lanes 0-7 the left pad of row `lane`, 8-15 the right pad of row lane-8
+            if (p.strips > 1) {  // cells just outside the strip: lanes 0..B-1 the left pad of row `lane`, B..2B-1 the right pad
                 uint32_t hw = 0;
                 if (lane < 2 * B) {
                     const unsigned char* rowb = reinterpret_cast<const unsigned char*>(box + (lane & (B - 1)) * RS);
@@ -490,8 +502,10 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
                 const uint4 vc = *reinterpret_cast<const uint4*>(rc + CPL + lane * CPL);
                 const uint4 vn = *reinterpret_cast<const uint4*>(rn + CPL + lane * CPL);
                 uint32_t hcell = 0;
-                if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
-                if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
+                if (p.strips > 1) {  // otherwise both pads are out of the grid (zero-filled)
+                    if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
+                    if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
+                }
                 const uint4 vo = make_uint4(vp.x | vc.x | vn.x, vp.y | vc.y | vn.y, vp.z | vc.z | vn.z, vp.w | vc.w | vn.w);
                 const uint32_t act = __ballot_sync(0xffffffffu, sw.seg_needs_look(vo, hcell));
                 sw.detail_row(y_begin - 1 + j, rp, rc, rn, act);
@@ -519,8 +533,10 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
     constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
     __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
     __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
+    __shared__ uint32_t lut_all[SWEEP_WARPS][32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SW::build_seg_lut(lut_all[warp], lane);
     const int H = p.H, pitch = p.pitch;
     const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
     CellT(*sm)[RS] = sm_all[warp];
@@ -530,7 +546,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
     EnvMeta* const mp = p.meta + (long long)par * p.E + env;
     const EnvMeta m = *mp;
     if (!m.running) continue;
-    SW sw(p, par, lane, env, strip, chunk, m, wq_all[warp]);
+    SW sw(p, par, lane, env, strip, chunk, m, wq_all[warp], lut_all[warp]);
     const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + sw.env_off;
     const int x0 = sw.x0;
     const int xl = x0 + lane * CPL;

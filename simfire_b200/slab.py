@@ -39,9 +39,11 @@ class SlabGrid:
         mine = [self.ctx.rank] if self.distributed else list(range(world))
         self.engines: List[FireEngine] = []
         self.my_slabs = mine
+        single = world == 1  # one slab = the whole grid: an ordinary engine (TMA sweep, no coordination)
         for i in mine:
             y0, h = self.slabs[i]
-            eng = FireEngine(h, W, E, device=device, slab_y0=y0, slab_total_H=self.total_H, **engine_kwargs)
+            eng = FireEngine(h, W, E, device=device, slab_y0=0 if single else y0,
+                             slab_total_H=0 if single else self.total_H, **engine_kwargs)  # fmt: skip
             eng.set_static({k: np.broadcast_to(np.asarray(v, dtype=np.float64), (self.total_H, W))[y0 : y0 + h]
                             for k, v in planes.items()})  # fmt: skip
             self.engines.append(eng)
@@ -116,6 +118,10 @@ class SlabGrid:
     def _step_local(self, n: int) -> None:
         import torch
 
+        if len(self.engines) == 1:
+            self.engines[0].step(n)
+            self._steps += n
+            return
         for _ in range(n):
             par = self._steps % 2
             for e in self.engines:
@@ -153,6 +159,9 @@ class SlabGrid:
         import torch
 
         if not self.distributed:
+            if len(self.engines) == 1:
+                self._steps += n
+                return self.engines[0].step_timed(n)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
