@@ -321,6 +321,8 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     ctx = RankContext.from_env(backend="nccl", device_id=torch.device("cuda", local))
     rank, world = ctx.rank, ctx.world
+    # host threads that patch the fire_map mirror: share the box's cores between the ranks
+    os.environ.setdefault("SFB_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
 
     wl, E, shared = make_workload(args.workload)
     if args.envs:

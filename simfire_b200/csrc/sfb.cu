@@ -8,6 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -37,6 +41,68 @@ static int fail(int code, const char* fmt, ...) {
             return fail(_e == cudaErrorMemoryAllocation ? SFB_ERR_NOMEM : SFB_ERR_CUDA,           \
                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+// ---------------------------------------------------------------------------------------
+// host worker pool (patching the host mirror from the change log)
+// ---------------------------------------------------------------------------------------
+class HostPool {
+  public:
+    explicit HostPool(unsigned n) : n_(std::max(1u, n)) {
+        for (unsigned t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    unsigned size() const { return n_; }
+    // runs fn(t) for t in [0, size()) and returns when all are done
+    void run(const std::function<void(unsigned)>& fn) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void loop(unsigned t) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(unsigned)>* fn;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(t);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    unsigned n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned)>* fn_ = nullptr;
+    unsigned pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
 
 // ---------------------------------------------------------------------------------------
 // handle
@@ -73,6 +139,10 @@ struct sfb_sim {
     int full_resync;           // something changed that the log does not describe
     unsigned long long* log_host;  // pinned staging for the change log
     size_t log_host_entries;
+    unsigned long long* log_head;  // pinned: {count, overflow} read back each sync
+    unsigned long long* log_mapped;  // the change log itself when it lives in mapped host memory
+    HostPool* pool;
+    std::vector<std::vector<unsigned long long>> buckets;  // [chunk * T + owner]
 };
 
 static int use(sfb_sim* s) {
@@ -303,10 +373,12 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.qcount);
     cudaFree(s->d.overflow);
     cudaFree(s->d.unit_next);
-    cudaFree(s->d.chg);
+    if (s->log_mapped) cudaFreeHost(s->log_mapped);
+    else cudaFree(s->d.chg);
     cudaFree(s->d.chg_count);
-    cudaFree(s->d.chg_overflow);
     if (s->log_host) cudaFreeHost(s->log_host);
+    if (s->log_head) cudaFreeHost(s->log_head);
+    delete s->pool;
     cudaFree((void*)s->d.filler);
     cudaFree(s->stage);
     cudaFree(s->obs);
@@ -383,12 +455,20 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.unit_next, 2 * sizeof(unsigned long long)))) return rc;
     d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
     if (d.track) {
-        d.chg_cap = std::max<int64_t>(1 << 20, total / 16);
-        if ((rc = dmalloc(s, &d.chg, (size_t)d.chg_cap * 8))) return rc;
-        if ((rc = dmalloc(s, &d.chg_count, sizeof(unsigned long long)))) return rc;
-        if ((rc = dmalloc(s, &d.chg_overflow, sizeof(int32_t)))) return rc;
-        CU(cudaMemsetAsync(d.chg_count, 0, sizeof(unsigned long long), s->stream));
-        CU(cudaMemsetAsync(d.chg_overflow, 0, sizeof(int32_t), s->stream));
+        // The log lives in pinned HOST memory mapped into the device address space: k_eval's
+        // warp-aggregated appends are coalesced 256-byte posted writes over PCIe, so by the time
+        // the stream is idle the entries are already on the host and no D2H copy is needed.
+        d.chg_cap = std::min<int64_t>(std::max<int64_t>(1 << 20, total / 16), (int64_t)16 << 20);
+        if (getenv("SFB_LOG_ON_DEVICE")) {
+            if ((rc = dmalloc(s, &d.chg, (size_t)d.chg_cap * 8))) return rc;
+        } else {
+            CU(cudaHostAlloc((void**)&s->log_mapped, (size_t)d.chg_cap * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU(cudaHostGetDevicePointer((void**)&d.chg, s->log_mapped, 0));
+        }
+        if ((rc = dmalloc(s, &d.chg_count, 2 * sizeof(unsigned long long)))) return rc;  // {count, overflow}
+        d.chg_overflow = reinterpret_cast<int32_t*>(d.chg_count + 1);
+        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
+        CU(cudaMallocHost((void**)&s->log_head, 2 * sizeof(unsigned long long)));
     }
     CU(cudaMemsetAsync(d.unit_next, 0, 2 * sizeof(unsigned long long), s->stream));
     {
@@ -853,42 +933,75 @@ extern "C" int sfb_get_fire_map(sfb_sim* s, int32_t env0, int32_t n, int8_t* out
 }
 
 // Patch entries [0, n) of the change log into the host mirror.  Entries of one cell are in
-// time order in the log; each thread owns a contiguous range of envs and walks the whole log,
-// so the order is preserved without any synchronisation.
-static void apply_log(const sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror) {
+// time order in the log and must be applied in that order.  Two passes on T pool threads:
+// (1) thread k splits chunk k of the log into T buckets by owner (owner = contiguous range of
+// cell indices), keeping the order; (2) owner o applies bucket (0, o), (1, o), ... in chunk
+// order.  Each entry is touched twice in total, whatever T is.
+static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror) {
     const DevParams& d = s->d;
     const long long hw = (long long)d.H * d.W;
     const bool linear = d.pitch == d.W;
-    unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-    nt = (unsigned)std::min<long long>(nt, std::max<long long>(1, n / 4096));
-    nt = std::min<unsigned>(nt, (unsigned)d.E);
-    auto work = [&](unsigned t) {
-        const long long e_lo = (long long)d.E * t / nt, e_hi = (long long)d.E * (t + 1) / nt;
-        const unsigned long long lo = (unsigned long long)(e_lo * d.plane), hi = (unsigned long long)(e_hi * d.plane);
-        for (long long i = 0; i < n; ++i) {
-            const unsigned long long e = log[i];
-            const unsigned long long idx = e & 0xFFFFFFFFFFFFull;
-            const int st = (int)(e >> 48) & 7;
-            if (st == LOG_ENV_RESET) {
-                if ((long long)idx >= e_lo && (long long)idx < e_hi) memset(mirror + idx * hw, 0, (size_t)hw);
-            } else if (idx >= lo && idx < hi) {
-                if (linear) {
-                    mirror[idx] = (int8_t)st;
-                } else {
-                    const long long env = (long long)(idx / d.plane), rem = (long long)(idx - env * d.plane);
-                    mirror[env * hw + (rem / d.pitch) * d.W + rem % d.pitch] = (int8_t)st;
-                }
-            }
+    const unsigned long long total = (unsigned long long)d.E * (unsigned long long)d.plane;
+    auto put = [&](unsigned long long idx, int st) {
+        if (linear) {
+            mirror[idx] = (int8_t)st;
+        } else {
+            const long long env = (long long)(idx / d.plane), rem = (long long)(idx - env * d.plane);
+            mirror[env * hw + (rem / d.pitch) * d.W + rem % d.pitch] = (int8_t)st;
         }
     };
-    if (nt <= 1) {
-        work(0);
+    auto clear_env_part = [&](long long env, unsigned long long lo, unsigned long long hi) {
+        // rows of `env` whose cells fall into the owner's range [lo, hi)
+        const unsigned long long e0 = (unsigned long long)env * d.plane;
+        const unsigned long long a = std::max(lo, e0), b = std::min(hi, e0 + (unsigned long long)d.plane);
+        if (a >= b) return;
+        if (linear) {
+            memset(mirror + a, 0, (size_t)(b - a));
+        } else {
+            for (unsigned long long i = a; i < b; ++i)
+                if ((long long)((i - e0) % d.pitch) < d.W) put(i, 0);
+        }
+    };
+    const unsigned T = (n < 16384 || !s->pool) ? 1u : s->pool->size();
+    if (T == 1) {
+        for (long long i = 0; i < n; ++i) {
+            const unsigned long long e = log[i], idx = e & 0xFFFFFFFFFFFFull;
+            const int st = (int)(e >> 48) & 7;
+            if (st == LOG_ENV_RESET) clear_env_part((long long)idx, 0, total);
+            else put(idx, st);
+        }
         return;
     }
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
+    const unsigned long long span = (total + T - 1) / T;  // cells per owner
+    if (s->buckets.size() != (size_t)T * T) s->buckets.assign((size_t)T * T, {});
+    s->pool->run([&](unsigned k) {
+        for (unsigned o = 0; o < T; ++o) s->buckets[(size_t)k * T + o].clear();
+        const long long i0 = n * k / T, i1 = n * (k + 1) / T;
+        for (long long i = i0; i < i1; ++i) {
+            const unsigned long long e = log[i], idx = e & 0xFFFFFFFFFFFFull;
+            if (((int)(e >> 48) & 7) == LOG_ENV_RESET) {
+                const unsigned long long e0 = idx * (unsigned long long)d.plane;
+                for (unsigned o = (unsigned)(e0 / span); o < T && (unsigned long long)o * span < e0 + (unsigned long long)d.plane; ++o)
+                    s->buckets[(size_t)k * T + o].push_back(e);
+            } else {
+                s->buckets[(size_t)k * T + (unsigned)(idx / span)].push_back(e);
+            }
+        }
+    });
+    s->pool->run([&](unsigned o) {
+        const unsigned long long lo = (unsigned long long)o * span, hi = std::min(total, lo + span);
+        for (unsigned k = 0; k < T; ++k)
+            for (const unsigned long long e : s->buckets[(size_t)k * T + o]) {
+                const unsigned long long idx = e & 0xFFFFFFFFFFFFull;
+                const int st = (int)(e >> 48) & 7;
+                if (st == LOG_ENV_RESET) clear_env_part((long long)idx, lo, hi);
+                else put(idx, st);
+            }
+    });
+}
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes) {
@@ -896,17 +1009,34 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     int rc;
     if ((rc = use(s))) return rc;
     DevParams& d = s->d;
+    static const bool debug = getenv("SFB_DEBUG_TIMING") != nullptr;
+    const double t0 = debug ? now_ms() : 0.0;
     unsigned long long cnt = 0;
-    int32_t ovf = 0;
+    bool ovf = false;
     if (d.track) {
-        CU(cudaMemcpyAsync(&cnt, d.chg_count, sizeof(cnt), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(&ovf, d.chg_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(s->log_head, d.chg_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
+        cnt = s->log_head[0];
+        ovf = (s->log_head[1] & 0xFFFFFFFFull) != 0;
     }
+    const double t1 = debug ? now_ms() : 0.0;
+    double t2 = t1;
     const bool full = !d.track || ovf || s->full_resync || s->mirror != mirror || cnt > (unsigned long long)d.chg_cap;
     if (full) {
         if ((rc = download_maps(s, 0, d.E, mirror))) return rc;
+        CU(cudaStreamSynchronize(s->stream));
         if (n_changes) *n_changes = -1;
+    } else if (cnt > 0 && s->log_mapped) {
+        // entries are already in host memory; patch, then let the device reuse the log
+        t2 = debug ? now_ms() : 0.0;
+        if (!s->pool) {
+            unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+            if (const char* e = getenv("SFB_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+            s->pool = new HostPool(std::min(nt, 64u));
+        }
+        apply_log(s, s->log_mapped, (long long)cnt, mirror);
+        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
+        if (n_changes) *n_changes = (int64_t)cnt;
     } else if (cnt > 0) {
         if (s->log_host_entries < cnt) {
             if (s->log_host) CU(cudaFreeHost(s->log_host));
@@ -918,18 +1048,25 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
         }
         CU(cudaMemcpyAsync(s->log_host, d.chg, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
+        // the device log may be refilled from here on: reset it before the host-side patching
+        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
+        t2 = debug ? now_ms() : 0.0;
+        if (!s->pool) {
+            unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+            if (const char* e = getenv("SFB_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+            s->pool = new HostPool(std::min(nt, 64u));
+        }
         apply_log(s, s->log_host, (long long)cnt, mirror);
         if (n_changes) *n_changes = (int64_t)cnt;
     } else if (n_changes) {
         *n_changes = 0;
     }
-    if (d.track) {
-        CU(cudaMemsetAsync(d.chg_count, 0, sizeof(unsigned long long), s->stream));
-        CU(cudaMemsetAsync(d.chg_overflow, 0, sizeof(int32_t), s->stream));
-    }
-    CU(cudaStreamSynchronize(s->stream));
+    if (d.track && (full || cnt == 0)) CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
     s->mirror = mirror;
     s->full_resync = 0;
+    if (debug)
+        fprintf(stderr, "[sfb_sync] wait+head %.3f ms, log d2h %.3f ms (%llu entries), patch %.3f ms%s\n", t1 - t0, t2 - t1,
+                cnt, now_ms() - t2, full ? " (full download)" : "");
     return 0;
 }
 
