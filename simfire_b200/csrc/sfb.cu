@@ -188,6 +188,8 @@ static int ensure_small(sfb_sim* s, size_t bytes) {
 }
 
 static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+// byte cells and no row padding: a plane is one linear run of H * W bytes
+static inline bool linear_bytes(const sfb_sim* s) { return s->cell_bytes == 1 && s->d.pitch == s->d.W; }
 
 // ---------------------------------------------------------------------------------------
 // setup / conversion kernels (not on the per-step path)
@@ -282,6 +284,48 @@ __global__ void k_get_map(DevParams p, int env0, int n, int8_t* maps) {
         const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
         const CellT c = reinterpret_cast<const CellT*>(p.state)[(long long)(env0 + k) * p.plane + (long long)y * p.pitch + x];
         maps[i] = (int8_t)to_burn_status(c & 7);
+    }
+}
+
+// 16 cells per thread; valid when cells are bytes and pitch == W (plane = H * W, multiple of 16)
+__global__ void k_get_map_v16(const uint4* __restrict__ state, uint4* __restrict__ maps, long long n16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        uint4 v = state[i];
+        auto conv = [](uint32_t w) { const uint32_t s = w & 0x07070707u; return s - ((s >> 2) & 0x01010101u); };
+        maps[i] = make_uint4(conv(v.x), conv(v.y), conv(v.z), conv(v.w));
+    }
+}
+
+__global__ void k_set_map_v16(uint4* __restrict__ state, const uint4* __restrict__ maps, long long n16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 m = maps[i];
+        uint4 v = state[i];
+        auto conv = [](uint32_t old, uint32_t e) {
+            e &= 0x07070707u;
+            const uint32_t in = e + (((e + 0x01010101u) >> 2) & 0x01010101u);  // BurnStatus -> internal
+            return (old & 0xF8F8F8F8u) | in;
+        };
+        state[i] = make_uint4(conv(v.x, m.x), conv(v.y, m.y), conv(v.z, m.z), conv(v.w, m.w));
+    }
+}
+
+// clears whole envs: state = UNBURNED, burn = 0 (ros = 0); same validity condition as above
+__global__ void k_clear_envs_v16(DevParams p, const int32_t* envs, int n, long long plane16) {
+    const long long total = (long long)n * plane16;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / plane16);
+        const long long w = i - (long long)k * plane16;
+        const long long env = envs ? envs[k] : k;
+        reinterpret_cast<uint4*>(p.state)[env * plane16 + w] = z;
+        uint4* b = reinterpret_cast<uint4*>(p.burn) + (env * plane16 + w) * 8;  // 16 cells x 8 B = 8 words
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = z;
+        if (p.ros) {
+            uint4* r = reinterpret_cast<uint4*>(p.ros) + (env * plane16 + w) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = z;
+        }
     }
 }
 
@@ -638,7 +682,12 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     int32_t* d_envs = envs ? s->small + 2 * (size_t)n : nullptr;
     CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (envs) CU(cudaMemcpyAsync(d_envs, envs, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
-    DISPATCH(s, k_clear_envs, cap_grid(s, (long long)n * d.plane, 256), 256, d, (const int32_t*)d_envs, n, 1);
+    if (linear_bytes(s) && d.plane % 16 == 0) {
+        k_clear_envs_v16<<<cap_grid(s, (long long)n * (d.plane / 16), 256), 256, 0, s->stream>>>(d, (const int32_t*)d_envs, n, d.plane / 16);
+        s->launches_all++;
+    } else {
+        DISPATCH(s, k_clear_envs, cap_grid(s, (long long)n * d.plane, 256), 256, d, (const int32_t*)d_envs, n, 1);
+    }
     DISPATCH(s, k_reset_meta, nblocks(n, 128), 128, d, s->parity, (const int32_t*)d_envs, (const int32_t*)d_xy, n,
              s->prm.slab_y0);
     CU(cudaGetLastError());
@@ -689,7 +738,13 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     int rc;
     if ((rc = ensure_stage(s, bytes))) return rc;
     CU(cudaMemcpyAsync(s->stage, maps, bytes, cudaMemcpyHostToDevice, s->stream));
-    DISPATCH(s, k_set_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (const int8_t*)s->stage);
+    if (linear_bytes(s)) {
+        k_set_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>(
+            reinterpret_cast<uint4*>((uint8_t*)d.state + (size_t)env0 * d.plane), (const uint4*)s->stage, (long long)bytes / 16);
+        s->launches_all++;
+    } else {
+        DISPATCH(s, k_set_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (const int8_t*)s->stage);
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -699,7 +754,13 @@ static int download_maps(sfb_sim* s, int env0, int n, int8_t* out) {
     const size_t bytes = (size_t)n * d.H * d.W;
     int rc;
     if ((rc = ensure_stage(s, bytes))) return rc;
-    DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (int8_t*)s->stage);
+    if (linear_bytes(s)) {
+        k_get_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>(
+            reinterpret_cast<const uint4*>((const uint8_t*)d.state + (size_t)env0 * d.plane), (uint4*)s->stage, (long long)bytes / 16);
+        s->launches_all++;
+    } else {
+        DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (int8_t*)s->stage);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, s->stage, bytes, cudaMemcpyDeviceToHost, s->stream));
     return 0;
@@ -1101,7 +1162,12 @@ extern "C" int sfb_fire_map_device(sfb_sim* s, void** dev) {
     if ((rc = use(s))) return rc;
     const size_t bytes = (size_t)s->d.E * s->d.H * s->d.W;
     if (!s->obs && (rc = dmalloc(s, (char**)&s->obs, bytes))) return rc;
-    DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, s->d, 0, s->d.E, (int8_t*)s->obs);
+    if (linear_bytes(s)) {
+        k_get_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>((const uint4*)s->d.state, (uint4*)s->obs,
+                                                                                      (long long)bytes / 16);
+        s->launches_all++;
+    } else
+        DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, s->d, 0, s->d.E, (int8_t*)s->obs);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     *dev = s->obs;
