@@ -1,8 +1,11 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "mirror" 2>&1 | tail -3
-for v in host device; do if [ $v = device ]; then export SFB_LOG_ON_DEVICE=1; fi
-SFB_DEBUG_TIMING=1 SFB_HOST_THREADS=8 python bench.py --no-cpu-baseline --steps 100 --e2e-steps 20 > gpurun_out/b.json 2> gpurun_out/b.err; grep sfb_sync gpurun_out/b.err | tail -3; python - <<PY
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+run() { # workload sweep extra
+python bench.py --workload $1 --sweep $2 $3 --no-cpu-baseline > gpurun_out/b.json 2>&1; python - <<PY
 import json
-j=json.loads(open("gpurun_out/b.json").read().strip().splitlines()[-1])
-print("$v value %.3e ms/step %.3f e2e %.3e eval_ms %.3f" % (j["value"], j["ms_per_step"], j["e2e"]["value"], j["roofline"]["k_eval_ms_per_launch"]), j["e2e"]["mirror_matches_download"])
+try:
+    j=json.loads(open("gpurun_out/b.json").read().strip().splitlines()[-1])
+    r=j["roofline"]; print("$1 $2 $3 value %.3e ms/step %.3f sweep_ms %.3f eval_ms %.3f frac %.3f e2e %.3e" % (j["value"], j["ms_per_step"], r["ms_per_launch"], r["k_eval_ms_per_launch"], r["frac"], j["e2e"]["value"]))
+except Exception as e: print("$1 $2 FAILED", e, open("gpurun_out/b.json").read()[-600:])
 PY
-done
+}
+run target tma ""; run cfg3 tma ""

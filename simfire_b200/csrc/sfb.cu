@@ -116,6 +116,7 @@ struct sfb_sim {
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
+    int static_dirty; // raw static planes changed since k_derive_static last ran
     int n_sm;
     cudaStream_t stream;      // stream in use
     cudaStream_t own_stream;  // created by the handle
@@ -376,6 +377,17 @@ __global__ void k_clear_ros(DevParams p, int par) {
     }
 }
 
+// fuel-only Rothermel terms of every static cell, through the same code as the one-shot path
+__global__ void k_derive_static(DevParams p, long long n_cells) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
+        const StaticRec r = p.stat[i];
+        DerivedRec d;
+        d.fuel = sfb_fuel_terms(r.fuel.x, r.fuel.y, r.fuel.z, r.fuel.w, p.part);
+        d.env = r.env;
+        const_cast<DerivedRec*>(p.drv)[i] = d;
+    }
+}
+
 __global__ void k_rate_of_spread(const int8_t* dir, const float* rec, SfbParticle fp, long long n, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sfb_rate_of_spread_pair(dir[i], rec + 8 * i, fp);
@@ -412,6 +424,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.burn);
     cudaFree(s->d.ros);
     cudaFree((void*)s->d.stat);
+    cudaFree((void*)s->d.drv);
     cudaFree(s->d.meta);
     cudaFree(s->d.queue);
     cudaFree(s->d.qcount);
@@ -492,6 +505,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if (d.keep_ros && (rc = dmalloc(s, &d.ros, (size_t)total * 8))) return rc;
     const int64_t stat_cells = d.shared_static ? d.plane : total;
     if ((rc = dmalloc(s, (StaticRec**)&d.stat, (size_t)stat_cells * sizeof(StaticRec)))) return rc;
+    if ((rc = dmalloc(s, (DerivedRec**)&d.drv, (size_t)stat_cells * sizeof(DerivedRec)))) return rc;
+    s->static_dirty = 1;
     if ((rc = dmalloc(s, &d.meta, (size_t)2 * d.E * sizeof(EnvMeta)))) return rc;
     if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
     if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
@@ -628,6 +643,7 @@ static int set_static_range(sfb_sim* s, int env, int plane, const float* dev_src
     const long long total = (long long)n * d.H * d.W;
     k_set_static<<<cap_grid(s, total, 256), 256, 0, s->stream>>>(d, first, n, plane, dev_src);
     s->launches_all++;
+    s->static_dirty = 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -782,6 +798,12 @@ extern "C" int sfb_set_fire_map(sfb_sim* s, int32_t env0, int32_t n, const int8_
 static int enqueue_sweep(sfb_sim* s) {
     const DevParams& d = s->d;
     const int par = s->parity;
+    if (s->static_dirty) {
+        const long long cells = d.shared_static ? d.plane : (long long)d.E * d.plane;
+        k_derive_static<<<cap_grid(s, cells, 128), 128, 0, s->stream>>>(d, cells);
+        s->launches_all++;
+        s->static_dirty = 0;
+    }
     if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
     if (s->use_tma) {
         const unsigned grid = (unsigned)s->sweep_blocks;

@@ -57,6 +57,11 @@ struct StaticRec {  // 32 B = one DRAM sector
     float4 env;     // U, U_dir, slope_mag, slope_dir
 };
 
+struct DerivedRec {  // 48 B: what k_eval gathers per candidate item
+    SfbFuelTerms fuel;  // fuel-only Rothermel terms of the cell (k_derive_static)
+    float4 env;         // U, U_dir, slope_mag, slope_dir
+};
+
 struct DevParams {
     int32_t H, W, E, pitch;  // pitch in cells, multiple of 16
     int32_t max_dur, diagonal, attenuate, shared_static, keep_ros, has_max_time;
@@ -69,7 +74,8 @@ struct DevParams {
     void* state;
     double* burn;
     double* ros;
-    const StaticRec* stat;
+    const StaticRec* stat;   // raw inputs as uploaded
+    const DerivedRec* drv;   // derived from `stat` by k_derive_static before the first step that needs it
     EnvMeta* meta;              // [2][E], double-buffered by step parity
     unsigned long long* queue;  // [qcap] work items
     unsigned long long* qcount; // [2]
@@ -154,11 +160,10 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
     double ros;
     if (dir != DIR_NONE) {
         const long long cell = idx - (long long)env * p.plane;
-        const StaticRec* rp = p.stat + (p.shared_static ? cell : idx);
-        const float4 f = __ldg(&rp->fuel);
-        const float4 e = __ldg(&rp->env);
-        const float rec[8] = {f.x, f.y, f.z, f.w, e.x, e.y, e.z, e.w};
-        ros = sfb_rate_of_spread_pair(dir, rec, p.part) * p.dt;  // fire.py:696
+        const float4* rp = reinterpret_cast<const float4*>(p.drv + (p.shared_static ? cell : idx));
+        const float4 t0 = __ldg(rp), t1 = __ldg(rp + 1), e = __ldg(rp + 2);
+        const SfbFuelTerms t = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        ros = sfb_spread_from_terms(dir, t, e.x, e.y, e.z, e.w) * p.dt;  // rothermel.py:4-136, fire.py:696
         if (s & ST_LINE_BIT) ros = p.attenuate ? ros - line_attenuation(s) : 0.0;  // fire.py:271-282
     } else {
         // control line that no fire touches: attenuated only if the step got past the
