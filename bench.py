@@ -253,7 +253,7 @@ def gpu_arm_slab(args):
     wl, E, _ = make_workload(args.workload)
     H, W = wl.H, wl.W
     grid = SlabGrid(H, W, wl.planes, ctx=ctx, n_slabs=1, E=E, device=local, track_changes=not args.no_track,
-                    **wl.engine_kwargs())  # fmt: skip
+                    sync=args.slab_sync, **wl.engine_kwargs())  # fmt: skip
     grid.reset([wl.init_pos])
     grid.step(args.burn_in)
     grid.step(args.warmup)
@@ -294,8 +294,10 @@ def gpu_arm_slab(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "u8+f32/f64", "data": "synthetic",
             "config": {"workload": args.workload, "grid": [H, W], "envs_total": E, "terrain": wl.description,
                        "burn_in_steps": args.burn_in,
-                       "parallelism": f"{ctx.world} row slabs, halo rows read from peer memory (CUDA IPC over "
-                                      "NVLink), 2 NCCL all-reduces of <= 32 B per step" if ctx.world > 1 else "1 GPU",
+                       "parallelism": (f"{ctx.world} row slabs, halo rows read from peer memory (CUDA IPC over NVLink), "
+                                       + ("per-step flags and hand-shakes stored into the peers' mailboxes (no NCCL)"
+                                          if args.slab_sync == "p2p" else "2 NCCL all-reduces of <= 32 B per step"))
+                                      if ctx.world > 1 else "1 GPU",
                        "l2": "a 67 MB state plane fits the 126 MB L2: this workload is launch/latency-bound"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16,
@@ -471,6 +473,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slab-sync", default="p2p", choices=["p2p", "nccl"], help="cfg5: how the slabs agree per step")
     ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

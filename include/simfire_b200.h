@@ -219,6 +219,18 @@ int sfb_step_eval(sfb_sim* sim);
  * sfb_step_eval): 8 int32 per env; an element-wise MAX across slabs ORs any_live / any_cand
  * and leaves the other fields (identical on every slab) unchanged. */
 int sfb_flags_device(sfb_sim* sim, void** flags, int64_t* n_int32);
+/* Peer-memory coordination (no host or NCCL round trip per step).  The handle owns a small
+ * mailbox (sfb_slab_mailbox: device pointer + byte offset from the state plane, so it can be
+ * reached through the state plane's IPC mapping); sfb_slab_connect receives, for every slab q of
+ * the grid, a device pointer to q's mailbox as seen from this device (own included).  After that
+ * sfb_step_slab(n) enqueues n x [sweep, flag exchange, eval, done handshake] on the stream: the
+ * handshakes are single-warp kernels that store into the peers' mailboxes and poll their own.
+ * Every slab of the grid must call sfb_step_slab with the same n.  A wait that is not satisfied
+ * within about a second sets an error that the next sfb_synchronize reports (SFB_ERR_STATE). */
+int sfb_slab_mailbox(sfb_sim* sim, void** mailbox, int64_t* offset_from_state);
+int sfb_slab_connect(sfb_sim* sim, int32_t rank, int32_t world, void* const* peer_mailboxes);
+int sfb_step_slab(sfb_sim* sim, int32_t n_steps);
+
 /* Run the handle's work on the caller's stream (cudaStream_t as void*), e.g. the stream a
  * communication library orders its collectives on.  NULL restores the handle's own stream. */
 int sfb_set_stream(sfb_sim* sim, void* stream);

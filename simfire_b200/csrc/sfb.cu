@@ -117,6 +117,8 @@ struct sfb_sim {
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
     int static_dirty; // raw static planes changed since k_derive_static last ran
+    size_t mailbox_off;   // byte offset of the slab mailbox behind the state plane
+    uint32_t slab_step;   // global step counter of sfb_step_slab (same on every slab)
     int n_sm;
     cudaStream_t stream;      // stream in use
     cudaStream_t own_stream;  // created by the handle
@@ -500,7 +502,12 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     d.qcap = qcap;
 
     int rc;
-    if ((rc = dmalloc(s, (char**)&d.state, (size_t)total * s->cell_bytes))) return rc;
+    // the slab mailbox sits behind the state plane, inside the same allocation, so that the one
+    // IPC handle of the plane also maps it into the peers
+    s->mailbox_off = ((size_t)total * s->cell_bytes + 255) / 256 * 256;
+    if ((rc = dmalloc(s, (char**)&d.state, s->mailbox_off + sizeof(SlabMailbox)))) return rc;
+    d.mailbox = reinterpret_cast<SlabMailbox*>((char*)d.state + s->mailbox_off);
+    CU(cudaMemsetAsync(d.mailbox, 0, sizeof(SlabMailbox), s->stream));
     if ((rc = dmalloc(s, &d.burn, (size_t)total * 8))) return rc;
     if (d.keep_ros && (rc = dmalloc(s, &d.ros, (size_t)total * 8))) return rc;
     const int64_t stat_cells = d.shared_static ? d.plane : total;
@@ -869,6 +876,50 @@ extern "C" int sfb_step_eval(sfb_sim* s) {
     return 0;
 }
 
+extern "C" int sfb_slab_mailbox(sfb_sim* s, void** mailbox, int64_t* offset_from_state) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_slab_mailbox: null handle");
+    if (mailbox) *mailbox = (void*)s->d.mailbox;
+    if (offset_from_state) *offset_from_state = (int64_t)s->mailbox_off;
+    return 0;
+}
+
+extern "C" int sfb_slab_connect(sfb_sim* s, int32_t rank, int32_t world, void* const* peer_mailboxes) {
+    if (!s || !peer_mailboxes) return fail(SFB_ERR_INVALID, "sfb_slab_connect: null argument");
+    if (world < 1 || world > SLAB_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(SFB_ERR_INVALID, "sfb_slab_connect: rank %d of %d (at most %d slabs)", rank, world, SLAB_MAX_WORLD);
+    if (s->d.E > SLAB_MAX_ENVS) return fail(SFB_ERR_INVALID, "sfb_slab_connect: at most %d envs in slab mode", SLAB_MAX_ENVS);
+    if (s->use_tma) return fail(SFB_ERR_STATE, "sfb_slab_connect: the handle was not created in slab mode");
+    int rc;
+    if ((rc = use(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    for (int q = 0; q < world; ++q) {
+        if (!peer_mailboxes[q]) return fail(SFB_ERR_INVALID, "sfb_slab_connect: mailbox of slab %d is null", q);
+        s->d.peer_box[q] = reinterpret_cast<SlabMailbox*>(peer_mailboxes[q]);
+    }
+    s->d.slab_rank = rank;
+    s->d.slab_world = world;
+    s->slab_step = 0;
+    return 0;
+}
+
+extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_step_slab: null handle");
+    if (s->d.slab_world < 1) return fail(SFB_ERR_STATE, "sfb_step_slab: call sfb_slab_connect first");
+    if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_slab: a step is half done");
+    int rc;
+    if ((rc = use(s))) return rc;
+    for (int i = 0; i < n_steps; ++i) {
+        const uint32_t g = ++s->slab_step;
+        if ((rc = enqueue_sweep(s))) return rc;
+        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->d, s->parity, g);
+        if ((rc = enqueue_eval(s))) return rc;
+        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->d, g);
+        s->launches_all += 2;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int sfb_flags_device(sfb_sim* s, void** flags, int64_t* n_int32) {
     if (!s || !flags || !n_int32) return fail(SFB_ERR_INVALID, "sfb_flags_device: null argument");
     *flags = (void*)(s->d.meta + (size_t)s->parity * s->d.E);
@@ -999,6 +1050,11 @@ extern "C" int sfb_synchronize(sfb_sim* s) {
     if ((rc = use(s))) return rc;
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    if (s->d.slab_world > 0) {
+        int32_t err = 0;
+        CU(cudaMemcpy(&err, (const void*)&s->d.mailbox->error, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return fail(SFB_ERR_STATE, "sfb_synchronize: a slab handshake timed out (a peer slab did not reach the same step)");
+    }
     return 0;
 }
 

@@ -57,6 +57,20 @@ struct StaticRec {  // 32 B = one DRAM sector
     float4 env;     // U, U_dir, slope_mag, slope_dir
 };
 
+// Slab mode: what the slabs of one grid tell each other every step, written straight into the
+// peers' memory (NVLink peer stores when the slabs are on different GPUs) and polled by tiny
+// single-warp kernels, so a run of n steps is enqueued once and needs no host or NCCL round trip.
+constexpr int SLAB_MAX_WORLD = 8, SLAB_MAX_ENVS = 16;
+struct SlabMailbox {
+    volatile uint32_t done_step[SLAB_MAX_WORLD];   // [q]: slab q has finished k_eval of step ...
+    // double-buffered by step parity: a slab that is one step ahead posts into the other half
+    // while a slower one is still reading this one (it cannot get two steps ahead: its next
+    // exchange needs the slower slab's post)
+    volatile uint32_t flag_step[2][SLAB_MAX_WORLD];   // [g & 1][q]: flags[g & 1][q] belong to step g
+    volatile int32_t flags[2][SLAB_MAX_WORLD][SLAB_MAX_ENVS][2];  // any_live, any_cand of slab q
+    volatile int32_t error;                        // a wait gave up (peer stalled)
+};
+
 struct DerivedRec {  // 48 B: what k_eval gathers per candidate item
     SfbFuelTerms fuel;  // fuel-only Rothermel terms of the cell (k_derive_static)
     float4 env;         // U, U_dir, slope_mag, slope_dir
@@ -86,6 +100,10 @@ struct DevParams {
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
     int64_t halo_top_plane, halo_bottom_plane;  // per-env stride (cells) of those neighbour planes
     const void* filler;       // (pitch + 2 * 16) BURNED cells: stands in for rows outside the grid
+    // slab mode without host round trips: per-step agreement through peer-visible mailboxes
+    struct SlabMailbox* mailbox;       // this slab's mailbox (peers write into it)
+    struct SlabMailbox* peer_box[8];   // every slab's mailbox as seen from this device (own included)
+    int32_t slab_rank, slab_world;
     // change log (SFB_TRACK_CHANGES)
     int32_t track;
     unsigned long long* chg;        // [chg_cap] idx | BurnStatus << 48
@@ -723,6 +741,71 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
         p.overflow[par ^ 1] = 0;
         p.unit_next[par ^ 1] = 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// slab mode synchronisation kernels (one warp each)
+// ---------------------------------------------------------------------------------------
+constexpr long long SLAB_SPIN_LIMIT = 1ll << 27;  // ~ a second of polling, then give up instead of hanging
+
+// after k_sweep of global step `gstep`: publish this slab's any_live / any_cand to every slab,
+// wait for everybody's, OR them into this slab's EnvMeta
+__global__ void k_slab_exchange_flags(const DevParams p, const int par, const uint32_t gstep) {
+    const int lane = threadIdx.x;
+    const int half = gstep & 1;
+    EnvMeta* meta = p.meta + (long long)par * p.E;
+    for (int q = 0; q < p.slab_world; ++q) {
+        SlabMailbox* box = p.peer_box[q];
+        for (int i = lane; i < p.E * 2; i += 32) {
+            const EnvMeta& m = meta[i >> 1];
+            box->flags[half][p.slab_rank][i >> 1][i & 1] = (i & 1) ? m.any_cand : m.any_live;
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < p.slab_world) p.peer_box[lane]->flag_step[half][p.slab_rank] = gstep;
+    __threadfence_system();
+    bool ok = true;
+    if (lane < p.slab_world) {
+        long long spins = 0;
+        while (p.mailbox->flag_step[half][lane] != gstep) {
+            if (++spins > SLAB_SPIN_LIMIT) { ok = false; break; }
+        }
+    }
+    __threadfence_system();
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) p.mailbox->error = 1;
+        return;
+    }
+    for (int i = lane; i < p.E * 2; i += 32) {
+        int v = 0;
+        for (int q = 0; q < p.slab_world; ++q) v |= p.mailbox->flags[half][q][i >> 1][i & 1];
+        if (v) {
+            if (i & 1) meta[i >> 1].any_cand = 1;
+            else meta[i >> 1].any_live = 1;
+        }
+    }
+}
+
+// after k_eval of global step `gstep`: tell the neighbours, and wait until they have finished it too
+// (their ignitions of this step must be visible before the next sweep reads their edge rows)
+__global__ void k_slab_step_done(const DevParams p, const uint32_t gstep) {
+    const int lane = threadIdx.x;
+    const int up = p.slab_rank - 1, down = p.slab_rank + 1;
+    __threadfence_system();
+    if (lane == 0 && up >= 0) p.peer_box[up]->done_step[p.slab_rank] = gstep;
+    if (lane == 1 && down < p.slab_world) p.peer_box[down]->done_step[p.slab_rank] = gstep;
+    __threadfence_system();
+    bool ok = true;
+    const int from = lane == 0 ? up : (lane == 1 ? down : -1);
+    if (from >= 0 && from < p.slab_world) {
+        long long spins = 0;
+        while ((int32_t)(p.mailbox->done_step[from] - gstep) < 0) {
+            if (++spins > SLAB_SPIN_LIMIT) { ok = false; break; }
+        }
+    }
+    __threadfence_system();
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) p.mailbox->error = 1;
 }
 
 }  // namespace sfb

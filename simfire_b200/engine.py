@@ -247,6 +247,20 @@ class FireEngine:
         _lib.check(self._lib.sfb_set_halo(self._h, C.c_void_p(top_row or None), int(top_plane),
                                           C.c_void_p(bottom_row or None), int(bottom_plane)))  # fmt: skip
 
+    def slab_mailbox(self):
+        """(device pointer of this slab's mailbox, its byte offset from the state plane)."""
+        ptr, off = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.sfb_slab_mailbox(self._h, C.byref(ptr), C.byref(off)))
+        return int(ptr.value), int(off.value)
+
+    def slab_connect(self, rank: int, world: int, peer_mailboxes) -> None:
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_mailboxes])
+        _lib.check(self._lib.sfb_slab_connect(self._h, int(rank), int(world), arr))
+
+    def step_slab(self, n: int = 1) -> None:
+        """n steps coordinated with the other slabs through peer memory; asynchronous."""
+        _lib.check(self._lib.sfb_step_slab(self._h, int(n)))
+
     def step_sweep(self) -> None:
         _lib.check(self._lib.sfb_step_sweep(self._h))
 

@@ -25,7 +25,8 @@ from .sharding import RankContext, row_slabs
 
 class SlabGrid:
     def __init__(self, total_H: int, W: int, planes: Dict[str, np.ndarray], *, n_slabs: Optional[int] = None,
-                 ctx: Optional[RankContext] = None, E: int = 1, device: int = 0, **engine_kwargs) -> None:  # fmt: skip
+                 ctx: Optional[RankContext] = None, E: int = 1, device: int = 0, sync: str = "p2p",
+                 **engine_kwargs) -> None:  # fmt: skip
         """
         `planes`: the eight static (total_H, W) planes of the WHOLE grid (each rank slices its
         rows).  With a multi-rank `ctx` there is one slab per rank; otherwise `n_slabs` slabs
@@ -34,6 +35,9 @@ class SlabGrid:
         self.ctx = ctx if ctx is not None else RankContext()
         self.total_H, self.W, self.E = int(total_H), int(W), int(E)
         self.distributed = self.ctx.world > 1
+        # per-step agreement between ranks: "p2p" = mailboxes in peer memory, polled by tiny
+        # kernels (no host or NCCL round trip); "nccl" = two small all-reduces per step
+        self.sync = sync
         world = self.ctx.world if self.distributed else int(n_slabs or 1)
         self.slabs = row_slabs(self.total_H, world)
         mine = [self.ctx.rank] if self.distributed else list(range(world))
@@ -75,21 +79,28 @@ class SlabGrid:
 
         eng = self.engines[0]
         ptr, plane, pitch, cb = geo[0]
-        info = [None] * self.ctx.world
-        dist.all_gather_object(info, (eng.ipc_export(), plane, pitch, cb, self.slabs[self.ctx.rank][1]))
-        r = self.ctx.rank
+        r, world = self.ctx.rank, self.ctx.world
+        info = [None] * world  # (ipc handle, plane cells, pitch cells, cell bytes, rows, mailbox offset)
+        dist.all_gather_object(info, (eng.ipc_export(), plane, pitch, cb, self.slabs[r][1], eng.slab_mailbox()[1]))
+        # map the state planes we need: the two neighbours (halo rows) and, for the peer-memory
+        # handshakes, every slab (its mailbox sits behind its state plane)
+        need = {q for q in (r - 1, r + 1) if 0 <= q < world}
+        if self.sync == "p2p":
+            need |= set(range(world)) - {r}
+        bases = {}
+        for q in sorted(need):
+            bases[q] = eng.ipc_open(info[q][0])
+            self._opened.append(bases[q])
         top = bottom = (0, 0)
         if r > 0:
-            h, pl, pi, c, rows = info[r - 1]
-            base = eng.ipc_open(h)
-            self._opened.append(base)
-            top = (base + (rows - 1) * pi * c, pl)
-        if r + 1 < self.ctx.world:
-            h, pl, pi, c, rows = info[r + 1]
-            base = eng.ipc_open(h)
-            self._opened.append(base)
-            bottom = (base, pl)
+            _, pl, pi, c, rows, _ = info[r - 1]
+            top = (bases[r - 1] + (rows - 1) * pi * c, pl)
+        if r + 1 < world:
+            bottom = (bases[r + 1], info[r + 1][1])
         eng.set_halo(top[0], top[1], bottom[0], bottom[1])
+        if self.sync == "p2p":
+            boxes = [eng.slab_mailbox()[0] if q == r else bases[q] + info[q][5] for q in range(world)]
+            eng.slab_connect(r, world, boxes)
         self.ctx.barrier()
 
     # -- mutations (coordinates are those of the whole grid) ---------------------------------------
@@ -144,6 +155,11 @@ class SlabGrid:
         import torch.distributed as dist
 
         eng = self.engines[0]
+        if self.sync == "p2p":
+            eng.step_slab(n)  # enqueues everything; the slabs meet in peer memory
+            self._steps += n
+            eng.synchronize()
+            return
         with torch.cuda.stream(self._stream):
             for _ in range(n):
                 par = self._steps % 2
@@ -172,10 +188,15 @@ class SlabGrid:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self._stream):
             a.record()
-        self._step_distributed(n)
+        if self.sync == "p2p":
+            self.engines[0].step_slab(n)
+            self._steps += n
+        else:
+            self._step_distributed(n)
         with torch.cuda.stream(self._stream):
             b.record()
         b.synchronize()
+        self.engines[0].synchronize()  # also surfaces a handshake time-out
         return a.elapsed_time(b)
 
     # -- results ------------------------------------------------------------------------------------------

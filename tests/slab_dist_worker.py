@@ -23,7 +23,7 @@ def main():
     mid = H // ctx.world
     starts = [(150, mid - 1), (40, mid + 2)]
     lines = [(e, x, y, 3 + (x % 3)) for e in range(E) for y in (20, mid, 150) for x in range(10, 290, 2)]
-    grid = SlabGrid(H, W, wl.planes, ctx=ctx, E=E, device=local, **kw)
+    grid = SlabGrid(H, W, wl.planes, ctx=ctx, E=E, device=local, sync=os.environ.get("SFB_SLAB_SYNC", "p2p"), **kw)
     grid.reset(starts)
     grid.apply_points(lines)
     ref = None
