@@ -181,6 +181,11 @@ int sfb_get_fire_map(sfb_sim* sim, int32_t env0, int32_t n, int8_t* out);
  * NULL) receives the number of patched cells, or -1 for a full download. */
 int sfb_sync_fire_maps(sfb_sim* sim, int8_t* mirror, int64_t* n_changes);
 
+/* Pause / resume the change log of a handle created with SFB_TRACK_CHANGES (a rollout that
+ * only consumes the device-resident observation does not need it; logging costs PCIe writes).
+ * Resuming forces the next sfb_sync_fire_maps to download everything once. */
+int sfb_set_tracking(sfb_sim* sim, int32_t enabled);
+
 /* One [H][W] plane of one env; element type per sfb_state_plane. */
 int sfb_get_plane(sfb_sim* sim, int32_t env, int32_t plane, void* out);
 /* Per-env GameStatus (int32), elapsed_time (float64, fire.py:717) and number of update()

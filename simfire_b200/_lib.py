@@ -25,7 +25,7 @@ EXPORTS = (
     "sfb_set_kernel_timing", "sfb_get_kernel_ms", "sfb_get_queue_stats", "sfb_device_bytes",
     "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
     "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
-    "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab",
+    "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab", "sfb_set_tracking",
 )  # fmt: skip
 
 
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
         "sfb_slab_mailbox": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "sfb_slab_connect": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
         "sfb_step_slab": (C.c_int, [vp, i32]),
+        "sfb_set_tracking": (C.c_int, [vp, i32]),
         "sfb_get_status": (C.c_int, [vp, vp, vp, vp]),
         "sfb_fire_map_device": (C.c_int, [vp, C.POINTER(vp)]),
         "sfb_get_stream": (C.c_int, [vp, C.POINTER(vp)]),

@@ -1164,6 +1164,7 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     if (full) {
         if ((rc = download_maps(s, 0, d.E, mirror))) return rc;
         CU(cudaStreamSynchronize(s->stream));
+        if (!d.track) s->full_resync = 1;
         if (n_changes) *n_changes = -1;
     } else if (cnt > 0 && s->log_mapped) {
         // entries are already in host memory; patch, then let the device reuse the log
@@ -1206,6 +1207,16 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     if (debug)
         fprintf(stderr, "[sfb_sync] wait+head %.3f ms, log d2h %.3f ms (%llu entries), patch %.3f ms%s\n", t1 - t0, t2 - t1,
                 cnt, now_ms() - t2, full ? " (full download)" : "");
+    return 0;
+}
+
+extern "C" int sfb_set_tracking(sfb_sim* s, int32_t enabled) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_set_tracking: null handle");
+    if (!s->d.chg) return fail(SFB_ERR_STATE, "sfb_set_tracking: the handle was created without SFB_TRACK_CHANGES");
+    if (s->in_step) return fail(SFB_ERR_STATE, "sfb_set_tracking: a step is half done");
+    const int on = enabled != 0;
+    if (on && !s->d.track) s->full_resync = 1;  // changes made while paused were not logged
+    s->d.track = on;
     return 0;
 }
 

@@ -193,6 +193,10 @@ class FireEngine:
         _lib.check(self._lib.sfb_sync_fire_maps(self._h, _ptr(mirror), C.byref(n)))
         return int(n.value)
 
+    def set_tracking(self, enabled: bool) -> None:
+        """Pause / resume the change log (engines created with track_changes=True)."""
+        _lib.check(self._lib.sfb_set_tracking(self._h, 1 if enabled else 0))
+
     def plane(self, which: str, env: int = 0) -> np.ndarray:
         pid, dt = {"burn": (_lib.PLANE_BURN, np.float64), "ros": (_lib.PLANE_ROS, np.float64),
                    "age": (_lib.PLANE_AGE, np.int32), "status": (_lib.PLANE_STATUS, np.int8)}[which]  # fmt: skip

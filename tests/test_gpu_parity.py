@@ -224,6 +224,14 @@ def test_incremental_host_mirror_matches_full_download(shape):
                 patched += n
             assert np.array_equal(mirror, eng.fire_map()), f"iteration {it}"
         assert patched > 100
+        eng.set_tracking(False)  # paused: changes are not logged ...
+        eng.step(3)
+        eng.set_tracking(True)  # ... so the first sync after resuming downloads everything
+        assert eng.sync_fire_maps(mirror) == -1
+        assert np.array_equal(mirror, eng.fire_map())
+        eng.step(2)
+        assert eng.sync_fire_maps(mirror) >= 0
+        assert np.array_equal(mirror, eng.fire_map())
         other = np.zeros_like(mirror)
         assert eng.sync_fire_maps(other) == -1  # a different buffer cannot be patched
         assert np.array_equal(other, mirror)
