@@ -66,8 +66,11 @@ enum sfb_flags {
                                   (it is selected automatically above that); tests only      */
     SFB_SWEEP_LDG = 64,        /* stream the state with 128-bit global loads instead of the TMA
                                   ring (A/B measurements; slab mode always uses it)          */
-    SFB_TRACK_CHANGES = 128    /* keep a device log of every BurnStatus change so that
+    SFB_TRACK_CHANGES = 128,   /* keep a device log of every BurnStatus change so that
                                   sfb_sync_fire_maps can patch a host mirror incrementally   */
+    SFB_KEEP_IGNITION = 256    /* keep an int32 plane with the update() call that ignited each
+                                  cell: enough to rebuild the fire-spread graph the reference
+                                  maintains per step (graph.py:84-150, called at fire.py:584)   */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the
@@ -90,7 +93,9 @@ enum sfb_state_plane {
     SFB_PLANE_BURN = 0, /* float64 burn_amounts (fire.py:370, :710)                     */
     SFB_PLANE_ROS = 1,  /* float64 rate_of_spread of the last step (needs SFB_KEEP_ROS) */
     SFB_PLANE_AGE = 2,  /* int32: -1 no sprite, else the sprite's duration (fire.py:633) */
-    SFB_PLANE_STATUS = 3/* int8 BurnStatus -- same as sfb_get_fire_map                  */
+    SFB_PLANE_STATUS = 3,/* int8 BurnStatus -- same as sfb_get_fire_map                 */
+    SFB_PLANE_IGNITION = 4 /* int32: update() call that ignited the cell (0 = initial fire,
+                              -1 = never ignited); needs SFB_KEEP_IGNITION                 */
 };
 
 /* Constructor arguments: RothermelFireManager.__init__ (fire.py:293-307) plus the
@@ -132,6 +137,13 @@ int sfb_abi_version(void);
 int sfb_set_static(sfb_sim* sim, int32_t env, int32_t plane, const float* host);
 /* All eight planes at once: float32 [8][H][W] in sfb_static_plane order. */
 int sfb_set_static_all(sfb_sim* sim, int32_t env, const float* host);
+
+/* RothermelFireManager._compute_slopes (fire.py:436-449) on the device: from float64
+ * elevations [H][W] (ft) computes np.gradient(elevations, pixel_scale) (central differences,
+ * one-sided at the borders), slope_mag = sqrt(gx^2 + gy^2) and slope_dir = atan2(gy, gx + 1e-6)
+ * in float64 and stores them as the SFB_SLOPE_MAG / SFB_SLOPE_DIR planes of env `env`
+ * (-1: all / shared).  Not available in slab mode (the gradient crosses slab borders). */
+int sfb_set_elevation(sfb_sim* sim, int32_t env, const double* elevations);
 
 /* ---- between-step mutations ------------------------------------------------------ */
 

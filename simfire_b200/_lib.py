@@ -12,8 +12,9 @@ ABI_VERSION = 1
 # sfb_flags
 DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
 TRACK_CHANGES = 128
+KEEP_IGNITION = 256
 # sfb_state_plane
-PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS = 0, 1, 2, 3
+PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS, PLANE_IGNITION = 0, 1, 2, 3, 4
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")
 
 # every symbol include/simfire_b200.h declares
@@ -26,6 +27,7 @@ EXPORTS = (
     "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
     "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
     "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab", "sfb_set_tracking",
+    "sfb_set_elevation",
 )  # fmt: skip
 
 
@@ -91,6 +93,7 @@ def load() -> C.CDLL:
         "sfb_slab_connect": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
         "sfb_step_slab": (C.c_int, [vp, i32]),
         "sfb_set_tracking": (C.c_int, [vp, i32]),
+        "sfb_set_elevation": (C.c_int, [vp, i32, vp]),
         "sfb_get_status": (C.c_int, [vp, vp, vp, vp]),
         "sfb_fire_map_device": (C.c_int, [vp, C.POINTER(vp)]),
         "sfb_get_stream": (C.c_int, [vp, C.POINTER(vp)]),

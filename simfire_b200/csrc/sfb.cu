@@ -211,6 +211,7 @@ __global__ void k_clear_envs(DevParams p, const int32_t* envs, int n, int clear_
         if (clear_burn) {
             p.burn[idx] = 0.0;
             if (p.ros) p.ros[idx] = 0.0;
+            if (p.ign) p.ign[idx] = -1;
         }
     }
 }
@@ -222,9 +223,11 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
     if (k >= n) return;
     const int env = envs ? envs[k] : k;
     const int x = xy[2 * k], y = xy[2 * k + 1] - y_off;
-    if (y >= 0 && y < p.H)
+    if (y >= 0 && y < p.H) {
         reinterpret_cast<CellT*>(p.state)[(long long)env * p.plane + (long long)y * p.pitch + x] =
             (CellT)(ST_BURNING | (1 << 3));  // sprite created before update() call 1: ign = 0
+        if (p.ign) p.ign[(long long)env * p.plane + (long long)y * p.pitch + x] = 0;
+    }
     EnvMeta m;
     m.t = 1;
     m.running = 1;
@@ -329,6 +332,12 @@ __global__ void k_clear_envs_v16(DevParams p, const int32_t* envs, int n, long l
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = z;
         }
+        if (p.ign) {
+            const uint4 m1 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            uint4* g = reinterpret_cast<uint4*>(p.ign) + (env * plane16 + w) * 4;  // 16 cells x 4 B
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = m1;
+        }
     }
 }
 
@@ -343,6 +352,8 @@ __global__ void k_get_plane(DevParams p, int par, int env, int plane, void* out)
         ((double*)out)[i] = p.burn[idx];
     } else if (plane == SFB_PLANE_ROS) {
         ((double*)out)[i] = p.ros[idx];
+    } else if (plane == SFB_PLANE_IGNITION) {
+        ((int32_t*)out)[i] = p.ign[idx];
     } else {
         const int c = reinterpret_cast<const CellT*>(p.state)[idx];
         if (plane == SFB_PLANE_STATUS) {
@@ -364,6 +375,31 @@ __global__ void k_set_static(DevParams p, int env_first, int n_env, int plane, c
         const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
         float* rec = (float*)(p.stat + (long long)(env_first + k) * p.plane + (long long)y * p.pitch + x);
         rec[plane] = src[r];  // the same host plane for every env of the range
+    }
+}
+
+// RothermelFireManager._compute_slopes (fire.py:436-449): np.gradient (second-order central
+// differences inside, first-order one-sided at the borders), all in float64
+__global__ void k_slopes(DevParams p, int env_first, int n_env, const double* elev, double spacing) {
+    const long long hw = (long long)p.H * p.W, total = (long long)n_env * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / hw);
+        const long long r = i - (long long)k * hw;
+        const int y = (int)(r / p.W), x = (int)(r - (long long)y * p.W);
+        auto at = [&](int yy, int xx) { return elev[(long long)yy * p.W + xx]; };
+        double gy, gx;
+        if (p.H == 1) gy = 0.0;
+        else if (y == 0) gy = (at(1, x) - at(0, x)) / spacing;
+        else if (y == p.H - 1) gy = (at(y, x) - at(y - 1, x)) / spacing;
+        else gy = (at(y + 1, x) - at(y - 1, x)) / (2.0 * spacing);
+        if (p.W == 1) gx = 0.0;
+        else if (x == 0) gx = (at(y, 1) - at(y, 0)) / spacing;
+        else if (x == p.W - 1) gx = (at(y, x) - at(y, x - 1)) / spacing;
+        else gx = (at(y, x + 1) - at(y, x - 1)) / (2.0 * spacing);
+        float* rec = (float*)(p.stat + (long long)(env_first + k) * p.plane + (long long)y * p.pitch + x);
+        rec[SFB_SLOPE_MAG] = (float)sqrt(gx * gx + gy * gy);
+        rec[SFB_SLOPE_DIR] = (float)atan2(gy, gx + 0.000001);
     }
 }
 
@@ -425,6 +461,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.state);
     cudaFree(s->d.burn);
     cudaFree(s->d.ros);
+    cudaFree(s->d.ign);
     cudaFree((void*)s->d.stat);
     cudaFree((void*)s->d.drv);
     cudaFree(s->d.meta);
@@ -510,6 +547,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     CU(cudaMemsetAsync(d.mailbox, 0, sizeof(SlabMailbox), s->stream));
     if ((rc = dmalloc(s, &d.burn, (size_t)total * 8))) return rc;
     if (d.keep_ros && (rc = dmalloc(s, &d.ros, (size_t)total * 8))) return rc;
+    if ((prm->flags & SFB_KEEP_IGNITION) && (rc = dmalloc(s, &d.ign, (size_t)total * 4))) return rc;
     const int64_t stat_cells = d.shared_static ? d.plane : total;
     if ((rc = dmalloc(s, (StaticRec**)&d.stat, (size_t)stat_cells * sizeof(StaticRec)))) return rc;
     if ((rc = dmalloc(s, (DerivedRec**)&d.drv, (size_t)stat_cells * sizeof(DerivedRec)))) return rc;
@@ -679,6 +717,29 @@ extern "C" int sfb_set_static_all(sfb_sim* s, int32_t env, const float* host) {
     CU(cudaMemcpyAsync(s->stage, host, hw * sizeof(float) * SFB_N_STATIC, cudaMemcpyHostToDevice, s->stream));
     for (int pl = 0; pl < SFB_N_STATIC; ++pl)
         if ((rc = set_static_range(s, env, pl, (const float*)s->stage + pl * hw))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int sfb_set_elevation(sfb_sim* s, int32_t env, const double* elevations) {
+    if (!s || !elevations) return fail(SFB_ERR_INVALID, "sfb_set_elevation: null argument");
+    if (env < -1 || env >= s->d.E) return fail(SFB_ERR_INVALID, "sfb_set_elevation: env %d of %d", env, s->d.E);
+    if (s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_set_elevation: not available in slab mode");
+    if (!(s->prm.pixel_scale != 0.0)) return fail(SFB_ERR_INVALID, "sfb_set_elevation: pixel_scale is 0");
+    int rc;
+    if ((rc = use(s))) return rc;
+    const DevParams& d = s->d;
+    const size_t bytes = (size_t)d.H * d.W * sizeof(double);
+    if ((rc = ensure_stage(s, bytes))) return rc;
+    CU(cudaMemcpyAsync(s->stage, elevations, bytes, cudaMemcpyHostToDevice, s->stream));
+    int first = env, n = 1;
+    if (d.shared_static) { first = 0; n = 1; }
+    else if (env < 0) { first = 0; n = d.E; }
+    k_slopes<<<cap_grid(s, (long long)n * d.H * d.W, 256), 256, 0, s->stream>>>(d, first, n, (const double*)s->stage,
+                                                                              s->prm.pixel_scale);
+    s->launches_all++;
+    s->static_dirty = 1;
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -1223,13 +1284,15 @@ extern "C" int sfb_set_tracking(sfb_sim* s, int32_t enabled) {
 extern "C" int sfb_get_plane(sfb_sim* s, int32_t env, int32_t plane, void* out) {
     if (!s || !out) return fail(SFB_ERR_INVALID, "sfb_get_plane: null argument");
     if (env < 0 || env >= s->d.E) return fail(SFB_ERR_INVALID, "sfb_get_plane: env %d of %d", env, s->d.E);
-    if (plane < 0 || plane > SFB_PLANE_STATUS) return fail(SFB_ERR_INVALID, "sfb_get_plane: plane %d", plane);
+    if (plane < 0 || plane > SFB_PLANE_IGNITION) return fail(SFB_ERR_INVALID, "sfb_get_plane: plane %d", plane);
     if (plane == SFB_PLANE_ROS && !s->d.keep_ros)
         return fail(SFB_ERR_STATE, "sfb_get_plane: rate_of_spread is only kept with SFB_KEEP_ROS");
+    if (plane == SFB_PLANE_IGNITION && !s->d.ign)
+        return fail(SFB_ERR_STATE, "sfb_get_plane: the ignition plane is only kept with SFB_KEEP_IGNITION");
     int rc;
     if ((rc = use(s))) return rc;
     const size_t hw = (size_t)s->d.H * s->d.W;
-    const size_t esz = plane <= SFB_PLANE_ROS ? 8 : (plane == SFB_PLANE_AGE ? 4 : 1);
+    const size_t esz = plane <= SFB_PLANE_ROS ? 8 : ((plane == SFB_PLANE_AGE || plane == SFB_PLANE_IGNITION) ? 4 : 1);
     if ((rc = ensure_stage(s, hw * esz))) return rc;
     DISPATCH(s, k_get_plane, nblocks((long long)hw, 256), 256, s->d, s->parity, env, plane, s->stage);
     CU(cudaGetLastError());

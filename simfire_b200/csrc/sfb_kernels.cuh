@@ -88,6 +88,7 @@ struct DevParams {
     void* state;
     double* burn;
     double* ros;
+    int32_t* ign;            // update() call that ignited the cell (SFB_KEEP_IGNITION), else nullptr
     const StaticRec* stat;   // raw inputs as uploaded
     const DerivedRec* drv;   // derived from `stat` by k_derive_static before the first step that needs it
     EnvMeta* meta;              // [2][E], double-buffered by step parity
@@ -198,6 +199,7 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
     if (dir != DIR_NONE && b > p.ps) {  // fire.py:568 (strict); tested for every candidate
         const int code = 1 + (m.t % Cell<CellT>::M);
         reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(ST_BURNING | (code << 3));  // fire.py:571-587
+        if (p.ign) p.ign[idx] = m.t;
         return true;
     }
     return false;

@@ -55,6 +55,7 @@ class FireEngine:
         wide_cells: bool = False,
         sweep_ldg: bool = False,
         track_changes: bool = False,
+        keep_ignition: bool = False,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -73,6 +74,7 @@ class FireEngine:
         flags |= _lib.WIDE_CELLS if wide_cells else 0
         flags |= _lib.SWEEP_LDG if sweep_ldg else 0
         flags |= _lib.TRACK_CHANGES if track_changes else 0
+        flags |= _lib.KEEP_IGNITION if keep_ignition else 0
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -118,6 +120,12 @@ class FireEngine:
                 )
             buf[i] = a.astype(np.float32)
         _lib.check(self._lib.sfb_set_static_all(self._h, int(env), _ptr(buf)))
+
+    def set_elevation(self, elevations: np.ndarray, env: int = -1) -> None:
+        """`_compute_slopes` (fire.py:436-449) on the device: fills the slope_mag / slope_dir planes
+        of `env` from (H, W) elevations in ft.  Call after `set_static` (which overwrites them)."""
+        e = np.ascontiguousarray(np.asarray(elevations, dtype=np.float64).reshape(self.H, self.W))
+        _lib.check(self._lib.sfb_set_elevation(self._h, int(env), _ptr(e)))
 
     def set_static_plane(self, name: str, values: ArrayOrFloat, env: int = -1) -> None:
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.H, self.W)).astype(np.float32))
@@ -199,7 +207,8 @@ class FireEngine:
 
     def plane(self, which: str, env: int = 0) -> np.ndarray:
         pid, dt = {"burn": (_lib.PLANE_BURN, np.float64), "ros": (_lib.PLANE_ROS, np.float64),
-                   "age": (_lib.PLANE_AGE, np.int32), "status": (_lib.PLANE_STATUS, np.int8)}[which]  # fmt: skip
+                   "age": (_lib.PLANE_AGE, np.int32), "status": (_lib.PLANE_STATUS, np.int8),
+                   "ignition": (_lib.PLANE_IGNITION, np.int32)}[which]  # fmt: skip
         out = np.empty((self.H, self.W), dtype=dt)
         _lib.check(self._lib.sfb_get_plane(self._h, int(env), pid, _ptr(out)))
         return out

@@ -8,7 +8,8 @@ Same constructor, same `update(fire_map) -> (fire_map, GameStatus)`, same attrib
   * no pygame sprites: `sprites` is a list of (x, y) tuples of the burning cells, built on
     demand from the device state (the reference uses it for rendering only,
     simulation.py:291, :534);
-  * no networkx `fs_graph` (out of scope).
+  * `fs_graph` is not maintained per step: with `keep_spread_graph=True` it is rebuilt on demand
+    from the device's ignition-step plane (simfire_b200/graph.py).
 """
 from __future__ import annotations
 
@@ -62,6 +63,7 @@ class RothermelFireManager:
         *,
         device: int = 0,
         keep_rate_of_spread: bool = False,
+        keep_spread_graph: bool = False,
     ) -> None:
         """
         Arguments as in fire.py:293-366.  `terrain` needs `.fuels` ((H, W) array of objects
@@ -94,7 +96,7 @@ class RothermelFireManager:
             H, W, 1, pixel_scale=pixel_scale, update_rate=update_rate, max_fire_duration=max_fire_duration,
             max_time=max_time, attenuate_line_ros=attenuate_line_ros, diagonal_spread=diagonal_spread,
             fuel_particle=(fuel_particle.h, fuel_particle.S_T, fuel_particle.S_e, fuel_particle.p_p),
-            M_f=environment.M_f, keep_ros=keep_rate_of_spread, device=device,
+            M_f=environment.M_f, keep_ros=keep_rate_of_spread, keep_ignition=keep_spread_graph, device=device,
         )  # fmt: skip
         self._engine.set_static(dict(w_0=w_0, delta=delta, M_x=M_x, sigma=sigma, U=self.U, U_dir=self.U_dir,
                                      slope_mag=self.slope_mag, slope_dir=self.slope_dir))  # fmt: skip
@@ -165,6 +167,20 @@ class RothermelFireManager:
         """(x, y) of every cell that carries a Fire sprite, row-major."""
         ys, xs = np.nonzero(self._engine.plane("age") >= 0)
         return [(int(x), int(y)) for x, y in zip(xs, ys)]
+
+    @property
+    def fs_graph(self):
+        """The fire-spread DiGraph the reference maintains per step (fire.py:380, :584), rebuilt
+        from the device's ignition-step plane (needs `keep_spread_graph=True`)."""
+        from .graph import to_networkx
+
+        return to_networkx(self._engine.plane("ignition"), self.max_fire_duration)
+
+    def spread_edges(self) -> np.ndarray:
+        """Edges of that graph as an int32 [n, 4] array (x_src, y_src, x_dst, y_dst)."""
+        from .graph import spread_edges
+
+        return spread_edges(self._engine.plane("ignition"), self.max_fire_duration)
 
     @property
     def engine(self) -> FireEngine:

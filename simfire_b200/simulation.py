@@ -25,7 +25,6 @@ from .engine import FireEngine
 from .enums import BurnStatus, ElevationConstants, FuelConstants, GameStatus, WindConstants
 from .fire_manager import fuel_planes
 from .parameters import Environment, FuelParticle
-from .workloads import compute_slopes
 
 
 def _static_planes(config: Config):
@@ -34,9 +33,9 @@ def _static_planes(config: Config):
     fuels = fdata[..., 0] if fdata.dtype == object else fdata
     w_0, delta, M_x, sigma = fuel_planes(fuels)
     elev = np.asarray(config.terrain.topography_layer.data, dtype=np.float64).reshape(H, W)
-    slope_mag, slope_dir = compute_slopes(elev, config.area.pixel_scale)
+    # slope planes are filled on the device by FireEngine.set_elevation
     return dict(w_0=w_0, delta=delta, M_x=M_x, sigma=sigma, U=config.wind.speed, U_dir=config.wind.direction,
-                slope_mag=slope_mag, slope_dir=slope_dir), elev  # fmt: skip
+                slope_mag=0.0, slope_dir=0.0), elev  # fmt: skip
 
 
 def _engine_from_config(config: Config, E: int, device: int, shared_static: bool, **kw) -> FireEngine:
@@ -69,6 +68,7 @@ class FireSimulation:
             self._engine = _engine_from_config(self.config, 1, self.device, shared_static=True)
         self._planes, self._elevations = _static_planes(self.config)
         self._engine.set_static(self._planes)
+        self._engine.set_elevation(self._elevations)  # slopes on the device (fire.py:436-449)
         self._engine.reset([self.config.fire.fire_initial_position])
         self.fuel_particle = FuelParticle()
         self.environment = Environment(self.config.environment.moisture, self.config.wind.speed,

@@ -240,3 +240,25 @@ def test_batched_simulation_matches_single_envs():
         assert batch.elapsed_time[e] == single.elapsed_time and batch.elapsed_steps[e] == single.elapsed_steps
         single.close()
     batch.close()
+
+
+def test_device_slopes_match_numpy_gradient():
+    """sfb_set_elevation vs RothermelFireManager._compute_slopes (np.gradient in float64): after
+    the float32 cast the planes agree (atan2 may differ in the last float64 bit, never more than
+    one float32 ulp), and a scenario driven by device-computed slopes reproduces the reference."""
+    from scenario_io import check_trajectory
+    from test_gpu_parity import EngineAdapter, _burn_tol, engine_for
+
+    from simfire_b200.workloads import compute_slopes
+
+    sc = load_scenario("scenario_c_random_fuel_hills")
+    planes = dict(sc["planes"])
+    mag, ang = compute_slopes(sc["elevations"], float(sc["ps"]))
+    assert np.array_equal(mag, planes["slope_mag"]) and np.array_equal(ang, planes["slope_dir"])
+    planes["slope_mag"] = 0.0
+    planes["slope_dir"] = 0.0
+    with engine_for(sc) as eng:
+        eng.set_static(planes)
+        eng.set_elevation(sc["elevations"])
+        eng.reset([sc["init"]])
+        check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
