@@ -259,12 +259,14 @@ struct SweepWarp {
     uint32_t look_mask;
     unsigned long long* wq;
     const uint32_t* seg_lut;
+    int* key_lut;    // [32] behind seg_lut
     int wcount = 0;  // warp-uniform
     int f_live = 0, f_cand = 0;
 
     __device__ __forceinline__ SweepWarp(const DevParams& p_, int par_, int lane_, int env_, int strip, int chunk,
                                          const EnvMeta& m, unsigned long long* wq_, const uint32_t* lut_)
-        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_), seg_lut(lut_) {
+        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_), seg_lut(lut_),
+          key_lut(reinterpret_cast<int*>(const_cast<uint32_t*>(lut_)) + 32) {
         x0 = strip * WR;
         y_end = min((chunk + 1) * p.rows_per_chunk, p.H);
         tm1 = (m.t - 1) % C::M;
@@ -274,6 +276,7 @@ struct SweepWarp {
         attenuate = p.attenuate != 0;
         env_off = (long long)env * p.plane;
         look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
+        build_key_lut();
     }
 
     // does this lane's segment (plus, for lanes 0 / 31, the cell outside the strip) need a look?
@@ -300,10 +303,21 @@ struct SweepWarp {
 
     // sort key of a cell as a fire source: duration * 8 if it carries a live sprite, else NO_SRC
     static constexpr int NO_SRC = 1 << 20;
-    __device__ __forceinline__ int source_key(int c) const {
-        const int code = c >> 3;
+    __device__ __forceinline__ int source_key_of_code(int code) const {
         const int a = sprite_age<CellT>(code, tm1);
         return (code != 0 && a < max_dur) ? a * 8 : NO_SRC;
+    }
+    // 8-bit cells have 32 sprite codes: one table look-up (filled per unit, it depends on t)
+    __device__ __forceinline__ int source_key(int c) const {
+        if constexpr (sizeof(CellT) == 1) return key_lut[c >> 3];
+        else return source_key_of_code(c >> 3);
+    }
+    __device__ __forceinline__ void build_key_lut() {
+        if constexpr (sizeof(CellT) == 1) {
+            __syncwarp();
+            key_lut[lane] = source_key_of_code(lane);
+            __syncwarp();
+        }
     }
 
     // rp / rc / rn: rows y-1, y, y+1 in shared memory (RS cells each); act: ballot of the
@@ -317,6 +331,7 @@ struct SweepWarp {
     // rank into the low bits of the key turns the selection into a warp-shuffle min.
     __device__ __forceinline__ void detail_row(int y, const CellT* rp, const CellT* rc, const CellT* rn, uint32_t act) {
         CellT* const state = reinterpret_cast<CellT*>(p.state);
+        const long long row_idx = env_off + (long long)y * p.pitch;  // cell index of (y, x = 0)
         uint32_t groups = 0;
         for (uint32_t a = act; a; a &= a - 1) groups |= seg_lut[__ffs(a) - 1];  // warp-uniform
         while (groups) {  // warp-uniform
@@ -337,10 +352,9 @@ struct SweepWarp {
             const int x = x0 + col;
             const bool owner = lane >= 1 && lane <= GW && col < WR && x < p.W;
             int s = cc & 7;
-            const long long idx = env_off + (long long)y * p.pitch + x;
             if (owner && (cc >> 3) != 0) {
                 if (kc == NO_SRC) {  // duration reached max_fire_duration (fire.py:116-161)
-                    state[idx] = (CellT)ST_BURNED;
+                    state[row_idx + x] = (CellT)ST_BURNED;
                     s = ST_BURNED;
                 } else {
                     f_live = 1;
@@ -363,7 +377,7 @@ struct SweepWarp {
             }
             const uint32_t pm = __ballot_sync(0xffffffffu, push);
             if (pm) {
-                if (push) wq[wcount + __popc(pm & ((1u << lane) - 1))] = make_item(idx, dir, s);
+                if (push) wq[wcount + __popc(pm & ((1u << lane) - 1))] = make_item(row_idx + x, dir, s);
                 wcount += __popc(pm);
                 if (wcount > WQ_CAP - 32) flush();
             }
@@ -408,7 +422,7 @@ constexpr int TMA_STAGES = SFB_TMA_STAGES;           // boxes in the per-warp ri
 constexpr int TMA_ROW_BYTES = 544;                   // 16 B pad | 512 B | 16 B pad
 constexpr int TMA_BOX_BYTES = TMA_BOX_ROWS * TMA_ROW_BYTES;
 constexpr int TMA_RING_ROWS = TMA_BOX_ROWS * TMA_STAGES;
-constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128 + 128;  // ring | work items | mbarriers | seg_lut
+constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128 + 256;  // ring | work items | mbarriers | seg_lut, key_lut
 static_assert(TMA_WARP_SMEM % 128 == 0 && TMA_BOX_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
 constexpr int TMA_BLOCK_SMEM = SWEEP_WARPS * TMA_WARP_SMEM + 128;              // + alignment slack
 
@@ -558,7 +572,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
     constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
     __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
     __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
-    __shared__ uint32_t lut_all[SWEEP_WARPS][32];
+    __shared__ uint32_t lut_all[SWEEP_WARPS][64];  // seg_lut | key_lut
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SW::build_seg_lut(lut_all[warp], lane);
