@@ -360,10 +360,12 @@ def gpu_arm(args):
     # ---- dominant-kernel timing for the roofline (separate, per-step synchronised pass)
     eng.set_kernel_timing(True)
     eng.step(args.roofline_steps)
-    sweep_ms, eval_ms, n_t = eng.kernel_ms()
+    sweep_ms, rows_ms, eval_ms, n_t = eng.kernel_ms()
     eng.set_kernel_timing(False)
     q_entries, q_cap, q_ovf = eng.queue_stats()
+    row_tasks, _ = eng.row_tasks()
     sweep_s = sweep_ms / n_t * 1e-3
+    rows_s = rows_ms / n_t * 1e-3
     eval_s = eval_ms / n_t * 1e-3
 
     if not args.no_track:
@@ -419,10 +421,11 @@ def gpu_arm(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
 
     # algorithmic bytes per launch of k_sweep in THIS design (DESIGN.md "Kernels"): every cell's
-    # packed state is read once (1 B/cell-update) plus one halo row pair per chunk; work items
-    # are 8 B each.  The survey's figure (a kernel that streams all planes) is kept beside it.
+    # packed state is read once (1 B/cell-update; halo rows and pads are re-read from L2) and
+    # an 8-byte row task is written per warp-row that needs a closer look.  The survey's figure
+    # (a kernel that streams all planes) is kept beside it.
     cells_rank = H * W * E
-    sweep_bytes = cells_rank * 1.0 + q_entries * 8.0
+    sweep_bytes = cells_rank * 1.0 + row_tasks * 8.0
     achieved = sweep_bytes / sweep_s / 1e9
     survey_b = SURVEY_BYTES_SHARED(E) if shared else SURVEY_BYTES_PER_ENV_STATIC
     line = {
@@ -448,12 +451,12 @@ def gpu_arm(args):
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "traffic": load_traffic_note(args.workload),
             "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,
-            "ms_per_launch": sweep_s * 1e3, "k_eval_ms_per_launch": eval_s * 1e3,
-            "sweep_share_of_step": sweep_s / (sweep_s + eval_s),
-            "work_items_per_step": q_entries, "queue_overflowed": q_ovf,
+            "ms_per_launch": sweep_s * 1e3, "k_rows_ms_per_launch": rows_s * 1e3, "k_eval_ms_per_launch": eval_s * 1e3,
+            "sweep_share_of_step": sweep_s / (sweep_s + rows_s + eval_s),
+            "row_tasks_per_step": row_tasks, "work_items_per_step": q_entries, "queue_overflowed": q_ovf,
             "survey_model": {"bytes_per_cell_update": survey_b,
-                             "achieved": cells_rank * survey_b / (sweep_s + eval_s) / 1e9,
-                             "frac": cells_rank * survey_b / (sweep_s + eval_s) / 1e9 / peak_gbs,
+                             "achieved": cells_rank * survey_b / (sweep_s + rows_s + eval_s) / 1e9,
+                             "frac": cells_rank * survey_b / (sweep_s + rows_s + eval_s) / 1e9 / peak_gbs,
                              "note": "SURVEY.md 8d counts a kernel that streams every plane each step; this design "
                                      "sweeps 1 B/cell and gathers the rest only at the fire front"},
         },

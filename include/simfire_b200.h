@@ -258,11 +258,13 @@ int sfb_set_stream(sfb_sim* sim, void* stream);
 int sfb_get_stream(sfb_sim* sim, void** stream);
 /* Kernel launches issued by this handle so far (all kernels / hot-path kernels only). */
 int sfb_get_launch_counts(sfb_sim* sim, int64_t* all_kernels, int64_t* step_kernels);
-/* Per-kernel device time: while enabled every step records events around the sweep and
- * the evaluate kernel.  sfb_get_kernel_ms returns the accumulated milliseconds and launch
- * counts since enabling and resets them. */
+/* Per-kernel device time: while enabled every step records events around its three kernels
+ * (k_sweep, k_rows, k_eval).  sfb_get_kernel_ms returns the accumulated milliseconds and the
+ * number of steps since enabling and resets them. */
 int sfb_set_kernel_timing(sfb_sim* sim, int32_t enabled);
-int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* eval_ms, int64_t* n_steps);
+int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* eval_ms, int64_t* n_steps);
+/* Row tasks (warp-rows that needed a cell-by-cell look) emitted by the last completed step. */
+int sfb_get_row_tasks(sfb_sim* sim, int64_t* tasks, int64_t* capacity);
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and
  * whether the step overflowed the queue and ran the dense fallback. */
 int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32_t* overflowed);

@@ -27,7 +27,7 @@ EXPORTS = (
     "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
     "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
     "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab", "sfb_set_tracking",
-    "sfb_set_elevation",
+    "sfb_set_elevation", "sfb_get_row_tasks",
 )  # fmt: skip
 
 
@@ -99,7 +99,9 @@ def load() -> C.CDLL:
         "sfb_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "sfb_get_launch_counts": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "sfb_set_kernel_timing": (C.c_int, [vp, i32]),
-        "sfb_get_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
+        "sfb_get_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(i64)]),
+        "sfb_get_row_tasks": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "sfb_get_queue_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_device_bytes": (C.c_int, [vp, C.POINTER(i64)]),
         "sfb_rate_of_spread": (C.c_int, [i32, vp, vp, vp, i64, vp]),

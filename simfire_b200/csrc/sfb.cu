@@ -113,6 +113,7 @@ struct sfb_sim {
     int cell_bytes;   // 1 or 2
     int use_tma;      // sweep front end
     int sweep_blocks; // persistent grid of the sweep kernel
+    int rows_blocks;  // persistent grid of k_rows
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
@@ -122,7 +123,7 @@ struct sfb_sim {
     int n_sm;
     cudaStream_t stream;      // stream in use
     cudaStream_t own_stream;  // created by the handle
-    cudaEvent_t ev[3];
+    cudaEvent_t ev[4];
     // scratch
     void* stage;          // device staging for host <-> device plane traffic
     size_t stage_bytes;
@@ -133,7 +134,7 @@ struct sfb_sim {
     int64_t launches_all, launches_step;
     int64_t dev_bytes;
     int timing;
-    double sweep_ms, eval_ms;
+    double sweep_ms, rows_ms, eval_ms;
     int64_t timed_steps;
     int64_t last_entries;
     int last_overflow;
@@ -469,6 +470,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.qcount);
     cudaFree(s->d.overflow);
     cudaFree(s->d.unit_next);
+    cudaFree(s->d.rows);
     if (s->log_mapped) cudaFreeHost(s->log_mapped);
     else cudaFree(s->d.chg);
     cudaFree(s->d.chg_count);
@@ -556,7 +558,11 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
     if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
     if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
-    if ((rc = dmalloc(s, &d.unit_next, 2 * sizeof(unsigned long long)))) return rc;
+    if ((rc = dmalloc(s, &d.unit_next, 6 * sizeof(unsigned long long)))) return rc;  // unit_next | rows_count | rows_next
+    d.rows_count = d.unit_next + 2;
+    d.rows_next = d.unit_next + 4;
+    d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
+    if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
     d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
     if (d.track) {
         // The log lives in pinned HOST memory mapped into the device address space: k_eval's
@@ -574,7 +580,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
         CU(cudaMallocHost((void**)&s->log_head, 2 * sizeof(unsigned long long)));
     }
-    CU(cudaMemsetAsync(d.unit_next, 0, 2 * sizeof(unsigned long long), s->stream));
+    CU(cudaMemsetAsync(d.unit_next, 0, 6 * sizeof(unsigned long long), s->stream));
     {
         const size_t n = (size_t)d.pitch + 32;
         std::vector<uint8_t> fill(n * s->cell_bytes, 0);
@@ -623,6 +629,12 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: sweep kernel does not fit on an SM");
         const long long need = (d.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
         s->sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
+        int rows_per_sm = 0;
+        if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint8_t>, ROWS_WARPS * 32, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint16_t>, ROWS_WARPS * 32, 0));
+        if (rows_per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_rows does not fit on an SM");
+        const long long rows_need = (d.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
+        s->rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
     }
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
@@ -882,7 +894,9 @@ static int enqueue_sweep(sfb_sim* s) {
         DISPATCH(s, k_sweep_ldg, (unsigned)s->sweep_blocks, SWEEP_WARPS * 32, d, par);
     }
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
-    s->launches_step += 1;
+    DISPATCH(s, k_rows, (unsigned)s->rows_blocks, ROWS_WARPS * 32, d, par);
+    if (s->timing) CU(cudaEventRecord(s->ev[2], s->stream));
+    s->launches_step += 2;
     s->in_step = 1;
     return 0;
 }
@@ -899,13 +913,15 @@ static int enqueue_eval(sfb_sim* s) {
     s->parity ^= 1;
     s->in_step = 0;
     if (s->timing) {
-        CU(cudaEventRecord(s->ev[2], s->stream));
-        CU(cudaEventSynchronize(s->ev[2]));
-        float a = 0, b = 0;
+        CU(cudaEventRecord(s->ev[3], s->stream));
+        CU(cudaEventSynchronize(s->ev[3]));
+        float a = 0, b = 0, c = 0;
         CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
         CU(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+        CU(cudaEventElapsedTime(&c, s->ev[2], s->ev[3]));
         s->sweep_ms += a;
-        s->eval_ms += b;
+        s->rows_ms += b;
+        s->eval_ms += c;
         s->timed_steps++;
     }
     return 0;
@@ -1345,17 +1361,18 @@ extern "C" int sfb_get_launch_counts(sfb_sim* s, int64_t* all_kernels, int64_t* 
 extern "C" int sfb_set_kernel_timing(sfb_sim* s, int32_t enabled) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_set_kernel_timing: null handle");
     s->timing = enabled != 0;
-    s->sweep_ms = s->eval_ms = 0;
+    s->sweep_ms = s->rows_ms = s->eval_ms = 0;
     s->timed_steps = 0;
     return 0;
 }
 
-extern "C" int sfb_get_kernel_ms(sfb_sim* s, double* sweep_ms, double* eval_ms, int64_t* n_steps) {
+extern "C" int sfb_get_kernel_ms(sfb_sim* s, double* sweep_ms, double* rows_ms, double* eval_ms, int64_t* n_steps) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_get_kernel_ms: null handle");
     if (sweep_ms) *sweep_ms = s->sweep_ms;
+    if (rows_ms) *rows_ms = s->rows_ms;
     if (eval_ms) *eval_ms = s->eval_ms;
     if (n_steps) *n_steps = s->timed_steps;
-    s->sweep_ms = s->eval_ms = 0;
+    s->sweep_ms = s->rows_ms = s->eval_ms = 0;
     s->timed_steps = 0;
     return 0;
 }
@@ -1375,6 +1392,18 @@ extern "C" int sfb_get_queue_stats(sfb_sim* s, int64_t* entries, int64_t* capaci
     if (entries) *entries = (int64_t)cnt;
     if (capacity) *capacity = s->d.qcap;
     if (overflowed) *overflowed = ovf;
+    return 0;
+}
+
+extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_row_tasks: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    unsigned long long cnt = 0;
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(&cnt, s->d.rows_count + (s->parity ^ 1), sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (tasks) *tasks = (int64_t)cnt;
+    if (capacity) *capacity = s->d.rows_cap;
     return 0;
 }
 

@@ -96,6 +96,10 @@ struct DevParams {
     unsigned long long* qcount; // [2]
     int32_t* overflow;          // [2]
     unsigned long long* unit_next;  // [2] next sweep unit to hand out (dynamic scheduling)
+    unsigned long long* rows;       // [rows_cap] row tasks written by k_sweep, consumed by k_rows
+    unsigned long long* rows_count; // [2]
+    unsigned long long* rows_next;  // [2] next row task to hand out
+    int64_t rows_cap;
     // slab mode: rows -1 and H of this slab live in a neighbour slab (peer device memory)
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
@@ -206,31 +210,71 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
 }
 
 // ---------------------------------------------------------------------------------------
-// k_sweep: one warp per (env, chunk of rows, strip of 32 x CPL columns).
+// The sweep is split in two kernels so that the expensive part is load-balanced:
 //
-// Common part (SweepWarp): the cell-by-cell examination of one row, entered only if the
-// three-row window around it holds a sprite code (or, with attenuation, a control line).
-// The window lives in shared memory as rows of RS cells: CPL pad | 32*CPL cells | CPL pad,
-// so the eight neighbours of every cell are plain byte reads.
+//   k_sweep_*  pure streaming: one persistent warp per (env, chunk of rows, strip of 512 B of
+//              columns) unit; decides per warp-row (one AND per 32-bit word) whether its 3-row
+//              window holds a sprite code (or, with attenuation, a control line) and, if so,
+//              appends an 8-byte row task to a list.  Nothing else: no state writes.
+//   k_rows     one warp per row task: re-reads the three rows (L2 / L1 hits: they were just
+//              streamed), stages them in shared memory as CPL pad | 32*CPL cells | CPL pad so that
+//              the eight neighbours of every cell are plain byte reads, and examines the row cell
+//              by cell (RowWorker::detail_row): prune, candidate search with a warp-shuffle min,
+//              work items for k_eval.  Row tasks cost about the same, so a fire front that sits
+//              in a few units no longer serialises inside the few warps that own them.
 //
-// Two streaming front ends feed it:
+// Two streaming front ends:
 //   k_sweep_tma  TMA (cp.async.bulk.tensor) boxes of 8 rows x 544 B land in a per-warp
-//                shared-memory ring, completion on mbarriers, 2 boxes in flight per warp;
+//                shared-memory ring, completion on mbarriers, all stages in flight;
 //                out-of-grid cells are zero-filled by the TMA unit.  Default.
-//   k_sweep_ldg  128-bit global loads into a register window, four rows in flight; rows
-//                outside the grid are read from a row of BURNED filler cells.
+//   k_sweep_ldg  128-bit global loads, four rows in flight; rows outside the grid are read from
+//                a row of BURNED filler cells (or from the neighbour slab in slab mode).
 // ---------------------------------------------------------------------------------------
 #ifndef SFB_SWEEP_WARPS
 #define SFB_SWEEP_WARPS 4
 #endif
 #ifndef SFB_LDG_MIN_BLOCKS
-#define SFB_LDG_MIN_BLOCKS 6
+#define SFB_LDG_MIN_BLOCKS 8
 #endif
 constexpr int SWEEP_WARPS = SFB_SWEEP_WARPS;
 constexpr int WQ_CAP = 96;  // >= 64: a flush is forced whenever fewer than 32 slots are free
 
+// row task: y | strip << 20 | env << 28
+__device__ __forceinline__ unsigned long long make_row_task(int env, int y, int strip) {
+    return (unsigned long long)(unsigned)y | ((unsigned long long)(unsigned)strip << 20) | ((unsigned long long)(unsigned)env << 28);
+}
+
+// per-warp staging of row tasks in shared memory, one global atomic per flush
+struct RowTaskList {
+    const DevParams& p;
+    int par, lane;
+    unsigned long long* buf;  // [WQ_CAP] shared
+    int count = 0;            // warp-uniform
+    __device__ __forceinline__ RowTaskList(const DevParams& p_, int par_, int lane_, unsigned long long* buf_)
+        : p(p_), par(par_), lane(lane_), buf(buf_) {}
+    // every lane calls; lanes with `have` contribute one task
+    __device__ __forceinline__ void push(bool have, unsigned long long task) {
+        const uint32_t m = __ballot_sync(0xffffffffu, have);
+        if (!m) return;
+        if (have) buf[count + __popc(m & ((1u << lane) - 1))] = task;
+        count += __popc(m);
+        if (count > WQ_CAP - 32) flush();
+    }
+    __device__ __forceinline__ void flush() {
+        if (count == 0) return;
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.rows_count + par, (unsigned long long)count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < count; i += 32)
+            if (base + i < (unsigned long long)p.rows_cap) p.rows[base + i] = buf[i];
+        count = 0;
+        __syncwarp();
+    }
+};
+
 template <typename CellT>
-struct SweepWarp {
+struct RowWorker {
     using C = Cell<CellT>;
     static constexpr int CPL = C::CPL;
     static constexpr int WR = 32 * CPL;      // cells per warp row
@@ -253,9 +297,9 @@ struct SweepWarp {
     }
 
     const DevParams& p;
-    int par, lane, env, x0, y_end, tm1, max_dur;
-    bool spread, diagonal, attenuate;
-    long long env_off;
+    int par, lane, env = -1, x0 = 0, tm1 = 0, max_dur;
+    bool spread = false, diagonal, attenuate;
+    long long env_off = 0;
     uint32_t look_mask;
     unsigned long long* wq;
     const uint32_t* seg_lut;
@@ -263,20 +307,36 @@ struct SweepWarp {
     int wcount = 0;  // warp-uniform
     int f_live = 0, f_cand = 0;
 
-    __device__ __forceinline__ SweepWarp(const DevParams& p_, int par_, int lane_, int env_, int strip, int chunk,
-                                         const EnvMeta& m, unsigned long long* wq_, const uint32_t* lut_)
-        : p(p_), par(par_), lane(lane_), env(env_), wq(wq_), seg_lut(lut_),
+    __device__ __forceinline__ RowWorker(const DevParams& p_, int par_, int lane_, unsigned long long* wq_,
+                                         const uint32_t* lut_)
+        : p(p_), par(par_), lane(lane_), wq(wq_), seg_lut(lut_),
           key_lut(reinterpret_cast<int*>(const_cast<uint32_t*>(lut_)) + 32) {
-        x0 = strip * WR;
-        y_end = min((chunk + 1) * p.rows_per_chunk, p.H);
-        tm1 = (m.t - 1) % C::M;
         max_dur = p.max_dur;
-        spread = !m.time_quit;
         diagonal = p.diagonal != 0;
         attenuate = p.attenuate != 0;
-        env_off = (long long)env * p.plane;
         look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
+    }
+
+    // switch to another env: publish the flags gathered for the previous one, rebuild what
+    // depends on the env's clock
+    __device__ __forceinline__ void set_env(int env_, const EnvMeta& m) {
+        publish_flags();
+        env = env_;
+        tm1 = (m.t - 1) % C::M;
+        spread = !m.time_quit;
+        env_off = (long long)env * p.plane;
         build_key_lut();
+    }
+
+    __device__ __forceinline__ void publish_flags() {
+        f_live = __any_sync(0xffffffffu, f_live);
+        f_cand = __any_sync(0xffffffffu, f_cand);
+        if (env >= 0 && lane == 0) {
+            EnvMeta* mp = p.meta + (long long)par * p.E + env;
+            if (f_live) mp->any_live = 1;
+            if (f_cand) mp->any_cand = 1;
+        }
+        f_live = f_cand = 0;
     }
 
     // does this lane's segment (plus, for lanes 0 / 31, the cell outside the strip) need a look?
@@ -384,20 +444,15 @@ struct SweepWarp {
         }
     }
 
-    __device__ __forceinline__ void finish(EnvMeta* mp) {
+    __device__ __forceinline__ void finish() {
         flush();
-        f_live = __any_sync(0xffffffffu, f_live);
-        f_cand = __any_sync(0xffffffffu, f_cand);
-        if (lane == 0) {
-            if (f_live) mp->any_live = 1;
-            if (f_cand) mp->any_cand = 1;
-        }
+        publish_flags();
     }
 };
 
+
 // Warps are persistent: each pulls the next (env, chunk, strip) unit from a device counter,
-// so a warp that drew a quiet piece of map immediately takes another one instead of idling
-// until its block retires.
+// so a warp that drew a short unit immediately takes another one.
 __device__ __forceinline__ bool next_unit(const DevParams& p, int par, int lane, int& strip, int& chunk, int& env) {
     unsigned long long unit = 0;
     if (lane == 0) unit = atomicAdd(p.unit_next + par, 1ULL);
@@ -422,7 +477,7 @@ constexpr int TMA_STAGES = SFB_TMA_STAGES;           // boxes in the per-warp ri
 constexpr int TMA_ROW_BYTES = 544;                   // 16 B pad | 512 B | 16 B pad
 constexpr int TMA_BOX_BYTES = TMA_BOX_ROWS * TMA_ROW_BYTES;
 constexpr int TMA_RING_ROWS = TMA_BOX_ROWS * TMA_STAGES;
-constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128 + 256;  // ring | work items | mbarriers | seg_lut, key_lut
+constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128;  // ring | row tasks | mbarriers
 static_assert(TMA_WARP_SMEM % 128 == 0 && TMA_BOX_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
 constexpr int TMA_BLOCK_SMEM = SWEEP_WARPS * TMA_WARP_SMEM + 128;              // + alignment slack
 
@@ -457,20 +512,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
 template <typename CellT>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const int par) {
-    using SW = SweepWarp<CellT>;
-    constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
+    using C = Cell<CellT>;
+    constexpr int CPL = C::CPL, WR = 32 * CPL, RS = WR + 2 * CPL;
     constexpr int B = TMA_BOX_ROWS, NR = TMA_RING_ROWS;
+    constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
     static_assert(RS * sizeof(CellT) == TMA_ROW_BYTES, "row bytes");
+    static_assert(B <= 16, "halo ballot uses lanes 0 .. 2B-1");
     extern __shared__ unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127) + warp * TMA_WARP_SMEM;
     CellT* const ring = reinterpret_cast<CellT*>(base);
-    unsigned long long* const wq = reinterpret_cast<unsigned long long*>(base + NR * TMA_ROW_BYTES);
     const uint32_t bar0 = smem_u32(base + NR * TMA_ROW_BYTES + WQ_CAP * 8);
-    uint32_t* const seg_lut = reinterpret_cast<uint32_t*>(base + NR * TMA_ROW_BYTES + WQ_CAP * 8 + 128);
     const uint32_t ring_u32 = smem_u32(ring);
-    SW::build_seg_lut(seg_lut, lane);
+    RowTaskList tasks(p, par, lane, reinterpret_cast<unsigned long long*>(base + NR * TMA_ROW_BYTES));
+    const uint32_t look_mask = p.attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
 
     if (lane == 0) {
         for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -482,25 +538,22 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
 
     int strip, chunk, env;
     while (next_unit(p, par, lane, strip, chunk, env)) {
-        EnvMeta* const mp = p.meta + (long long)par * p.E + env;
-        const EnvMeta m = *mp;
-        if (!m.running) continue;
-        SW sw(p, par, lane, env, strip, chunk, m, wq, seg_lut);
+        if (!p.meta[(long long)par * p.E + env].running) continue;
+        const int x0 = strip * WR;
         const int y_begin = chunk * p.rows_per_chunk;
-        const int n_rows = sw.y_end - y_begin;           // rows this unit owns
+        const int n_rows = min(y_begin + p.rows_per_chunk, p.H) - y_begin;  // rows this unit owns
         const int n_box = (n_rows + 2 + B - 1) / B;      // local row j <-> grid row y_begin - 1 + j
-        const int c0 = (sw.x0 - CPL) * (int)sizeof(CellT) / 4;
+        const int c0 = (x0 - CPL) * (int)sizeof(CellT) / 4;
         const uint32_t kb = boxes_done;                  // global index of this unit's box 0
-        auto slot_of_row = [&](int j) { return (int)((kb * B + (uint32_t)j) % NR); };
 
         auto issue_box = [&](int k) {  // lane 0 only
             const uint32_t st = (kb + k) % TMA_STAGES;
             mbar_expect_tx(bar0 + 8 * st, TMA_BOX_BYTES);
             tma_load_3d(ring_u32 + st * TMA_BOX_BYTES, &tmap, c0, y_begin - 1 + k * B, env, bar0 + 8 * st);
         };
-        __syncwarp();  // every lane is done with the previous unit's rows
+        __syncwarp();  // every lane is done with the previous unit's boxes
         if (lane == 0)
-            for (int k = 0; k < min(n_box, TMA_STAGES - 1); ++k) issue_box(k);
+            for (int k = 0; k < min(n_box, TMA_STAGES); ++k) issue_box(k);
 
         // bit i of `nz`: local row (k*B - 2 + i) holds something to look at; two rows carried over
         uint32_t carry = 0;
@@ -512,7 +565,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
 #pragma unroll
             for (int i = 0; i < B; ++i) {
                 const uint4 v = *reinterpret_cast<const uint4*>(box + i * RS + CPL + lane * CPL);
-                const bool a = (((v.x | v.y) | (v.z | v.w)) & sw.look_mask) != 0;
+                const bool a = (((v.x | v.y) | (v.z | v.w)) & look_mask) != 0;
                 if (__any_sync(0xffffffffu, a)) nz |= 4u << i;
             }
             if (p.strips > 1) {  // cells just outside the strip: lanes 0..B-1 the left pad of row `lane`, B..2B-1 the right pad
@@ -521,144 +574,189 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
                     const unsigned char* rowb = reinterpret_cast<const unsigned char*>(box + (lane & (B - 1)) * RS);
                     hw = *reinterpret_cast<const uint32_t*>(rowb + (lane < B ? 12 : TMA_ROW_BYTES - 16));
                     // only the adjacent cell counts: the last cell of the left pad, the first of the right pad
-                    hw = lane < B ? (hw >> (32 - 8 * (int)sizeof(CellT))) : (hw & SW::CELL_ALL);
+                    hw = lane < B ? (hw >> (32 - 8 * (int)sizeof(CellT))) : (hw & CELL_ALL);
                 }
-                const uint32_t hb = __ballot_sync(0xffffffffu, (hw & sw.look_mask & SW::CELL_ALL) != 0);
+                const uint32_t hb = __ballot_sync(0xffffffffu, (hw & look_mask & CELL_ALL) != 0);
                 nz |= ((hb | (hb >> B)) & ((1u << B) - 1u)) << 2;
             }
             carry = nz >> B;
-            // local row j = k*B - 1 + i is complete once box k is here (its row j+1 = k*B + i), i = 0..B-1
-            uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
-            while (rows) {  // warp-uniform
-                const int i = __ffs(rows) - 1;
-                rows &= rows - 1;
-                const int j = k * B - 1 + i;
-                if (j < 1 || j > n_rows) continue;
-                const CellT* rp = ring + slot_of_row(j - 1) * RS;
-                const CellT* rc = ring + slot_of_row(j) * RS;
-                const CellT* rn = ring + slot_of_row(j + 1) * RS;
-                const uint4 vp = *reinterpret_cast<const uint4*>(rp + CPL + lane * CPL);
-                const uint4 vc = *reinterpret_cast<const uint4*>(rc + CPL + lane * CPL);
-                const uint4 vn = *reinterpret_cast<const uint4*>(rn + CPL + lane * CPL);
-                uint32_t hcell = 0;
-                if (p.strips > 1) {  // otherwise both pads are out of the grid (zero-filled)
-                    if (lane == 0) hcell = (uint32_t)rp[CPL - 1] | rc[CPL - 1] | rn[CPL - 1];
-                    if (lane == 31) hcell = (uint32_t)rp[CPL + WR] | rc[CPL + WR] | rn[CPL + WR];
-                }
-                const uint4 vo = make_uint4(vp.x | vc.x | vn.x, vp.y | vc.y | vn.y, vp.z | vc.z | vn.z, vp.w | vc.w | vn.w);
-                const uint32_t act = __ballot_sync(0xffffffffu, sw.seg_needs_look(vo, hcell));
-                sw.detail_row(y_begin - 1 + j, rp, rc, rn, act);
-            }
-            // box k-1 is dead now (its last row was the `prev` of this box's first row): refill its slot
+            // the box is consumed (only `nz` survives): refill its slot right away
             __syncwarp();
-            if (lane == 0 && k + TMA_STAGES - 1 < n_box) issue_box(k + TMA_STAGES - 1);
+            if (lane == 0 && k + TMA_STAGES < n_box) issue_box(k + TMA_STAGES);
+            // local row j = k*B - 1 + i is decided once box k is here (its row j+1 = k*B + i), i = 0..B-1
+            const uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
+            if (rows) {  // warp-uniform
+                const int j = k * B - 1 + lane;
+                tasks.push(lane < B && ((rows >> lane) & 1u) && j >= 1 && j <= n_rows, make_row_task(env, y_begin - 1 + j, strip));
+            }
         }
         boxes_done += (uint32_t)n_box;
-        sw.finish(mp);
     }
+    tasks.flush();
 }
 
-// ---- front end 2: register window -------------------------------------------------------
-struct RowRegs {
-    uint4 v;     // this lane's CPL cells
-    uint32_t h;  // lane 0: cell left of the strip, lane 31: cell right of it
-    uint32_t b;  // ballot: lanes whose segment needs a look
-};
-
+// ---- front end 2: 128-bit loads ------------------------------------------------------------
 template <typename CellT>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_ldg(const DevParams p, const int par) {
-    using SW = SweepWarp<CellT>;
     using C = Cell<CellT>;
-    constexpr int CPL = SW::CPL, WR = SW::WR, RS = SW::RS;
-    __shared__ __align__(16) CellT sm_all[SWEEP_WARPS][3][RS];
-    __shared__ unsigned long long wq_all[SWEEP_WARPS][WQ_CAP];  // per-warp staging of work items
-    __shared__ uint32_t lut_all[SWEEP_WARPS][64];  // seg_lut | key_lut
+    constexpr int CPL = C::CPL, WR = 32 * CPL;
+    constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
+    __shared__ unsigned long long tl_all[SWEEP_WARPS][WQ_CAP];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SW::build_seg_lut(lut_all[warp], lane);
     const int H = p.H, pitch = p.pitch;
     const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;  // valid for [-CPL, pitch + CPL)
-    CellT(*sm)[RS] = sm_all[warp];
+    RowTaskList tasks(p, par, lane, tl_all[warp]);
+    const uint32_t look_mask = p.attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
 
     int strip, chunk, env;
     while (next_unit(p, par, lane, strip, chunk, env)) {
-    EnvMeta* const mp = p.meta + (long long)par * p.E + env;
-    const EnvMeta m = *mp;
-    if (!m.running) continue;
-    SW sw(p, par, lane, env, strip, chunk, m, wq_all[warp], lut_all[warp]);
-    const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + sw.env_off;
-    const int x0 = sw.x0;
-    const int xl = x0 + lane * CPL;
-    const int y_begin = chunk * p.rows_per_chunk;
-    const int y_end = sw.y_end;
-    const bool in_x = xl < pitch;
-    // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
-    const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
-    const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
+        if (!p.meta[(long long)par * p.E + env].running) continue;
+        const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + (long long)env * p.plane;
+        const int x0 = strip * WR;
+        const int xl = x0 + lane * CPL;
+        const int y_begin = chunk * p.rows_per_chunk;
+        const int y_end = min(y_begin + p.rows_per_chunk, H);
+        const bool in_x = xl < pitch;
+        // lanes 0 / 31 fetch the cell just outside the strip (if there is one)
+        const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
+        const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
 
-    // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
-    auto edge_row = [&](int y) -> const CellT* {
-        if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
-        if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
-        return filler;
-    };
-    auto issue = [&](const CellT* rowp, RowRegs& r) {
-        r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
-        r.h = ST_BURNED;
-        if (in_x) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
-        if (hpred) r.h = rowp[hoff];
-    };
-    auto finish = [&](RowRegs& r) { r.b = __ballot_sync(0xffffffffu, sw.seg_needs_look(r.v, r.h)); };
+        // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
+        auto edge_row = [&](int y) -> const CellT* {
+            if (y == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
+            if (y == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
+            return filler;
+        };
+        struct Row { uint4 v; uint32_t h; };
+        auto issue = [&](const CellT* rowp, Row& r) {
+            r.v = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+            r.h = ST_BURNED;
+            if (in_x) r.v = *reinterpret_cast<const uint4*>(rowp + xl);
+            if (hpred) r.h = rowp[hoff];
+        };
+        auto busy = [&](const Row& r) -> bool {  // warp-uniform: does the row hold anything to look at?
+            const uint32_t a = (((r.v.x | r.v.y) | (r.v.z | r.v.w)) & look_mask) | (r.h & look_mask & CELL_ALL);
+            return __any_sync(0xffffffffu, a != 0);
+        };
 
-    auto process_row = [&](int y, const RowRegs& rp, const RowRegs& rc, const RowRegs& rn) {
-        const uint32_t act = rp.b | rc.b | rn.b;
-        if (act == 0 || y >= y_end) return;  // warp-uniform
-        __syncwarp();
-        *reinterpret_cast<uint4*>(&sm[0][CPL + lane * CPL]) = rp.v;
-        *reinterpret_cast<uint4*>(&sm[1][CPL + lane * CPL]) = rc.v;
-        *reinterpret_cast<uint4*>(&sm[2][CPL + lane * CPL]) = rn.v;
-        if (lane == 0) { sm[0][CPL - 1] = (CellT)rp.h; sm[1][CPL - 1] = (CellT)rc.h; sm[2][CPL - 1] = (CellT)rn.h; }
-        if (lane == 31) { sm[0][CPL + WR] = (CellT)rp.h; sm[1][CPL + WR] = (CellT)rc.h; sm[2][CPL + WR] = (CellT)rn.h; }
-        __syncwarp();
-        sw.detail_row(y, sm[0], sm[1], sm[2], act);
-    };
-
-    // rolling three-row window; the four loads of a batch are issued before any is used
-    RowRegs r0, r1, r2, r3, r4, r5;
-    const CellT* rowp = envbase + (long long)y_begin * pitch;  // row y of the loop below
-    issue(y_begin > 0 ? rowp - pitch : edge_row(-1), r0);
-    issue(rowp, r1);
-    finish(r0);
-    finish(r1);
-    for (int y = y_begin; y < y_end; y += 4) {
-        const CellT* q1 = rowp + pitch;
-        const CellT* q2 = q1 + pitch;
-        const CellT* q3 = q2 + pitch;
-        const CellT* q4 = q3 + pitch;
-        if (y + 4 >= H) {  // warp-uniform, last batch of the grid only
-            if (y + 1 >= H) q1 = edge_row(y + 1);
-            if (y + 2 >= H) q2 = edge_row(y + 2);
-            if (y + 3 >= H) q3 = edge_row(y + 3);
-            q4 = edge_row(y + 4);
+        // rolling window of "busy" flags; the four loads of a batch are issued before any is used
+        Row r2, r3, r4, r5;
+        const CellT* rowp = envbase + (long long)y_begin * pitch;  // row y of the loop below
+        issue(y_begin > 0 ? rowp - pitch : edge_row(-1), r2);
+        issue(rowp, r3);
+        bool b0 = busy(r2), b1 = busy(r3);
+        for (int y = y_begin; y < y_end; y += 4) {
+            const CellT* q1 = rowp + pitch;
+            const CellT* q2 = q1 + pitch;
+            const CellT* q3 = q2 + pitch;
+            const CellT* q4 = q3 + pitch;
+            if (y + 4 >= H) {  // warp-uniform, last batch of the grid only
+                if (y + 1 >= H) q1 = edge_row(y + 1);
+                if (y + 2 >= H) q2 = edge_row(y + 2);
+                if (y + 3 >= H) q3 = edge_row(y + 3);
+                q4 = edge_row(y + 4);
+            }
+            issue(q1, r2);
+            issue(q2, r3);
+            issue(q3, r4);
+            issue(q4, r5);
+            const bool b2 = busy(r2), b3 = busy(r3), b4 = busy(r4), b5 = busy(r5);
+            // rows y .. y+3: lane i decides row y + i
+            const uint32_t rows = ((b0 | b1 | b2) ? 1u : 0u) | ((b1 | b2 | b3) ? 2u : 0u) | ((b2 | b3 | b4) ? 4u : 0u) |
+                                  ((b3 | b4 | b5) ? 8u : 0u);
+            if (rows) tasks.push(lane < 4 && ((rows >> lane) & 1u) && y + lane < y_end, make_row_task(env, y + lane, strip));
+            b0 = b4;
+            b1 = b5;
+            rowp = q4;
         }
-        issue(q1, r2);
-        issue(q2, r3);
-        issue(q3, r4);
-        issue(q4, r5);
-        finish(r2);
-        finish(r3);
-        finish(r4);
-        finish(r5);
-        process_row(y, r0, r1, r2);
-        process_row(y + 1, r1, r2, r3);
-        process_row(y + 2, r2, r3, r4);
-        process_row(y + 3, r3, r4, r5);
-        r0 = r4;
-        r1 = r5;
-        rowp = q4;
     }
-    sw.finish(mp);
-    }  // units
+    tasks.flush();
+}
+
+// ---------------------------------------------------------------------------------------
+// k_rows: the row tasks are split in equal contiguous ranges, one per warp (consecutive tasks are
+// mostly consecutive rows of one env, so two of the three rows of a task come from L1); the
+// loads of task t+1 are in flight while task t is examined.
+// ---------------------------------------------------------------------------------------
+constexpr int ROWS_WARPS = 4;
+
+template <typename CellT>
+__global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, const int par) {
+    using RW = RowWorker<CellT>;
+    using C = Cell<CellT>;
+    constexpr int CPL = RW::CPL, WR = RW::WR, RS = RW::RS;
+    __shared__ __align__(16) CellT sm_all[ROWS_WARPS][3][RS];
+    __shared__ unsigned long long wq_all[ROWS_WARPS][WQ_CAP];  // per-warp staging of work items
+    __shared__ uint32_t lut_all[ROWS_WARPS][64];                // seg_lut | key_lut
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * ROWS_WARPS;
+    const unsigned long long w = (unsigned long long)blockIdx.x * ROWS_WARPS + warp;
+    const unsigned long long per = (n + n_warps - 1) / n_warps;
+    unsigned long long t = w * per;
+    const unsigned long long t_end = min(t + per, n);
+    if (t >= t_end) return;
+
+    RW::build_seg_lut(lut_all[warp], lane);
+    RW rw(p, par, lane, wq_all[warp], lut_all[warp]);
+    CellT(*sm)[RS] = sm_all[warp];
+    const int H = p.H, pitch = p.pitch;
+    const CellT* const state = reinterpret_cast<const CellT*>(p.state);
+    const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;
+
+    struct Loaded {
+        uint4 v[3];
+        uint32_t h[3];
+        int y, strip, env;
+    };
+    auto load = [&](unsigned long long task, Loaded& L) {
+        L.y = (int)(task & 0xFFFFFu);
+        L.strip = (int)((task >> 20) & 0xFFu);
+        L.env = (int)(task >> 28);
+        const int x0 = L.strip * WR;
+        const int xl = x0 + lane * CPL;
+        const bool in_x = xl < pitch;
+        const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
+        const bool hpred = (lane == 0 && L.strip > 0) || (lane == 31 && x0 + WR < pitch);
+        const CellT* const envbase = state + (long long)L.env * p.plane;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int yy = L.y - 1 + r;
+            const CellT* rowp = filler;
+            if (yy >= 0 && yy < H) rowp = envbase + (long long)yy * pitch;
+            else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)L.env * p.halo_top_plane;
+            else if (yy == H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)L.env * p.halo_bottom_plane;
+            L.v[r] = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+            L.h[r] = ST_BURNED;
+            if (in_x) L.v[r] = *reinterpret_cast<const uint4*>(rowp + xl);
+            if (hpred) L.h[r] = rowp[hoff];
+        }
+    };
+
+    Loaded cur, nxt;
+    load(p.rows[t], cur);
+    for (; t < t_end; ++t) {
+        const bool more = t + 1 < t_end;
+        if (more) load(p.rows[t + 1], nxt);  // in flight while `cur` is examined
+        if (cur.env != rw.env) rw.set_env(cur.env, p.meta[(long long)par * p.E + cur.env]);
+        rw.x0 = cur.strip * WR;
+        __syncwarp();  // the previous task's readers are done with the staging rows
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            *reinterpret_cast<uint4*>(&sm[r][CPL + lane * CPL]) = cur.v[r];
+            if (lane == 0) sm[r][CPL - 1] = (CellT)cur.h[r];
+            if (lane == 31) sm[r][CPL + WR] = (CellT)cur.h[r];
+        }
+        __syncwarp();
+        const uint4 vo = make_uint4(cur.v[0].x | cur.v[1].x | cur.v[2].x, cur.v[0].y | cur.v[1].y | cur.v[2].y,
+                                    cur.v[0].z | cur.v[1].z | cur.v[2].z, cur.v[0].w | cur.v[1].w | cur.v[2].w);
+        const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, cur.h[0] | cur.h[1] | cur.h[2]));
+        rw.detail_row(cur.y, sm[0], sm[1], sm[2], act);
+        if (more) cur = nxt;
+    }
+    rw.finish();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -756,6 +854,7 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
         p.qcount[par ^ 1] = 0;
         p.overflow[par ^ 1] = 0;
         p.unit_next[par ^ 1] = 0;
+        p.rows_count[par ^ 1] = 0;
     }
 }
 

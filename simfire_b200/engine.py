@@ -302,7 +302,7 @@ class FireEngine:
     def _parity_probe(self) -> int:
         # parity = number of completed steps mod 2 (every handle starts at 0)
         _, step_kernels = self.launch_counts()
-        return (step_kernels // 2) % 2
+        return (step_kernels // 3) % 2
 
     def flags_parity(self) -> int:
         return self._parity_probe()
@@ -326,9 +326,15 @@ class FireEngine:
         _lib.check(self._lib.sfb_set_kernel_timing(self._h, 1 if enabled else 0))
 
     def kernel_ms(self):
-        a, b, n = C.c_double(), C.c_double(), C.c_int64()
-        _lib.check(self._lib.sfb_get_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(n)))
-        return float(a.value), float(b.value), int(n.value)
+        """(k_sweep ms, k_rows ms, k_eval ms, steps) accumulated since timing was enabled."""
+        a, r, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self._lib.sfb_get_kernel_ms(self._h, C.byref(a), C.byref(r), C.byref(b), C.byref(n)))
+        return float(a.value), float(r.value), float(b.value), int(n.value)
+
+    def row_tasks(self):
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.sfb_get_row_tasks(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def queue_stats(self):
         a, b, o = C.c_int64(), C.c_int64(), C.c_int32()
