@@ -331,7 +331,8 @@ def gpu_arm(args):
         E = args.envs
     H, W = wl.H, wl.W
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
-                     sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, **wl.engine_kwargs())  # fmt: skip
+                     sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, env_groups=args.env_groups,
+                     **wl.engine_kwargs())  # fmt: skip
     eng.set_static(wl.planes)
     starts = wl.burnable_starts(E, seed=1000 + rank)
     eng.reset(starts)
@@ -478,6 +479,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--burn-in", type=int, default=60)
     ap.add_argument("--rows-per-chunk", type=int, default=0)
+    ap.add_argument("--env-groups", type=int, default=0, help="env groups stepped on separate streams (0 = auto)")
     ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
     ap.add_argument("--roofline-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)

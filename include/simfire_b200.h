@@ -113,7 +113,9 @@ typedef struct sfb_params {
     double max_time;           /* minutes; used when SFB_HAS_MAX_TIME */
     float h, S_T, S_e, p_p;    /* FuelParticle */
     float M_f;                 /* Environment.M_f */
-    int32_t reserved0;
+    int32_t env_groups;        /* 0 = auto; envs are stepped as this many independent groups on
+                                  separate CUDA streams (k_sweep of one overlaps k_rows / k_eval of
+                                  another); 1 in slab mode */
     int64_t queue_capacity;    /* 0 = auto; work-queue entries (8 B each) */
     /* Slab mode (single huge grid split in rows across handles): this handle holds rows
      * [slab_y0, slab_y0 + H) of a grid with slab_total_H rows.  0/0 = whole grid. */

@@ -37,7 +37,7 @@ class SfbParams(C.Structure):
         ("E", C.c_int32), ("max_fire_duration", C.c_int32), ("flags", C.c_int32),
         ("rows_per_chunk", C.c_int32), ("pixel_scale", C.c_double), ("update_rate", C.c_double),
         ("max_time", C.c_double), ("h", C.c_float), ("S_T", C.c_float), ("S_e", C.c_float),
-        ("p_p", C.c_float), ("M_f", C.c_float), ("reserved0", C.c_int32),
+        ("p_p", C.c_float), ("M_f", C.c_float), ("env_groups", C.c_int32),
         ("queue_capacity", C.c_int64), ("slab_y0", C.c_int32), ("slab_total_H", C.c_int32),
     ]  # fmt: skip
 

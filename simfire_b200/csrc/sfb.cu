@@ -107,9 +107,24 @@ class HostPool {
 // ---------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------
+// Envs never interact, so a handle steps them as G independent groups on G streams: while one
+// group is in its issue-bound kernels (k_rows, k_eval) another one streams (k_sweep), and the
+// hardware overlaps the two.  Each group sees its envs through a DevParams view with offset
+// plane pointers and its own work queue, row-task list and counters.
+struct EnvGroup {
+    DevParams d;
+    CUtensorMap tmap;
+    cudaStream_t stream;
+    cudaEvent_t done;
+    unsigned long long* counters;  // qcount[2] | unit_next[2] | rows_count[2] | rows_next[2]
+    int sweep_blocks, rows_blocks;
+};
+
 struct sfb_sim {
     sfb_params prm;
-    DevParams d;
+    DevParams d;   // the whole handle (setup / conversion kernels, group 0's queues)
+    std::vector<EnvGroup> groups;
+    cudaEvent_t fork_ev;
     int cell_bytes;   // 1 or 2
     int use_tma;      // sweep front end
     int sweep_blocks; // persistent grid of the sweep kernel
@@ -235,7 +250,7 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
     m.elapsed = 0.0;
     m.any_live = m.any_cand = m.pad = 0;
     m.time_quit = p.has_max_time && (p.dt > p.max_time || 0.0 > p.max_time);
-    p.meta[(long long)par * p.E + env] = m;
+    p.meta[(long long)par * p.meta_stride + env] = m;
     if (p.track) {  // "env was cleared", then its first burning cell, in this order
         const unsigned long long slot = atomicAdd(p.chg_count, 2ULL);
         if (slot + 1 < (unsigned long long)p.chg_cap) {
@@ -361,7 +376,7 @@ __global__ void k_get_plane(DevParams p, int par, int env, int plane, void* out)
             ((int8_t*)out)[i] = (int8_t)to_burn_status(c & 7);
         } else {
             // duration as the NEXT update() call will see it before pruning
-            const int t = p.meta[(long long)par * p.E + env].t;
+            const int t = p.meta[(long long)par * p.meta_stride + env].t;
             ((int32_t*)out)[i] = (c >> 3) ? sprite_age<CellT>(c >> 3, (t - 1) % Cell<CellT>::M) : -1;
         }
     }
@@ -411,7 +426,7 @@ __global__ void k_clear_ros(DevParams p, int par) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int env = (int)(i / p.plane);
-        const EnvMeta& m = p.meta[(long long)par * p.E + env];
+        const EnvMeta& m = p.meta[(long long)par * p.meta_stride + env];
         if (m.running && !m.time_quit && m.any_cand) p.ros[i] = 0.0;
     }
 }
@@ -466,11 +481,14 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree((void*)s->d.stat);
     cudaFree((void*)s->d.drv);
     cudaFree(s->d.meta);
-    cudaFree(s->d.queue);
-    cudaFree(s->d.qcount);
-    cudaFree(s->d.overflow);
-    cudaFree(s->d.unit_next);
-    cudaFree(s->d.rows);
+    for (auto& gr : s->groups) {
+        cudaFree(gr.d.queue);
+        cudaFree(gr.d.rows);
+        cudaFree(gr.counters);
+        if (gr.stream) cudaStreamDestroy(gr.stream);
+        if (gr.done) cudaEventDestroy(gr.done);
+    }
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     if (s->log_mapped) cudaFreeHost(s->log_mapped);
     else cudaFree(s->d.chg);
     cudaFree(s->d.chg_count);
@@ -555,14 +573,6 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, (DerivedRec**)&d.drv, (size_t)stat_cells * sizeof(DerivedRec)))) return rc;
     s->static_dirty = 1;
     if ((rc = dmalloc(s, &d.meta, (size_t)2 * d.E * sizeof(EnvMeta)))) return rc;
-    if ((rc = dmalloc(s, &d.queue, (size_t)qcap * 8))) return rc;
-    if ((rc = dmalloc(s, &d.qcount, 2 * sizeof(unsigned long long)))) return rc;
-    if ((rc = dmalloc(s, &d.overflow, 2 * sizeof(int32_t)))) return rc;
-    if ((rc = dmalloc(s, &d.unit_next, 6 * sizeof(unsigned long long)))) return rc;  // unit_next | rows_count | rows_next
-    d.rows_count = d.unit_next + 2;
-    d.rows_next = d.unit_next + 4;
-    d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
-    if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
     d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
     if (d.track) {
         // The log lives in pinned HOST memory mapped into the device address space: k_eval's
@@ -580,7 +590,6 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
         CU(cudaMallocHost((void**)&s->log_head, 2 * sizeof(unsigned long long)));
     }
-    CU(cudaMemsetAsync(d.unit_next, 0, 6 * sizeof(unsigned long long), s->stream));
     {
         const size_t n = (size_t)d.pitch + 32;
         std::vector<uint8_t> fill(n * s->cell_bytes, 0);
@@ -590,57 +599,103 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     }
 
     s->use_tma = !(prm->flags & SFB_SWEEP_LDG) && prm->slab_total_H == 0;
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* encode = nullptr;
     if (s->use_tma) {
         // driver entry point through the runtime: no link-time dependency on libcuda
-        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
-        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess)
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode, cudaEnableDefault, &qres));
+        if (!encode || qres != cudaDriverEntryPointSuccess)
             return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled is not available in this driver");
-        const cuuint64_t row_bytes = (cuuint64_t)d.pitch * s->cell_bytes;
-        const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)d.H, (cuuint64_t)d.E};
-        const cuuint64_t strides[2] = {row_bytes, row_bytes * (cuuint64_t)d.H};  // bytes, dims 1 and 2
-        const cuuint32_t box[3] = {TMA_ROW_BYTES / 4, TMA_BOX_ROWS, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d.state, dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
         CU(cudaFuncSetAttribute(k_sweep_tma<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
         CU(cudaFuncSetAttribute(k_sweep_tma<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_BLOCK_SMEM));
     }
-
-    {   // persistent sweep grid: as many blocks as fit on the device, never more than there are units
-        int per_sm = 0;
-        if (s->use_tma) {
-            if (s->cell_bytes == 1)
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_tma<uint8_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
-            else
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_tma<uint16_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
-        } else {
-            if (s->cell_bytes == 1)
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ldg<uint8_t>, SWEEP_WARPS * 32, 0));
-            else
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ldg<uint16_t>, SWEEP_WARPS * 32, 0));
-        }
-        if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: sweep kernel does not fit on an SM");
-        const long long need = (d.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
-        s->sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
-        int rows_per_sm = 0;
-        if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint8_t>, ROWS_WARPS * 32, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint16_t>, ROWS_WARPS * 32, 0));
-        if (rows_per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_rows does not fit on an SM");
-        const long long rows_need = (d.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
-        s->rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
+    int sweep_per_sm = 0, rows_per_sm = 0;
+    if (s->use_tma) {
+        if (s->cell_bytes == 1)
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_per_sm, k_sweep_tma<uint8_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
+        else
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_per_sm, k_sweep_tma<uint16_t>, SWEEP_WARPS * 32, TMA_BLOCK_SMEM));
+    } else {
+        if (s->cell_bytes == 1)
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_per_sm, k_sweep_ldg<uint8_t>, SWEEP_WARPS * 32, 0));
+        else
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_per_sm, k_sweep_ldg<uint16_t>, SWEEP_WARPS * 32, 0));
     }
+    if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint8_t>, ROWS_WARPS * 32, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rows_per_sm, k_rows<uint16_t>, ROWS_WARPS * 32, 0));
+    if (sweep_per_sm < 1 || rows_per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: a step kernel does not fit on an SM");
+
+    // env groups
+    int G = prm->env_groups;
+    if (G <= 0) G = (prm->slab_total_H == 0 && d.E >= 64) ? 2 : 1;
+    if (prm->slab_total_H != 0) G = 1;
+    G = std::min(G, std::min(d.E, 16));
+    d.meta_stride = d.E;
+    d.idx_base = 0;
+    CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+    s->groups.resize(G);
+    for (int g = 0; g < G; ++g) {
+        EnvGroup& gr = s->groups[g];
+        const int e0 = (int)((long long)d.E * g / G), cnt = (int)((long long)d.E * (g + 1) / G) - e0;
+        const int64_t off = (int64_t)e0 * d.plane;
+        gr.d = d;
+        DevParams& v = gr.d;
+        v.E = cnt;
+        v.state = (char*)d.state + off * s->cell_bytes;
+        v.burn = d.burn + off;
+        if (d.ros) v.ros = d.ros + off;
+        if (d.ign) v.ign = d.ign + off;
+        if (!d.shared_static) {
+            v.stat = d.stat + off;
+            v.drv = d.drv + off;
+        }
+        v.meta = d.meta + e0;
+        v.idx_base = off;
+        v.n_units = (int64_t)cnt * d.chunks * d.strips;
+        v.qcap = std::max<int64_t>(1, (d.qcap * cnt + d.E - 1) / d.E);
+        v.rows_cap = (int64_t)cnt * d.H * d.strips;  // every warp-row of the group: the list cannot overflow
+        if ((rc = dmalloc(s, &v.queue, (size_t)v.qcap * 8))) return rc;
+        if ((rc = dmalloc(s, &v.rows, (size_t)v.rows_cap * 8))) return rc;
+        if ((rc = dmalloc(s, &gr.counters, 10 * sizeof(unsigned long long)))) return rc;
+        CU(cudaMemsetAsync(gr.counters, 0, 10 * sizeof(unsigned long long), s->stream));
+        v.qcount = gr.counters;
+        v.unit_next = gr.counters + 2;
+        v.rows_count = gr.counters + 4;
+        v.rows_next = gr.counters + 6;
+        v.overflow = reinterpret_cast<int32_t*>(gr.counters + 8);
+        if (s->use_tma) {
+            const cuuint64_t row_bytes = (cuuint64_t)d.pitch * s->cell_bytes;
+            const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)d.H, (cuuint64_t)cnt};
+            const cuuint64_t strides[2] = {row_bytes, row_bytes * (cuuint64_t)d.H};  // bytes, dims 1 and 2
+            const cuuint32_t box[3] = {TMA_ROW_BYTES / 4, TMA_BOX_ROWS, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = ((encode_fn)encode)(&gr.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.state, dims, strides, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        }
+        if (G > 1) CU(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
+        else gr.stream = nullptr;  // single group: the handle's stream
+        CU(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
+        const long long need = (v.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
+        gr.sweep_blocks = (int)std::min<long long>(need, (long long)sweep_per_sm * s->n_sm);
+        const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
+        gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
+    }
+    // the handle-wide view keeps group 0's queues (setup kernels never touch them)
+    d.queue = s->groups[0].d.queue;
+    d.rows = s->groups[0].d.rows;
+    d.qcount = s->groups[0].d.qcount;
+    d.unit_next = s->groups[0].d.unit_next;
+    d.rows_count = s->groups[0].d.rows_count;
+    d.rows_next = s->groups[0].d.rows_next;
+    d.overflow = s->groups[0].d.overflow;
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
     CU(cudaMemsetAsync(d.meta, 0, (size_t)2 * d.E * sizeof(EnvMeta), s->stream));  // running = 0
-    CU(cudaMemsetAsync(d.qcount, 0, 2 * sizeof(unsigned long long), s->stream));
-    CU(cudaMemsetAsync(d.overflow, 0, 2 * sizeof(int32_t), s->stream));
     DISPATCH(s, k_clear_envs, cap_grid(s, total, 256), 256, d, (const int32_t*)nullptr, d.E, 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
@@ -875,41 +930,77 @@ extern "C" int sfb_set_fire_map(sfb_sim* s, int32_t env0, int32_t n, const int8_
 // ---------------------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------------------
-static int enqueue_sweep(sfb_sim* s) {
+static int derive_if_dirty(sfb_sim* s) {
+    if (!s->static_dirty) return 0;
     const DevParams& d = s->d;
-    const int par = s->parity;
-    if (s->static_dirty) {
-        const long long cells = d.shared_static ? d.plane : (long long)d.E * d.plane;
-        k_derive_static<<<cap_grid(s, cells, 128), 128, 0, s->stream>>>(d, cells);
-        s->launches_all++;
-        s->static_dirty = 0;
-    }
-    if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
+    const long long cells = d.shared_static ? d.plane : (long long)d.E * d.plane;
+    k_derive_static<<<cap_grid(s, cells, 128), 128, 0, s->stream>>>(d, cells);
+    s->launches_all++;
+    s->static_dirty = 0;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (s->use_tma) {
-        const unsigned grid = (unsigned)s->sweep_blocks;
-        if (s->cell_bytes == 1) k_sweep_tma<uint8_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
-        else k_sweep_tma<uint16_t><<<grid, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, s->stream>>>(s->tmap, d, par);
-        s->launches_all++;
+        if (s->cell_bytes == 1) k_sweep_tma<uint8_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st>>>(gr.tmap, gr.d, par);
+        else k_sweep_tma<uint16_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st>>>(gr.tmap, gr.d, par);
     } else {
-        DISPATCH(s, k_sweep_ldg, (unsigned)s->sweep_blocks, SWEEP_WARPS * 32, d, par);
+        if (s->cell_bytes == 1) k_sweep_ldg<uint8_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, 0, st>>>(gr.d, par);
+        else k_sweep_ldg<uint16_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, 0, st>>>(gr.d, par);
     }
+    s->launches_all++;
+    s->launches_step++;
+}
+static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (s->cell_bytes == 1) k_rows<uint8_t><<<gr.rows_blocks, ROWS_WARPS * 32, 0, st>>>(gr.d, par);
+    else k_rows<uint16_t><<<gr.rows_blocks, ROWS_WARPS * 32, 0, st>>>(gr.d, par);
+    s->launches_all++;
+    s->launches_step++;
+}
+static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (gr.d.keep_ros) {
+        k_clear_ros<<<cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st>>>(gr.d, par);
+        s->launches_all++;
+    }
+    if (s->cell_bytes == 1) k_eval<uint8_t><<<s->n_sm * 8, 256, 0, st>>>(gr.d, par);
+    else k_eval<uint16_t><<<s->n_sm * 8, 256, 0, st>>>(gr.d, par);
+    s->launches_all++;
+    s->launches_step++;
+}
+
+// refresh the fields of the group views that setters may have changed on the handle-wide params
+static void sync_group_views(sfb_sim* s) {
+    for (auto& gr : s->groups) {
+        gr.d.track = s->d.track;
+        gr.d.halo_top = s->d.halo_top;
+        gr.d.halo_bottom = s->d.halo_bottom;
+        gr.d.halo_top_plane = s->d.halo_top_plane;
+        gr.d.halo_bottom_plane = s->d.halo_bottom_plane;
+        gr.d.mailbox = s->d.mailbox;
+        gr.d.slab_rank = s->d.slab_rank;
+        gr.d.slab_world = s->d.slab_world;
+        for (int q = 0; q < SLAB_MAX_WORLD; ++q) gr.d.peer_box[q] = s->d.peer_box[q];
+    }
+}
+
+// single-group handles (slab mode, small batches): the two halves of a step on the handle's stream
+static int enqueue_sweep(sfb_sim* s) {
+    int rc;
+    if ((rc = derive_if_dirty(s))) return rc;
+    sync_group_views(s);
+    EnvGroup& gr = s->groups[0];
+    if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
+    launch_sweep(s, gr, s->stream, s->parity);
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
-    DISPATCH(s, k_rows, (unsigned)s->rows_blocks, ROWS_WARPS * 32, d, par);
+    launch_rows(s, gr, s->stream, s->parity);
     if (s->timing) CU(cudaEventRecord(s->ev[2], s->stream));
-    s->launches_step += 2;
     s->in_step = 1;
     return 0;
 }
 
 static int enqueue_eval(sfb_sim* s) {
-    const DevParams& d = s->d;
-    const int par = s->parity;
-    if (d.keep_ros) {
-        k_clear_ros<<<cap_grid(s, (long long)d.E * d.plane, 256), 256, 0, s->stream>>>(d, par);
-        s->launches_all++;
-    }
-    DISPATCH(s, k_eval, (unsigned)(s->n_sm * 8), 256, d, par);
-    s->launches_step += 1;
+    launch_eval(s, s->groups[0], s->stream, s->parity);
     s->parity ^= 1;
     s->in_step = 0;
     if (s->timing) {
@@ -927,15 +1018,76 @@ static int enqueue_eval(sfb_sim* s) {
     return 0;
 }
 
-static int enqueue_step(sfb_sim* s) {
+// n steps of every env.  One group: everything on the handle's stream.  Several groups: each on
+// its own stream, forked from / joined to the handle's stream, so that the streaming kernel of
+// one group overlaps the issue-bound kernels of another.  With kernel timing enabled the groups
+// run one after the other and the per-kernel times add up.
+static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
-    int rc = enqueue_sweep(s);
-    return rc ? rc : enqueue_eval(s);
+    if (n <= 0) return 0;
+    int rc;
+    if (s->groups.size() == 1) {
+        for (int i = 0; i < n; ++i) {
+            if ((rc = enqueue_sweep(s))) return rc;
+            if ((rc = enqueue_eval(s))) return rc;
+        }
+        return 0;
+    }
+    if ((rc = derive_if_dirty(s))) return rc;
+    sync_group_views(s);
+    if (s->timing) {
+        for (int i = 0; i < n; ++i) {
+            float a = 0, b = 0, c = 0;
+            for (auto& gr : s->groups) {
+                CU(cudaEventRecord(s->ev[0], s->stream));
+                launch_sweep(s, gr, s->stream, s->parity);
+                CU(cudaEventRecord(s->ev[1], s->stream));
+                launch_rows(s, gr, s->stream, s->parity);
+                CU(cudaEventRecord(s->ev[2], s->stream));
+                launch_eval(s, gr, s->stream, s->parity);
+                CU(cudaEventRecord(s->ev[3], s->stream));
+                CU(cudaEventSynchronize(s->ev[3]));
+                float x = 0, y = 0, z = 0;
+                CU(cudaEventElapsedTime(&x, s->ev[0], s->ev[1]));
+                CU(cudaEventElapsedTime(&y, s->ev[1], s->ev[2]));
+                CU(cudaEventElapsedTime(&z, s->ev[2], s->ev[3]));
+                a += x;
+                b += y;
+                c += z;
+            }
+            s->sweep_ms += a;
+            s->rows_ms += b;
+            s->eval_ms += c;
+            s->timed_steps++;
+            s->parity ^= 1;
+        }
+        return 0;
+    }
+    CU(cudaEventRecord(s->fork_ev, s->stream));
+    for (auto& gr : s->groups) CU(cudaStreamWaitEvent(gr.stream, s->fork_ev, 0));
+    int par = s->parity;
+    for (int i = 0; i < n; ++i) {
+        for (auto& gr : s->groups) {
+            launch_sweep(s, gr, gr.stream, par);
+            launch_rows(s, gr, gr.stream, par);
+            launch_eval(s, gr, gr.stream, par);
+        }
+        par ^= 1;
+    }
+    s->parity = par;
+    for (auto& gr : s->groups) {
+        CU(cudaEventRecord(gr.done, gr.stream));
+        CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
+    }
+    return 0;
 }
+
+static int enqueue_step(sfb_sim* s) { return enqueue_steps(s, 1); }
 
 extern "C" int sfb_step_sweep(sfb_sim* s) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_step_sweep: null handle");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_sweep: the previous sweep has not been evaluated");
+    if (s->groups.size() != 1) return fail(SFB_ERR_STATE, "sfb_step_sweep: create the handle with env_groups = 1");
     int rc;
     if ((rc = use(s))) return rc;
     if ((rc = enqueue_sweep(s))) return rc;
@@ -983,14 +1135,15 @@ extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_step_slab: null handle");
     if (s->d.slab_world < 1) return fail(SFB_ERR_STATE, "sfb_step_slab: call sfb_slab_connect first");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_slab: a step is half done");
+    if (s->groups.size() != 1) return fail(SFB_ERR_STATE, "sfb_step_slab: slab handles have one env group");
     int rc;
     if ((rc = use(s))) return rc;
     for (int i = 0; i < n_steps; ++i) {
         const uint32_t g = ++s->slab_step;
         if ((rc = enqueue_sweep(s))) return rc;
-        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->d, s->parity, g);
+        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->groups[0].d, s->parity, g);
         if ((rc = enqueue_eval(s))) return rc;
-        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->d, g);
+        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->groups[0].d, g);
         s->launches_all += 2;
     }
     CU(cudaGetLastError());
@@ -1069,8 +1222,7 @@ extern "C" int sfb_step(sfb_sim* s, int32_t n_steps, int32_t sync) {
     if (n_steps < 0) return fail(SFB_ERR_INVALID, "sfb_step: n_steps %d", n_steps);
     int rc;
     if ((rc = use(s))) return rc;
-    for (int i = 0; i < n_steps; ++i)
-        if ((rc = enqueue_step(s))) return rc;
+    if ((rc = enqueue_steps(s, n_steps))) return rc;
     CU(cudaGetLastError());
     if (sync) CU(cudaStreamSynchronize(s->stream));
     return 0;
@@ -1084,8 +1236,7 @@ extern "C" int sfb_step_timed(sfb_sim* s, int32_t n_steps, float* ms) {
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, s->stream));
-    for (int i = 0; i < n_steps; ++i)
-        if ((rc = enqueue_step(s))) return rc;
+    if ((rc = enqueue_steps(s, n_steps))) return rc;
     CU(cudaEventRecord(b, s->stream));
     CU(cudaEventSynchronize(b));
     CU(cudaEventElapsedTime(ms, a, b));
@@ -1381,17 +1532,22 @@ extern "C" int sfb_get_queue_stats(sfb_sim* s, int64_t* entries, int64_t* capaci
     if (!s) return fail(SFB_ERR_INVALID, "sfb_get_queue_stats: null handle");
     int rc;
     if ((rc = use(s))) return rc;
-    // the step that ran last used parity^1; k_eval leaves its count in place until the
-    // step after next resets it
+    // the step that ran last used parity^1; k_eval leaves its counters in place until the
+    // step after next resets them
     const int par = s->parity ^ 1;
-    unsigned long long cnt = 0;
-    int32_t ovf = 0;
     CU(cudaStreamSynchronize(s->stream));
-    CU(cudaMemcpy(&cnt, s->d.qcount + par, sizeof(cnt), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&ovf, s->d.overflow + par, sizeof(ovf), cudaMemcpyDeviceToHost));
-    if (entries) *entries = (int64_t)cnt;
-    if (capacity) *capacity = s->d.qcap;
-    if (overflowed) *overflowed = ovf;
+    int64_t tot = 0, cap = 0;
+    int32_t any_ovf = 0;
+    for (auto& gr : s->groups) {
+        unsigned long long c[10];
+        CU(cudaMemcpy(c, gr.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        tot += (int64_t)c[par];
+        cap += gr.d.qcap;
+        any_ovf |= reinterpret_cast<int32_t*>(c + 8)[par];
+    }
+    if (entries) *entries = tot;
+    if (capacity) *capacity = cap;
+    if (overflowed) *overflowed = any_ovf;
     return 0;
 }
 
@@ -1399,11 +1555,17 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
     if (!s) return fail(SFB_ERR_INVALID, "sfb_get_row_tasks: null handle");
     int rc;
     if ((rc = use(s))) return rc;
-    unsigned long long cnt = 0;
+    const int par = s->parity ^ 1;
     CU(cudaStreamSynchronize(s->stream));
-    CU(cudaMemcpy(&cnt, s->d.rows_count + (s->parity ^ 1), sizeof(cnt), cudaMemcpyDeviceToHost));
-    if (tasks) *tasks = (int64_t)cnt;
-    if (capacity) *capacity = s->d.rows_cap;
+    int64_t tot = 0, cap = 0;
+    for (auto& gr : s->groups) {
+        unsigned long long c[10];
+        CU(cudaMemcpy(c, gr.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        tot += (int64_t)c[4 + par];
+        cap += gr.d.rows_cap;
+    }
+    if (tasks) *tasks = tot;
+    if (capacity) *capacity = cap;
     return 0;
 }
 

@@ -91,7 +91,9 @@ struct DevParams {
     int32_t* ign;            // update() call that ignited the cell (SFB_KEEP_IGNITION), else nullptr
     const StaticRec* stat;   // raw inputs as uploaded
     const DerivedRec* drv;   // derived from `stat` by k_derive_static before the first step that needs it
-    EnvMeta* meta;              // [2][E], double-buffered by step parity
+    EnvMeta* meta;              // [2][meta_stride], double-buffered by step parity
+    int32_t meta_stride;        // envs of the whole handle (a kernel may see a group of them: E <= meta_stride)
+    int64_t idx_base;           // cell index of this group's first cell within the handle (change-log entries)
     unsigned long long* queue;  // [qcap] work items
     unsigned long long* qcount; // [2]
     int32_t* overflow;          // [2]
@@ -332,7 +334,7 @@ struct RowWorker {
         f_live = __any_sync(0xffffffffu, f_live);
         f_cand = __any_sync(0xffffffffu, f_cand);
         if (env >= 0 && lane == 0) {
-            EnvMeta* mp = p.meta + (long long)par * p.E + env;
+            EnvMeta* mp = p.meta + (long long)par * p.meta_stride + env;
             if (f_live) mp->any_live = 1;
             if (f_cand) mp->any_cand = 1;
         }
@@ -538,7 +540,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
 
     int strip, chunk, env;
     while (next_unit(p, par, lane, strip, chunk, env)) {
-        if (!p.meta[(long long)par * p.E + env].running) continue;
+        if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
         const int x0 = strip * WR;
         const int y_begin = chunk * p.rows_per_chunk;
         const int n_rows = min(y_begin + p.rows_per_chunk, p.H) - y_begin;  // rows this unit owns
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
 
     int strip, chunk, env;
     while (next_unit(p, par, lane, strip, chunk, env)) {
-        if (!p.meta[(long long)par * p.E + env].running) continue;
+        if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
         const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + (long long)env * p.plane;
         const int x0 = strip * WR;
         const int xl = x0 + lane * CPL;
@@ -740,7 +742,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
     for (; t < t_end; ++t) {
         const bool more = t + 1 < t_end;
         if (more) load(p.rows[t + 1], nxt);  // in flight while `cur` is examined
-        if (cur.env != rw.env) rw.set_env(cur.env, p.meta[(long long)par * p.E + cur.env]);
+        if (cur.env != rw.env) rw.set_env(cur.env, p.meta[(long long)par * p.meta_stride + cur.env]);
         rw.x0 = cur.strip * WR;
         __syncwarp();  // the previous task's readers are done with the staging rows
 #pragma unroll
@@ -770,7 +772,7 @@ __device__ void dense_cell(const DevParams& p, const int par, long long idx) {
     const long long cell = idx - (long long)env * p.plane;
     const int y = (int)(cell / p.pitch), x = (int)(cell - (long long)y * p.pitch);
     if (x >= p.W) return;
-    const EnvMeta m = p.meta[(long long)par * p.E + env];
+    const EnvMeta m = p.meta[(long long)par * p.meta_stride + env];
     if (!m.running || m.time_quit) return;
     const CellT* st = reinterpret_cast<const CellT*>(p.state);
     const int s = st[idx] & 7;
@@ -827,17 +829,17 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
                     logged = 2;  // BurnStatus.BURNED
                 } else {
                     const int env = (int)(idx / p.plane);
-                    const EnvMeta m = p.meta[(long long)par * p.E + env];
+                    const EnvMeta m = p.meta[(long long)par * p.meta_stride + env];
                     if (process_item<CellT>(p, m, env, idx, dir, s)) logged = 1;  // BurnStatus.BURNING
                 }
             }
-            if (p.track) log_append(p, logged >= 0, idx, logged);
+            if (p.track) log_append(p, logged >= 0, idx + p.idx_base, logged);
         }
     }
 
     // per-env clock for the next step (reads only what k_sweep finalised)
     for (long long env = gid; env < p.E; env += gstride) {
-        const EnvMeta cur = p.meta[(long long)par * p.E + env];
+        const EnvMeta cur = p.meta[(long long)par * p.meta_stride + env];
         EnvMeta nxt = cur;
         if (cur.running) {
             if (!cur.any_live) nxt.running = 0;            // fire.py:637
@@ -848,7 +850,7 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
         nxt.any_live = 0;
         nxt.any_cand = 0;
         nxt.time_quit = p.has_max_time && (p.dt > p.max_time || nxt.elapsed > p.max_time);
-        p.meta[(long long)(par ^ 1) * p.E + env] = nxt;
+        p.meta[(long long)(par ^ 1) * p.meta_stride + env] = nxt;
     }
     if (gid == 0) {
         p.qcount[par ^ 1] = 0;
@@ -868,7 +870,7 @@ constexpr long long SLAB_SPIN_LIMIT = 1ll << 27;  // ~ a second of polling, then
 __global__ void k_slab_exchange_flags(const DevParams p, const int par, const uint32_t gstep) {
     const int lane = threadIdx.x;
     const int half = gstep & 1;
-    EnvMeta* meta = p.meta + (long long)par * p.E;
+    EnvMeta* meta = p.meta + (long long)par * p.meta_stride;
     for (int q = 0; q < p.slab_world; ++q) {
         SlabMailbox* box = p.peer_box[q];
         for (int i = lane; i < p.E * 2; i += 32) {

@@ -56,6 +56,7 @@ class FireEngine:
         sweep_ldg: bool = False,
         track_changes: bool = False,
         keep_ignition: bool = False,
+        env_groups: int = 0,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -81,7 +82,7 @@ class FireEngine:
             max_fire_duration=int(max_fire_duration), flags=flags, rows_per_chunk=int(rows_per_chunk),
             pixel_scale=float(pixel_scale), update_rate=float(update_rate),
             max_time=float(max_time) if max_time is not None else 0.0,
-            h=h, S_T=S_T, S_e=S_e, p_p=p_p, M_f=float(M_f), reserved0=0,
+            h=h, S_T=S_T, S_e=S_e, p_p=p_p, M_f=float(M_f), env_groups=int(env_groups),
             queue_capacity=int(queue_capacity), slab_y0=int(slab_y0), slab_total_H=int(slab_total_H),
         )  # fmt: skip
         _lib.check(self._lib.sfb_create(C.byref(prm), C.byref(self._h)))

@@ -154,6 +154,39 @@ def test_batched_envs_are_independent():
                 assert np.array_equal(maps[e], o.status), f"env {e} step {step}"
 
 
+@pytest.mark.parametrize("groups", [1, 2, 3, 5])
+def test_env_groups_on_streams_equal_one_group(groups):
+    """Stepping the envs as G groups on G streams is only a scheduling choice."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    wl = synthetic_operational(96, 160, seed=4, patch=8)
+    E = 13
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True, max_time=60.0)
+    starts = wl.burnable_starts(E, seed=3, margin=4)
+    lines = [(e, x, 40 + e, 3 + (x % 3)) for e in range(E) for x in range(10, 150, 3)]
+    res = []
+    for g in (1, groups):
+        with FireEngine(96, 160, E, shared_static=True, env_groups=g, track_changes=True, keep_ros=True, **kw) as eng:
+            eng.set_static(wl.planes)
+            eng.reset(starts)
+            eng.apply_points(lines)
+            mirror = np.zeros((E, 96, 160), dtype=np.int8)
+            eng.sync_fire_maps(mirror)
+            for _ in range(6):
+                eng.step(7)
+                eng.sync_fire_maps(mirror)
+                assert np.array_equal(mirror, eng.fire_map())
+            eng.reset(starts[:2], envs=[4, 9])
+            eng.step(20, sync=False)
+            eng.synchronize()
+            res.append((eng.fire_map(), [eng.plane("burn", e) for e in (0, 6, 12)], eng.plane("ros", 12), eng.status()))
+    a, b = res
+    assert np.array_equal(a[0], b[0])
+    assert all(np.array_equal(x, y) for x, y in zip(a[1], b[1])) and np.array_equal(a[2], b[2])
+    assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
+
+
 def test_multi_step_launch_equals_single_steps():
     sc = load_scenario("scenario_c_random_fuel_hills")
     with engine_for(sc) as a, engine_for(sc) as b:
