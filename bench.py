@@ -448,7 +448,7 @@ def gpu_arm(args):
                        "as changed (8 B each)" if not args.no_track else " by a full download")},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "traffic": load_traffic_note(args.workload),
             "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,

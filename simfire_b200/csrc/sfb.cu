@@ -123,7 +123,10 @@ struct EnvGroup {
 struct sfb_sim {
     sfb_params prm;
     DevParams d;   // the whole handle (setup / conversion kernels, group 0's queues)
-    std::vector<EnvGroup> groups;
+    std::vector<EnvGroup> groups;  // G >= 1 views of disjoint env ranges (slices of the queue / row list)
+    EnvGroup all;                  // one view of every env (whole queue / row list); used when the
+                                   // groups would not overlap anyway (kernel timing, change log on)
+    int last_mode;                 // 0 none yet, 1 `all`, 2 `groups`
     cudaEvent_t fork_ev;
     int cell_bytes;   // 1 or 2
     int use_tma;      // sweep front end
@@ -481,9 +484,10 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree((void*)s->d.stat);
     cudaFree((void*)s->d.drv);
     cudaFree(s->d.meta);
+    cudaFree(s->d.queue);
+    cudaFree(s->d.rows);
+    s->groups.push_back(s->all);
     for (auto& gr : s->groups) {
-        cudaFree(gr.d.queue);
-        cudaFree(gr.d.rows);
         cudaFree(gr.counters);
         if (gr.stream) cudaStreamDestroy(gr.stream);
         if (gr.done) cudaEventDestroy(gr.done);
@@ -630,16 +634,17 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
 
     // env groups
     int G = prm->env_groups;
-    if (G <= 0) G = (prm->slab_total_H == 0 && d.E >= 64) ? 2 : 1;
+    if (G <= 0) G = prm->slab_total_H != 0 ? 1 : (d.E >= 512 ? 4 : (d.E >= 64 ? 2 : 1));
     if (prm->slab_total_H != 0) G = 1;
     G = std::min(G, std::min(d.E, 16));
     d.meta_stride = d.E;
     d.idx_base = 0;
+    d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
+    if ((rc = dmalloc(s, &d.queue, (size_t)d.qcap * 8))) return rc;
+    if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-    s->groups.resize(G);
-    for (int g = 0; g < G; ++g) {
-        EnvGroup& gr = s->groups[g];
-        const int e0 = (int)((long long)d.E * g / G), cnt = (int)((long long)d.E * (g + 1) / G) - e0;
+
+    auto make_view = [&](EnvGroup& gr, int e0, int cnt, int64_t q_off, int64_t q_cap, bool own_stream) -> int {
         const int64_t off = (int64_t)e0 * d.plane;
         gr.d = d;
         DevParams& v = gr.d;
@@ -655,11 +660,12 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.meta = d.meta + e0;
         v.idx_base = off;
         v.n_units = (int64_t)cnt * d.chunks * d.strips;
-        v.qcap = std::max<int64_t>(1, (d.qcap * cnt + d.E - 1) / d.E);
-        v.rows_cap = (int64_t)cnt * d.H * d.strips;  // every warp-row of the group: the list cannot overflow
-        if ((rc = dmalloc(s, &v.queue, (size_t)v.qcap * 8))) return rc;
-        if ((rc = dmalloc(s, &v.rows, (size_t)v.rows_cap * 8))) return rc;
-        if ((rc = dmalloc(s, &gr.counters, 10 * sizeof(unsigned long long)))) return rc;
+        v.queue = d.queue + q_off;
+        v.qcap = q_cap;
+        v.rows = d.rows + (int64_t)e0 * d.H * d.strips;
+        v.rows_cap = (int64_t)cnt * d.H * d.strips;
+        int rc2;
+        if ((rc2 = dmalloc(s, &gr.counters, 10 * sizeof(unsigned long long)))) return rc2;
         CU(cudaMemsetAsync(gr.counters, 0, 10 * sizeof(unsigned long long), s->stream));
         v.qcount = gr.counters;
         v.unit_next = gr.counters + 2;
@@ -677,22 +683,32 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
         }
-        if (G > 1) CU(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
-        else gr.stream = nullptr;  // single group: the handle's stream
+        gr.stream = nullptr;
+        if (own_stream) CU(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
         const long long need = (v.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)sweep_per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
+        return 0;
+    };
+    if ((rc = make_view(s->all, 0, d.E, 0, d.qcap, false))) return rc;
+    s->groups.resize(G > 1 ? G : 0);
+    {
+        int64_t q_off = 0;
+        for (int g = 0; g < (int)s->groups.size(); ++g) {
+            const int e0 = (int)((long long)d.E * g / G), cnt = (int)((long long)d.E * (g + 1) / G) - e0;
+            const int64_t q_cap = g + 1 == G ? d.qcap - q_off : std::max<int64_t>(1, d.qcap * cnt / d.E);
+            if ((rc = make_view(s->groups[g], e0, cnt, q_off, q_cap, true))) return rc;
+            q_off += q_cap;
+        }
     }
-    // the handle-wide view keeps group 0's queues (setup kernels never touch them)
-    d.queue = s->groups[0].d.queue;
-    d.rows = s->groups[0].d.rows;
-    d.qcount = s->groups[0].d.qcount;
-    d.unit_next = s->groups[0].d.unit_next;
-    d.rows_count = s->groups[0].d.rows_count;
-    d.rows_next = s->groups[0].d.rows_next;
-    d.overflow = s->groups[0].d.overflow;
+    // the handle-wide params point at the `all` view's counters (setup kernels never touch them)
+    d.qcount = s->all.d.qcount;
+    d.unit_next = s->all.d.unit_next;
+    d.rows_count = s->all.d.rows_count;
+    d.rows_next = s->all.d.rows_next;
+    d.overflow = s->all.d.overflow;
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
     CU(cudaMemsetAsync(d.meta, 0, (size_t)2 * d.E * sizeof(EnvMeta), s->stream));  // running = 0
@@ -970,8 +986,13 @@ static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
 }
 
 // refresh the fields of the group views that setters may have changed on the handle-wide params
+static void sync_one_view(sfb_sim* s, EnvGroup& gr);
 static void sync_group_views(sfb_sim* s) {
-    for (auto& gr : s->groups) {
+    sync_one_view(s, s->all);
+    for (auto& gr : s->groups) sync_one_view(s, gr);
+}
+static void sync_one_view(sfb_sim* s, EnvGroup& gr) {
+    {
         gr.d.track = s->d.track;
         gr.d.halo_top = s->d.halo_top;
         gr.d.halo_bottom = s->d.halo_bottom;
@@ -989,7 +1010,7 @@ static int enqueue_sweep(sfb_sim* s) {
     int rc;
     if ((rc = derive_if_dirty(s))) return rc;
     sync_group_views(s);
-    EnvGroup& gr = s->groups[0];
+    EnvGroup& gr = s->all;
     if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
     launch_sweep(s, gr, s->stream, s->parity);
     if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
@@ -1000,7 +1021,7 @@ static int enqueue_sweep(sfb_sim* s) {
 }
 
 static int enqueue_eval(sfb_sim* s) {
-    launch_eval(s, s->groups[0], s->stream, s->parity);
+    launch_eval(s, s->all, s->stream, s->parity);
     s->parity ^= 1;
     s->in_step = 0;
     if (s->timing) {
@@ -1022,47 +1043,36 @@ static int enqueue_eval(sfb_sim* s) {
 // its own stream, forked from / joined to the handle's stream, so that the streaming kernel of
 // one group overlaps the issue-bound kernels of another.  With kernel timing enabled the groups
 // run one after the other and the per-kernel times add up.
+// switching between the `all` view and the group views: the views keep separate counters, and a
+// view that sat out some steps may hold counts of the wrong parity
+static int enter_mode(sfb_sim* s, int mode) {
+    if (s->last_mode == mode) return 0;
+    if (s->last_mode != 0) {
+        CU(cudaMemsetAsync(s->all.counters, 0, 10 * sizeof(unsigned long long), s->stream));
+        for (auto& gr : s->groups) CU(cudaMemsetAsync(gr.counters, 0, 10 * sizeof(unsigned long long), s->stream));
+    }
+    s->last_mode = mode;
+    return 0;
+}
+
 static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
     int rc;
-    if (s->groups.size() == 1) {
+    // one view of all envs on the handle's stream: single-group handles, per-kernel timing, and
+    // with the change log on (the log then stays ordered by env, which keeps the host-side
+    // patching cache-friendly; that path is bound by the host anyway)
+    if (s->groups.empty() || s->timing || s->d.track) {
+        if ((rc = enter_mode(s, 1))) return rc;
         for (int i = 0; i < n; ++i) {
             if ((rc = enqueue_sweep(s))) return rc;
             if ((rc = enqueue_eval(s))) return rc;
         }
         return 0;
     }
+    if ((rc = enter_mode(s, 2))) return rc;
     if ((rc = derive_if_dirty(s))) return rc;
     sync_group_views(s);
-    if (s->timing) {
-        for (int i = 0; i < n; ++i) {
-            float a = 0, b = 0, c = 0;
-            for (auto& gr : s->groups) {
-                CU(cudaEventRecord(s->ev[0], s->stream));
-                launch_sweep(s, gr, s->stream, s->parity);
-                CU(cudaEventRecord(s->ev[1], s->stream));
-                launch_rows(s, gr, s->stream, s->parity);
-                CU(cudaEventRecord(s->ev[2], s->stream));
-                launch_eval(s, gr, s->stream, s->parity);
-                CU(cudaEventRecord(s->ev[3], s->stream));
-                CU(cudaEventSynchronize(s->ev[3]));
-                float x = 0, y = 0, z = 0;
-                CU(cudaEventElapsedTime(&x, s->ev[0], s->ev[1]));
-                CU(cudaEventElapsedTime(&y, s->ev[1], s->ev[2]));
-                CU(cudaEventElapsedTime(&z, s->ev[2], s->ev[3]));
-                a += x;
-                b += y;
-                c += z;
-            }
-            s->sweep_ms += a;
-            s->rows_ms += b;
-            s->eval_ms += c;
-            s->timed_steps++;
-            s->parity ^= 1;
-        }
-        return 0;
-    }
     CU(cudaEventRecord(s->fork_ev, s->stream));
     for (auto& gr : s->groups) CU(cudaStreamWaitEvent(gr.stream, s->fork_ev, 0));
     int par = s->parity;
@@ -1087,7 +1097,8 @@ static int enqueue_step(sfb_sim* s) { return enqueue_steps(s, 1); }
 extern "C" int sfb_step_sweep(sfb_sim* s) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_step_sweep: null handle");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_sweep: the previous sweep has not been evaluated");
-    if (s->groups.size() != 1) return fail(SFB_ERR_STATE, "sfb_step_sweep: create the handle with env_groups = 1");
+    if (!s->groups.empty()) return fail(SFB_ERR_STATE, "sfb_step_sweep: create the handle with env_groups = 1");
+    { int rcm = enter_mode(s, 1); if (rcm) return rcm; }
     int rc;
     if ((rc = use(s))) return rc;
     if ((rc = enqueue_sweep(s))) return rc;
@@ -1135,15 +1146,16 @@ extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_step_slab: null handle");
     if (s->d.slab_world < 1) return fail(SFB_ERR_STATE, "sfb_step_slab: call sfb_slab_connect first");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_slab: a step is half done");
-    if (s->groups.size() != 1) return fail(SFB_ERR_STATE, "sfb_step_slab: slab handles have one env group");
+    if (!s->groups.empty()) return fail(SFB_ERR_STATE, "sfb_step_slab: slab handles have one env group");
+    { int rcm = enter_mode(s, 1); if (rcm) return rcm; }
     int rc;
     if ((rc = use(s))) return rc;
     for (int i = 0; i < n_steps; ++i) {
         const uint32_t g = ++s->slab_step;
         if ((rc = enqueue_sweep(s))) return rc;
-        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->groups[0].d, s->parity, g);
+        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->all.d, s->parity, g);
         if ((rc = enqueue_eval(s))) return rc;
-        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->groups[0].d, g);
+        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->all.d, g);
         s->launches_all += 2;
     }
     CU(cudaGetLastError());
@@ -1538,7 +1550,11 @@ extern "C" int sfb_get_queue_stats(sfb_sim* s, int64_t* entries, int64_t* capaci
     CU(cudaStreamSynchronize(s->stream));
     int64_t tot = 0, cap = 0;
     int32_t any_ovf = 0;
-    for (auto& gr : s->groups) {
+    std::vector<EnvGroup*> views;
+    if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
+    else views.push_back(&s->all);
+    for (EnvGroup* grp : views) {
+        EnvGroup& gr = *grp;
         unsigned long long c[10];
         CU(cudaMemcpy(c, gr.counters, sizeof(c), cudaMemcpyDeviceToHost));
         tot += (int64_t)c[par];
@@ -1558,7 +1574,11 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
     const int par = s->parity ^ 1;
     CU(cudaStreamSynchronize(s->stream));
     int64_t tot = 0, cap = 0;
-    for (auto& gr : s->groups) {
+    std::vector<EnvGroup*> views;
+    if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
+    else views.push_back(&s->all);
+    for (EnvGroup* grp : views) {
+        EnvGroup& gr = *grp;
         unsigned long long c[10];
         CU(cudaMemcpy(c, gr.counters, sizeof(c), cudaMemcpyDeviceToHost));
         tot += (int64_t)c[4 + par];

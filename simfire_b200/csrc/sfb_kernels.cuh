@@ -677,11 +677,13 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
 }
 
 // ---------------------------------------------------------------------------------------
-// k_rows: the row tasks are split in equal contiguous ranges, one per warp (consecutive tasks are
-// mostly consecutive rows of one env, so two of the three rows of a task come from L1); the
-// loads of task t+1 are in flight while task t is examined.
+// k_rows: one warp per row task.
 // ---------------------------------------------------------------------------------------
+#ifndef SFB_ROWS_CHUNK
+#define SFB_ROWS_CHUNK 4
+#endif
 constexpr int ROWS_WARPS = 4;
+constexpr int ROWS_CHUNK = SFB_ROWS_CHUNK;
 
 template <typename CellT>
 __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, const int par) {
@@ -696,10 +698,9 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
     const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
     const unsigned long long n_warps = (unsigned long long)gridDim.x * ROWS_WARPS;
     const unsigned long long w = (unsigned long long)blockIdx.x * ROWS_WARPS + warp;
-    const unsigned long long per = (n + n_warps - 1) / n_warps;
-    unsigned long long t = w * per;
-    const unsigned long long t_end = min(t + per, n);
-    if (t >= t_end) return;
+    // chunk of consecutive tasks per deal: small lists are spread task by task
+    const unsigned long long chunk = n >= n_warps * ROWS_CHUNK ? ROWS_CHUNK : (n >= n_warps * 2 ? 2 : 1);
+    if (w * chunk >= n) return;
 
     RW::build_seg_lut(lut_all[warp], lane);
     RW rw(p, par, lane, wq_all[warp], lut_all[warp]);
@@ -708,55 +709,49 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
     const CellT* const state = reinterpret_cast<const CellT*>(p.state);
     const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;
 
-    struct Loaded {
-        uint4 v[3];
-        uint32_t h[3];
-        int y, strip, env;
-    };
-    auto load = [&](unsigned long long task, Loaded& L) {
-        L.y = (int)(task & 0xFFFFFu);
-        L.strip = (int)((task >> 20) & 0xFFu);
-        L.env = (int)(task >> 28);
-        const int x0 = L.strip * WR;
-        const int xl = x0 + lane * CPL;
-        const bool in_x = xl < pitch;
-        const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
-        const bool hpred = (lane == 0 && L.strip > 0) || (lane == 31 && x0 + WR < pitch);
-        const CellT* const envbase = state + (long long)L.env * p.plane;
+    // chunks of ROWS_CHUNK consecutive tasks, dealt round-robin to the warps: consecutive tasks are
+    // mostly consecutive rows of one env (two of the three rows of a task then come from L1),
+    // and dealing small chunks spreads a long fire front over many warps
+    for (unsigned long long c = w; c * chunk < n; c += n_warps) {
+        const unsigned long long t_end = min((c + 1) * chunk, n);
+        for (unsigned long long t = c * chunk; t < t_end; ++t) {
+            const unsigned long long task = p.rows[t];
+            const int y = (int)(task & 0xFFFFFu), strip = (int)((task >> 20) & 0xFFu), env = (int)(task >> 28);
+            if (env != rw.env) rw.set_env(env, p.meta[(long long)par * p.meta_stride + env]);
+            const int x0 = strip * WR;
+            rw.x0 = x0;
+            const int xl = x0 + lane * CPL;
+            const bool in_x = xl < pitch;
+            const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
+            const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
+            const CellT* const envbase = state + (long long)env * p.plane;
+            uint4 v[3];
+            uint32_t h[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int yy = L.y - 1 + r;
-            const CellT* rowp = filler;
-            if (yy >= 0 && yy < H) rowp = envbase + (long long)yy * pitch;
-            else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)L.env * p.halo_top_plane;
-            else if (yy == H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)L.env * p.halo_bottom_plane;
-            L.v[r] = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
-            L.h[r] = ST_BURNED;
-            if (in_x) L.v[r] = *reinterpret_cast<const uint4*>(rowp + xl);
-            if (hpred) L.h[r] = rowp[hoff];
-        }
-    };
-
-    Loaded cur, nxt;
-    load(p.rows[t], cur);
-    for (; t < t_end; ++t) {
-        const bool more = t + 1 < t_end;
-        if (more) load(p.rows[t + 1], nxt);  // in flight while `cur` is examined
-        if (cur.env != rw.env) rw.set_env(cur.env, p.meta[(long long)par * p.meta_stride + cur.env]);
-        rw.x0 = cur.strip * WR;
-        __syncwarp();  // the previous task's readers are done with the staging rows
+            for (int r = 0; r < 3; ++r) {
+                const int yy = y - 1 + r;
+                const CellT* rowp = filler;
+                if (yy >= 0 && yy < H) rowp = envbase + (long long)yy * pitch;
+                else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
+                else if (yy == H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
+                v[r] = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+                h[r] = ST_BURNED;
+                if (in_x) v[r] = *reinterpret_cast<const uint4*>(rowp + xl);
+                if (hpred) h[r] = rowp[hoff];
+            }
+            __syncwarp();  // the previous task's readers are done with the staging rows
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            *reinterpret_cast<uint4*>(&sm[r][CPL + lane * CPL]) = cur.v[r];
-            if (lane == 0) sm[r][CPL - 1] = (CellT)cur.h[r];
-            if (lane == 31) sm[r][CPL + WR] = (CellT)cur.h[r];
+            for (int r = 0; r < 3; ++r) {
+                *reinterpret_cast<uint4*>(&sm[r][CPL + lane * CPL]) = v[r];
+                if (lane == 0) sm[r][CPL - 1] = (CellT)h[r];
+                if (lane == 31) sm[r][CPL + WR] = (CellT)h[r];
+            }
+            __syncwarp();
+            const uint4 vo = make_uint4(v[0].x | v[1].x | v[2].x, v[0].y | v[1].y | v[2].y, v[0].z | v[1].z | v[2].z,
+                                        v[0].w | v[1].w | v[2].w);
+            const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, h[0] | h[1] | h[2]));
+            rw.detail_row(y, sm[0], sm[1], sm[2], act);
         }
-        __syncwarp();
-        const uint4 vo = make_uint4(cur.v[0].x | cur.v[1].x | cur.v[2].x, cur.v[0].y | cur.v[1].y | cur.v[2].y,
-                                    cur.v[0].z | cur.v[1].z | cur.v[2].z, cur.v[0].w | cur.v[1].w | cur.v[2].w);
-        const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, cur.h[0] | cur.h[1] | cur.h[2]));
-        rw.detail_row(cur.y, sm[0], sm[1], sm[2], act);
-        if (more) cur = nxt;
     }
     rw.finish();
 }
