@@ -18,7 +18,7 @@ def _oracle(wl, start):
     return DenseFire(wl.planes, DenseParams(**wl.engine_kwargs()), tuple(int(v) for v in start))
 
 
-def _run_against_oracle(wl, start, n_steps, check_every=1, **engine_kw):
+def _run_against_oracle(wl, start, n_steps, check_every=1, min_steps=15, **engine_kw):
     """Steps engine and oracle together; fire_map must be identical at every checked step.
     The oracle also yields the smallest relative distance of any ignition test from the
     threshold: float32 libm differences (<= 1e-6) cannot flip a test further away than that."""
@@ -37,7 +37,11 @@ def _run_against_oracle(wl, start, n_steps, check_every=1, **engine_kw):
                 margin = min(margin, float(np.min(np.abs(o.burn[changed] - wl.pixel_scale)) / max(wl.pixel_scale, 1e-9)))
             eng.step(1)
             if margin < 2e-5:
-                pytest.skip(f"oracle ignition margin {margin:.1e} at step {step}: a 1-ulp libm difference could flip it")
+                # an ignition test this close to the threshold could be flipped by a 1-ulp libm
+                # difference: everything up to the previous step has been verified, stop here
+                if step <= min_steps:
+                    pytest.skip(f"oracle ignition margin {margin:.1e} already at step {step}")
+                return o
             if step % check_every == 0 or st != 1:
                 gst, gel, gn = eng.status()
                 assert int(gst[0]) == st and float(gel[0]) == o.elapsed_time and int(gn[0]) == o.step_count, step
@@ -211,3 +215,34 @@ def test_cell_life_cycle_is_monotone():
             assert np.array_equal(age >= 0, cur[3] == 1)
             assert age.max() <= wl.max_fire_duration  # == max: pruned by the next update()
             prev = cur
+
+
+@pytest.mark.parametrize("shape,start", [((1, 1), (0, 0)), ((1, 40), (39, 0)), ((40, 1), (0, 0)), ((3, 3), (2, 2)),
+                                          ((17, 513), (512, 16)), ((70, 1030), (0, 69))])
+def test_degenerate_and_ragged_grids_against_oracle(shape, start):
+    """Single cells, single rows / columns, widths that are not a multiple of the 16-cell load or
+    of the 512-cell strip, ignition in a corner: the reference's bounds handling (fire.py:192-205)."""
+    from simfire_b200.workloads import Workload
+
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    planes = dict(w_0=rng.uniform(0.02, 0.4, (H, W)), delta=rng.uniform(0.5, 4.0, (H, W)),
+                  M_x=rng.uniform(0.15, 0.4, (H, W)), sigma=rng.uniform(1200, 3400, (H, W)),
+                  U=rng.uniform(0, 2000, (H, W)), U_dir=rng.uniform(0, 360, (H, W)),
+                  slope_mag=rng.uniform(0, 0.3, (H, W)), slope_dir=rng.uniform(-3, 3, (H, W)))  # fmt: skip
+    planes["w_0"][rng.random((H, W)) < 0.1] = 0.0
+    planes["w_0"][start[1], start[0]] = 0.2
+    wl = Workload("ragged", H, W, planes, pixel_scale=60.0, update_rate=1.5, max_fire_duration=3, max_time=90.0,
+                  attenuate_line_ros=True, diagonal_spread=True, M_f=0.02, init_pos=start)  # fmt: skip
+    _run_against_oracle(wl, start, 70)
+
+
+@pytest.mark.parametrize("max_dur", [1, 30, 31, 200])
+def test_fire_duration_limits_of_the_two_cell_layouts(max_dur):
+    """max_fire_duration 30 is the last value the 8-bit cell can encode, 31 switches to 16-bit."""
+    from simfire_b200.workloads import synthetic_operational
+
+    wl = synthetic_operational(64, 96, seed=11, patch=8)
+    wl.max_fire_duration = max_dur
+    wl.pixel_scale = 400.0  # slow spread: sprites really live for many steps
+    _run_against_oracle(wl, wl.init_pos, 90 if max_dur < 100 else 260, check_every=5)
