@@ -142,6 +142,7 @@ struct sfb_sim {
     cudaStream_t stream;      // stream in use
     cudaStream_t own_stream;  // created by the handle
     cudaEvent_t ev[4];
+    cudaEvent_t span[2];      // sfb_step_timed
     // scratch
     void* stage;          // device staging for host <-> device plane traffic
     size_t stage_bytes;
@@ -505,6 +506,8 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : s->span)
+        if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -518,6 +521,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     s->stream = s->own_stream;
     for (auto& e : s->ev) CU(cudaEventCreate(&e));
+    for (auto& e : s->span) CU(cudaEventCreate(&e));
 
     DevParams& d = s->d;
     memset(&d, 0, sizeof(d));
@@ -1242,18 +1246,20 @@ extern "C" int sfb_step(sfb_sim* s, int32_t n_steps, int32_t sync) {
 
 extern "C" int sfb_step_timed(sfb_sim* s, int32_t n_steps, float* ms) {
     if (!s || !ms) return fail(SFB_ERR_INVALID, "sfb_step_timed: null argument");
+    if (n_steps < 0) return fail(SFB_ERR_INVALID, "sfb_step_timed: n_steps %d", n_steps);
     int rc;
     if ((rc = use(s))) return rc;
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
-    CU(cudaEventRecord(a, s->stream));
-    if ((rc = enqueue_steps(s, n_steps))) return rc;
-    CU(cudaEventRecord(b, s->stream));
-    CU(cudaEventSynchronize(b));
-    CU(cudaEventElapsedTime(ms, a, b));
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    // the handle's own events (ev[0] / ev[3] are only used by the per-kernel timing mode, which
+    // synchronises after every step, so they are free here)
+    const bool was_timing = s->timing != 0;
+    s->timing = 0;
+    CU(cudaEventRecord(s->span[0], s->stream));
+    rc = enqueue_steps(s, n_steps);
+    s->timing = was_timing;
+    if (rc) return rc;
+    CU(cudaEventRecord(s->span[1], s->stream));
+    CU(cudaEventSynchronize(s->span[1]));
+    CU(cudaEventElapsedTime(ms, s->span[0], s->span[1]));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1603,17 +1609,21 @@ extern "C" int sfb_rate_of_spread(int32_t device, const int8_t* dir, const float
     int8_t* d_dir = nullptr;
     float* d_rec = nullptr;
     double* d_out = nullptr;
-    CU(cudaMalloc((void**)&d_dir, (size_t)n));
-    CU(cudaMalloc((void**)&d_rec, (size_t)n * 8 * sizeof(float)));
-    CU(cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)));
-    CU(cudaMemcpy(d_dir, dir, (size_t)n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_rec, rec, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice));
-    SfbParticle fp{particle[0], particle[1], particle[2], particle[3], particle[4]};
-    k_rate_of_spread<<<nblocks(n, 128), 128>>>(d_dir, d_rec, fp, (long long)n, d_out);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    auto body = [&]() -> int {
+        CU(cudaMalloc((void**)&d_dir, (size_t)n));
+        CU(cudaMalloc((void**)&d_rec, (size_t)n * 8 * sizeof(float)));
+        CU(cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)));
+        CU(cudaMemcpy(d_dir, dir, (size_t)n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_rec, rec, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice));
+        SfbParticle fp{particle[0], particle[1], particle[2], particle[3], particle[4]};
+        k_rate_of_spread<<<nblocks(n, 128), 128>>>(d_dir, d_rec, fp, (long long)n, d_out);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int rc = body();
     cudaFree(d_dir);
     cudaFree(d_rec);
     cudaFree(d_out);
-    return 0;
+    return rc;
 }
