@@ -114,7 +114,9 @@ class HostPool {
 struct EnvGroup {
     DevParams d;
     CUtensorMap tmap;
-    cudaStream_t stream;
+    cudaStream_t stream;       // equal priority: best overlap between the groups
+    cudaStream_t stream_prio;  // descending priority: groups finish one after the other (change log on)
+    cudaStream_t last_stream;  // the one the last steps ran on
     cudaEvent_t done;
     unsigned long long* counters;  // qcount[2] | unit_next[2] | rows_count[2] | rows_next[2]
     int sweep_blocks, rows_blocks;
@@ -160,10 +162,9 @@ struct sfb_sim {
     // host mirror bookkeeping (sfb_sync_fire_maps)
     const int8_t* mirror;      // buffer the last sync wrote, nullptr = none valid
     int full_resync;           // something changed that the log does not describe
-    unsigned long long* log_host;  // pinned staging for the change log
-    size_t log_host_entries;
-    unsigned long long* log_head;  // pinned: {count, overflow} read back each sync
-    unsigned long long* log_mapped;  // the change log itself when it lives in mapped host memory
+    unsigned long long* log_head;    // pinned: {count, overflow} of every log, read back each sync
+    unsigned long long* log_mapped[MAX_ENV_GROUPS];  // the change logs (mapped host memory)
+    unsigned long long* log_counts;  // device: {count, overflow} x n_logs
     HostPool* pool;
     std::vector<std::vector<unsigned long long>> buckets;  // [chunk * T + owner]
 };
@@ -256,17 +257,14 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
     m.time_quit = p.has_max_time && (p.dt > p.max_time || 0.0 > p.max_time);
     p.meta[(long long)par * p.meta_stride + env] = m;
     if (p.track) {  // "env was cleared", then its first burning cell, in this order
-        const unsigned long long slot = atomicAdd(p.chg_count, 2ULL);
-        if (slot + 1 < (unsigned long long)p.chg_cap) {
-            p.chg[slot] = (unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48);
-            const bool inside = y >= 0 && y < p.H;
-            const long long idx = (long long)env * p.plane + (long long)(inside ? y : 0) * p.pitch + x;
-            // a slab that does not hold the ignition row logs the reset twice (harmless)
-            p.chg[slot + 1] = inside ? ((unsigned long long)idx | (1ULL << 48))
-                                     : ((unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48));
-        } else {
-            *p.chg_overflow = 1;
-        }
+        const LogRef& L = log_of_env(p, env);
+        const unsigned long long slot = atomicAdd(L.count, 2ULL);
+        const unsigned long long reset = (unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48);
+        const bool inside = y >= 0 && y < p.H;
+        const long long idx = (long long)env * p.plane + (long long)(inside ? y : 0) * p.pitch + x;
+        log_put(L, slot, reset);
+        // a slab that does not hold the ignition row logs the reset twice (harmless)
+        log_put(L, slot + 1, inside ? ((unsigned long long)idx | (1ULL << 48)) : reset);
     }
 }
 
@@ -281,9 +279,8 @@ __global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int
     CellT* c = reinterpret_cast<CellT*>(p.state) + idx;
     *c = (CellT)((*c & ~7) | to_internal(k));
     if (p.track) {
-        const unsigned long long slot = atomicAdd(p.chg_count, 1ULL);
-        if (slot < (unsigned long long)p.chg_cap) p.chg[slot] = (unsigned long long)idx | ((unsigned long long)k << 48);
-        else *p.chg_overflow = 1;
+        const LogRef& L = log_of_env(p, env);
+        log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48));
     }
 }
 
@@ -491,13 +488,13 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     for (auto& gr : s->groups) {
         cudaFree(gr.counters);
         if (gr.stream) cudaStreamDestroy(gr.stream);
+        if (gr.stream_prio) cudaStreamDestroy(gr.stream_prio);
         if (gr.done) cudaEventDestroy(gr.done);
     }
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
-    if (s->log_mapped) cudaFreeHost(s->log_mapped);
-    else cudaFree(s->d.chg);
-    cudaFree(s->d.chg_count);
-    if (s->log_host) cudaFreeHost(s->log_host);
+    for (auto& m : s->log_mapped)
+        if (m) cudaFreeHost(m);
+    cudaFree(s->log_counts);
     if (s->log_head) cudaFreeHost(s->log_head);
     delete s->pool;
     cudaFree((void*)s->d.filler);
@@ -582,22 +579,6 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     s->static_dirty = 1;
     if ((rc = dmalloc(s, &d.meta, (size_t)2 * d.E * sizeof(EnvMeta)))) return rc;
     d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
-    if (d.track) {
-        // The log lives in pinned HOST memory mapped into the device address space: k_eval's
-        // warp-aggregated appends are coalesced 256-byte posted writes over PCIe, so by the time
-        // the stream is idle the entries are already on the host and no D2H copy is needed.
-        d.chg_cap = std::min<int64_t>(std::max<int64_t>(1 << 20, total / 16), (int64_t)16 << 20);
-        if (getenv("SFB_LOG_ON_DEVICE")) {
-            if ((rc = dmalloc(s, &d.chg, (size_t)d.chg_cap * 8))) return rc;
-        } else {
-            CU(cudaHostAlloc((void**)&s->log_mapped, (size_t)d.chg_cap * 8, cudaHostAllocMapped | cudaHostAllocPortable));
-            CU(cudaHostGetDevicePointer((void**)&d.chg, s->log_mapped, 0));
-        }
-        if ((rc = dmalloc(s, &d.chg_count, 2 * sizeof(unsigned long long)))) return rc;  // {count, overflow}
-        d.chg_overflow = reinterpret_cast<int32_t*>(d.chg_count + 1);
-        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
-        CU(cudaMallocHost((void**)&s->log_head, 2 * sizeof(unsigned long long)));
-    }
     {
         const size_t n = (size_t)d.pitch + 32;
         std::vector<uint8_t> fill(n * s->cell_bytes, 0);
@@ -648,6 +629,13 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
 
+    // second set of streams with descending priority: the kernels of earlier groups are scheduled
+    // first, so the groups finish one after the other and the host can patch the change log of a
+    // finished group while the later ones still compute (used when the change log is on; without
+    // it the equal-priority streams overlap the groups slightly better)
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // hi is numerically smaller
+    int next_prio = prio_hi;
     auto make_view = [&](EnvGroup& gr, int e0, int cnt, int64_t q_off, int64_t q_cap, bool own_stream) -> int {
         const int64_t off = (int64_t)e0 * d.plane;
         gr.d = d;
@@ -688,7 +676,13 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
             if (r != CUDA_SUCCESS) return fail(SFB_ERR_CUDA, "sfb_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
         }
         gr.stream = nullptr;
-        if (own_stream) CU(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
+        gr.stream_prio = nullptr;
+        gr.last_stream = nullptr;
+        if (own_stream) {
+            CU(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithPriority(&gr.stream_prio, cudaStreamNonBlocking, next_prio));
+            if (next_prio < prio_lo) ++next_prio;
+        }
         CU(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
         const long long need = (v.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)sweep_per_sm * s->n_sm);
@@ -706,6 +700,44 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
             if ((rc = make_view(s->groups[g], e0, cnt, q_off, q_cap, true))) return rc;
             q_off += q_cap;
         }
+    }
+    // change logs: one per env group (one in all if there is a single group).  They live in pinned
+    // HOST memory mapped into the device address space: the warp-aggregated appends of k_eval
+    // are coalesced 256-byte posted writes over PCIe, so by the time a group's stream is idle its
+    // entries are already on the host and no D2H copy is needed.
+    if (d.track) {
+        const int nl = std::max<int>(1, (int)s->groups.size());
+        const int64_t cap_all = std::min<int64_t>(std::max<int64_t>(1 << 20, total / 16), (int64_t)16 << 20);
+        if ((rc = dmalloc(s, &s->log_counts, (size_t)nl * 2 * sizeof(unsigned long long)))) return rc;
+        CU(cudaMemsetAsync(s->log_counts, 0, (size_t)nl * 2 * sizeof(unsigned long long), s->stream));
+        CU(cudaMallocHost((void**)&s->log_head, (size_t)nl * 2 * sizeof(unsigned long long)));
+        d.n_logs = nl;
+        for (int g = 0; g < nl; ++g) {
+            const int e0 = nl == 1 ? 0 : (int)((long long)d.E * g / nl);
+            const int e1 = nl == 1 ? d.E : (int)((long long)d.E * (g + 1) / nl);
+            LogRef& L = d.logs[g];
+            L.cap = std::max<int64_t>(1 << 16, cap_all * (e1 - e0) / d.E);
+            CU(cudaHostAlloc((void**)&s->log_mapped[g], (size_t)L.cap * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU(cudaHostGetDevicePointer((void**)&L.buf, s->log_mapped[g], 0));
+            L.count = s->log_counts + 2 * g;
+            d.log_e0[g] = e0;
+            d.log_e0[g + 1] = e1;
+        }
+        auto bind = [&](EnvGroup& gr, int g) {
+            gr.d.n_logs = d.n_logs;
+            for (int k = 0; k <= nl; ++k) gr.d.log_e0[k] = d.log_e0[k];
+            for (int k = 0; k < nl; ++k) gr.d.logs[k] = d.logs[k];
+            gr.d.chg = d.logs[g].buf;
+            gr.d.chg_count = d.logs[g].count;
+            gr.d.chg_overflow = reinterpret_cast<int32_t*>(d.logs[g].count + 1);
+            gr.d.chg_cap = d.logs[g].cap;
+        };
+        bind(s->all, 0);  // only used for stepping when there is a single log
+        for (int g = 0; g < (int)s->groups.size(); ++g) bind(s->groups[g], g);
+        d.chg = d.logs[0].buf;
+        d.chg_count = d.logs[0].count;
+        d.chg_overflow = reinterpret_cast<int32_t*>(d.logs[0].count + 1);
+        d.chg_cap = d.logs[0].cap;
     }
     // the handle-wide params point at the `all` view's counters (setup kernels never touch them)
     d.qcount = s->all.d.qcount;
@@ -997,7 +1029,8 @@ static void sync_group_views(sfb_sim* s) {
 }
 static void sync_one_view(sfb_sim* s, EnvGroup& gr) {
     {
-        gr.d.track = s->d.track;
+        // the whole-handle view of a multi-group handle does not log (its steps invalidate the logs)
+        gr.d.track = (&gr == &s->all && !s->groups.empty()) ? 0 : s->d.track;
         gr.d.halo_top = s->d.halo_top;
         gr.d.halo_bottom = s->d.halo_bottom;
         gr.d.halo_top_plane = s->d.halo_top_plane;
@@ -1063,11 +1096,10 @@ static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
     int rc;
-    // one view of all envs on the handle's stream: single-group handles, per-kernel timing, and
-    // with the change log on (the log then stays ordered by env, which keeps the host-side
-    // patching cache-friendly; that path is bound by the host anyway)
-    if (s->groups.empty() || s->timing || s->d.track) {
+    // one view of all envs on the handle's stream: single-group handles and per-kernel timing
+    if (s->groups.empty() || s->timing) {
         if ((rc = enter_mode(s, 1))) return rc;
+        if (!s->groups.empty() && s->d.track) s->full_resync = 1;  // the whole-handle view does not log per group
         for (int i = 0; i < n; ++i) {
             if ((rc = enqueue_sweep(s))) return rc;
             if ((rc = enqueue_eval(s))) return rc;
@@ -1078,19 +1110,22 @@ static int enqueue_steps(sfb_sim* s, int n) {
     if ((rc = derive_if_dirty(s))) return rc;
     sync_group_views(s);
     CU(cudaEventRecord(s->fork_ev, s->stream));
-    for (auto& gr : s->groups) CU(cudaStreamWaitEvent(gr.stream, s->fork_ev, 0));
+    for (auto& gr : s->groups) {
+        gr.last_stream = s->d.track ? gr.stream_prio : gr.stream;
+        CU(cudaStreamWaitEvent(gr.last_stream, s->fork_ev, 0));
+    }
     int par = s->parity;
     for (int i = 0; i < n; ++i) {
         for (auto& gr : s->groups) {
-            launch_sweep(s, gr, gr.stream, par);
-            launch_rows(s, gr, gr.stream, par);
-            launch_eval(s, gr, gr.stream, par);
+            launch_sweep(s, gr, gr.last_stream, par);
+            launch_rows(s, gr, gr.last_stream, par);
+            launch_eval(s, gr, gr.last_stream, par);
         }
         par ^= 1;
     }
     s->parity = par;
     for (auto& gr : s->groups) {
-        CU(cudaEventRecord(gr.done, gr.stream));
+        CU(cudaEventRecord(gr.done, gr.last_stream));
         CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
     }
     return 0;
@@ -1322,11 +1357,12 @@ extern "C" int sfb_get_fire_map(sfb_sim* s, int32_t env0, int32_t n, int8_t* out
 // (1) thread k splits chunk k of the log into T buckets by owner (owner = contiguous range of
 // cell indices), keeping the order; (2) owner o applies bucket (0, o), (1, o), ... in chunk
 // order.  Each entry is touched twice in total, whatever T is.
-static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror) {
+// [base, base + total): the cells this log can name (its env group); the owners split that range.
+static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror, unsigned long long base,
+                      unsigned long long total) {
     const DevParams& d = s->d;
     const long long hw = (long long)d.H * d.W;
     const bool linear = d.pitch == d.W;
-    const unsigned long long total = (unsigned long long)d.E * (unsigned long long)d.plane;
     auto put = [&](unsigned long long idx, int st) {
         if (linear) {
             mirror[idx] = (int8_t)st;
@@ -1352,7 +1388,7 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
         for (long long i = 0; i < n; ++i) {
             const unsigned long long e = log[i], idx = e & 0xFFFFFFFFFFFFull;
             const int st = (int)(e >> 48) & 7;
-            if (st == LOG_ENV_RESET) clear_env_part((long long)idx, 0, total);
+            if (st == LOG_ENV_RESET) clear_env_part((long long)idx, base, base + total);
             else put(idx, st);
         }
         return;
@@ -1365,16 +1401,16 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
         for (long long i = i0; i < i1; ++i) {
             const unsigned long long e = log[i], idx = e & 0xFFFFFFFFFFFFull;
             if (((int)(e >> 48) & 7) == LOG_ENV_RESET) {
-                const unsigned long long e0 = idx * (unsigned long long)d.plane;
+                const unsigned long long e0 = idx * (unsigned long long)d.plane - base;  // relative to the log's range
                 for (unsigned o = (unsigned)(e0 / span); o < T && (unsigned long long)o * span < e0 + (unsigned long long)d.plane; ++o)
                     s->buckets[(size_t)k * T + o].push_back(e);
             } else {
-                s->buckets[(size_t)k * T + (unsigned)(idx / span)].push_back(e);
+                s->buckets[(size_t)k * T + std::min<unsigned>(T - 1, (unsigned)((idx - base) / span))].push_back(e);
             }
         }
     });
     s->pool->run([&](unsigned o) {
-        const unsigned long long lo = (unsigned long long)o * span, hi = std::min(total, lo + span);
+        const unsigned long long lo = base + (unsigned long long)o * span, hi = std::min(base + total, lo + span);
         for (unsigned k = 0; k < T; ++k)
             for (const unsigned long long e : s->buckets[(size_t)k * T + o]) {
                 const unsigned long long idx = e & 0xFFFFFFFFFFFFull;
@@ -1396,69 +1432,73 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     DevParams& d = s->d;
     static const bool debug = getenv("SFB_DEBUG_TIMING") != nullptr;
     const double t0 = debug ? now_ms() : 0.0;
-    unsigned long long cnt = 0;
-    bool ovf = false;
-    if (d.track) {
-        CU(cudaMemcpyAsync(s->log_head, d.chg_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    const int nl = d.track ? d.n_logs : 0;
+    const bool grouped = !s->groups.empty() && s->last_mode == 2;
+
+    if (!d.track || s->full_resync || s->mirror != mirror) {
         CU(cudaStreamSynchronize(s->stream));
-        cnt = s->log_head[0];
-        ovf = (s->log_head[1] & 0xFFFFFFFFull) != 0;
+        if ((rc = download_maps(s, 0, d.E, mirror))) return rc;
+        if (s->log_counts) CU(cudaMemsetAsync(s->log_counts, 0, (size_t)d.n_logs * 2 * sizeof(unsigned long long), s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (n_changes) *n_changes = -1;
+        s->mirror = mirror;
+        s->full_resync = 0;
+        if (debug) fprintf(stderr, "[sfb_sync] full download %.3f ms\n", now_ms() - t0);
+        return 0;
     }
-    const double t1 = debug ? now_ms() : 0.0;
-    double t2 = t1;
-    const bool full = !d.track || ovf || s->full_resync || s->mirror != mirror || cnt > (unsigned long long)d.chg_cap;
-    if (full) {
+    if (!s->pool) {
+        unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+        if (const char* e = getenv("SFB_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        s->pool = new HostPool(std::min(nt, 64u));
+    }
+    // Log by log: wait for the group that feeds it (the other groups may still be computing),
+    // fetch its {count, overflow}, patch.  The entries themselves are already in host memory.
+    long long total = 0;
+    bool overflow = false;
+    double wait_ms = 0, patch_ms = 0;
+    for (int g = 0; g < nl && !overflow; ++g) {
+        const double ta = debug ? now_ms() : 0.0;
+        cudaStream_t st = s->stream;
+        if (grouped) {
+            CU(cudaEventSynchronize(s->groups[g].done));
+            st = s->groups[g].last_stream ? s->groups[g].last_stream : s->groups[g].stream;
+        }
+        CU(cudaMemcpyAsync(s->log_head + 2 * g, d.logs[g].count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const unsigned long long cnt = s->log_head[2 * g];
+        if ((s->log_head[2 * g + 1] & 0xFFFFFFFFull) != 0 || cnt > (unsigned long long)d.logs[g].cap) {
+            overflow = true;
+            break;
+        }
+        const double tb = debug ? now_ms() : 0.0;
+        if (cnt > 0)
+            apply_log(s, s->log_mapped[g], (long long)cnt, mirror, (unsigned long long)d.log_e0[g] * d.plane,
+                      (unsigned long long)(d.log_e0[g + 1] - d.log_e0[g]) * d.plane);
+        total += (long long)cnt;
+        if (debug) {
+            wait_ms += tb - ta;
+            patch_ms += now_ms() - tb;
+        }
+    }
+    CU(cudaStreamSynchronize(s->stream));  // every group has joined the handle's stream
+    CU(cudaMemsetAsync(s->log_counts, 0, (size_t)d.n_logs * 2 * sizeof(unsigned long long), s->stream));
+    if (overflow) {  // a log ran full: what was patched so far is consistent but incomplete
         if ((rc = download_maps(s, 0, d.E, mirror))) return rc;
         CU(cudaStreamSynchronize(s->stream));
-        if (!d.track) s->full_resync = 1;
-        if (n_changes) *n_changes = -1;
-    } else if (cnt > 0 && s->log_mapped) {
-        // entries are already in host memory; patch, then let the device reuse the log
-        t2 = debug ? now_ms() : 0.0;
-        if (!s->pool) {
-            unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-            if (const char* e = getenv("SFB_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-            s->pool = new HostPool(std::min(nt, 64u));
-        }
-        apply_log(s, s->log_mapped, (long long)cnt, mirror);
-        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
-        if (n_changes) *n_changes = (int64_t)cnt;
-    } else if (cnt > 0) {
-        if (s->log_host_entries < cnt) {
-            if (s->log_host) CU(cudaFreeHost(s->log_host));
-            s->log_host = nullptr;
-            s->log_host_entries = 0;
-            const size_t want = std::max<size_t>((size_t)cnt * 2, (size_t)1 << 20);
-            CU(cudaMallocHost((void**)&s->log_host, want * 8));
-            s->log_host_entries = want;
-        }
-        CU(cudaMemcpyAsync(s->log_host, d.chg, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        // the device log may be refilled from here on: reset it before the host-side patching
-        CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
-        t2 = debug ? now_ms() : 0.0;
-        if (!s->pool) {
-            unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-            if (const char* e = getenv("SFB_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-            s->pool = new HostPool(std::min(nt, 64u));
-        }
-        apply_log(s, s->log_host, (long long)cnt, mirror);
-        if (n_changes) *n_changes = (int64_t)cnt;
-    } else if (n_changes) {
-        *n_changes = 0;
+        total = -1;
     }
-    if (d.track && (full || cnt == 0)) CU(cudaMemsetAsync(d.chg_count, 0, 2 * sizeof(unsigned long long), s->stream));
+    if (n_changes) *n_changes = total;
     s->mirror = mirror;
     s->full_resync = 0;
     if (debug)
-        fprintf(stderr, "[sfb_sync] wait+head %.3f ms, log d2h %.3f ms (%llu entries), patch %.3f ms%s\n", t1 - t0, t2 - t1,
-                cnt, now_ms() - t2, full ? " (full download)" : "");
+        fprintf(stderr, "[sfb_sync] %d logs, %lld entries: waiting for the device %.3f ms, patching %.3f ms%s\n", nl, total,
+                wait_ms, patch_ms, overflow ? " (overflow: full download)" : "");
     return 0;
 }
 
 extern "C" int sfb_set_tracking(sfb_sim* s, int32_t enabled) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_set_tracking: null handle");
-    if (!s->d.chg) return fail(SFB_ERR_STATE, "sfb_set_tracking: the handle was created without SFB_TRACK_CHANGES");
+    if (!s->log_counts) return fail(SFB_ERR_STATE, "sfb_set_tracking: the handle was created without SFB_TRACK_CHANGES");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_set_tracking: a step is half done");
     const int on = enabled != 0;
     if (on && !s->d.track) s->full_resync = 1;  // changes made while paused were not logged

@@ -71,6 +71,13 @@ struct SlabMailbox {
     volatile int32_t error;                        // a wait gave up (peer stalled)
 };
 
+constexpr int MAX_ENV_GROUPS = 16;
+struct LogRef {
+    unsigned long long* buf;    // entries (host-mapped memory)
+    unsigned long long* count;  // [0] entries so far, [1] overflow flag
+    long long cap;
+};
+
 struct DerivedRec {  // 48 B: what k_eval gathers per candidate item
     SfbFuelTerms fuel;  // fuel-only Rothermel terms of the cell (k_derive_static)
     float4 env;         // U, U_dir, slope_mag, slope_dir
@@ -111,13 +118,29 @@ struct DevParams {
     struct SlabMailbox* mailbox;       // this slab's mailbox (peers write into it)
     struct SlabMailbox* peer_box[8];   // every slab's mailbox as seen from this device (own included)
     int32_t slab_rank, slab_world;
-    // change log (SFB_TRACK_CHANGES)
+    // change log (SFB_TRACK_CHANGES): one log per env group so that each stays ordered by env and
+    // the host can patch the log of a group that is done while the other groups still compute.
+    // A view's k_eval appends to chg (its own group's log); the setup kernels, which see the
+    // whole handle, route by env through logs[] / log_e0[].
     int32_t track;
     unsigned long long* chg;        // [chg_cap] idx | BurnStatus << 48
     unsigned long long* chg_count;  // entries appended since the host last drained the log
     int32_t* chg_overflow;
     int64_t chg_cap;
+    int32_t n_logs;
+    int32_t log_e0[MAX_ENV_GROUPS + 1];  // log g holds envs [log_e0[g], log_e0[g + 1])
+    LogRef logs[MAX_ENV_GROUPS];
 };
+
+__device__ __forceinline__ const LogRef& log_of_env(const DevParams& p, int env) {
+    int g = 0;
+    while (g + 1 < p.n_logs && env >= p.log_e0[g + 1]) ++g;
+    return p.logs[g];
+}
+__device__ __forceinline__ void log_put(const LogRef& L, unsigned long long slot, unsigned long long entry) {
+    if (slot < (unsigned long long)L.cap) L.buf[slot] = entry;
+    else *reinterpret_cast<int32_t*>(L.count + 1) = 1;
+}
 
 template <typename CellT>
 struct Cell;
