@@ -322,8 +322,8 @@ struct RowWorker {
     }
 
     const DevParams& p;
-    int par, lane, env = -1, x0 = 0, tm1 = 0, max_dur;
-    bool spread = false, diagonal, attenuate;
+    int par, lane, env = -1, x0 = 0, tm1 = 0, max_dur, W;
+    bool spread = false, diagonal, attenuate, track, lane_owner;
     long long env_off = 0;
     uint32_t look_mask;
     unsigned long long* wq;
@@ -337,8 +337,11 @@ struct RowWorker {
         : p(p_), par(par_), lane(lane_), wq(wq_), seg_lut(lut_),
           key_lut(reinterpret_cast<int*>(const_cast<uint32_t*>(lut_)) + 32) {
         max_dur = p.max_dur;
+        W = p.W;
         diagonal = p.diagonal != 0;
         attenuate = p.attenuate != 0;
+        track = p.track != 0;
+        lane_owner = lane >= 1 && lane <= GW;
         look_mask = attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
     }
 
@@ -417,6 +420,7 @@ struct RowWorker {
     __device__ __forceinline__ void detail_row(int y, const CellT* rp, const CellT* rc, const CellT* rn, uint32_t act) {
         CellT* const state = reinterpret_cast<CellT*>(p.state);
         const long long row_idx = env_off + (long long)y * p.pitch;  // cell index of (y, x = 0)
+        const int cells = min(W - x0, WR);  // columns of this strip that exist in the grid
         uint32_t groups = 0;
         for (uint32_t a = act; a; a &= a - 1) groups |= seg_lut[__ffs(a) - 1];  // warp-uniform
         while (groups) {  // warp-uniform
@@ -435,7 +439,7 @@ struct RowWorker {
                 best = min(best, min(__shfl_down_sync(0xffffffffu, kp, 1) + 5, __shfl_up_sync(0xffffffffu, kp, 1) + 7));
             }
             const int x = x0 + col;
-            const bool owner = lane >= 1 && lane <= GW && col < WR && x < p.W;
+            const bool owner = lane_owner && col < cells;
             int s = cc & 7;
             if (owner && (cc >> 3) != 0) {
                 if (kc == NO_SRC) {  // duration reached max_fire_duration (fire.py:116-161)
@@ -447,7 +451,7 @@ struct RowWorker {
             }
             bool push = false;
             int dir = DIR_NONE;
-            if (p.track && owner && (cc >> 3) != 0 && kc == NO_SRC) {
+            if (track && owner && (cc >> 3) != 0 && kc == NO_SRC) {
                 push = true;
                 dir = DIR_PRUNED;
             }
@@ -729,8 +733,15 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
     RW rw(p, par, lane, wq_all[warp], lut_all[warp]);
     CellT(*sm)[RS] = sm_all[warp];
     const int H = p.H, pitch = p.pitch;
+    const long long plane = p.plane;
     const CellT* const state = reinterpret_cast<const CellT*>(p.state);
     const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;
+    // rows outside [0, H): the neighbour slab's edge row in slab mode, BURNED filler otherwise
+    auto edge_row = [&](int yy, int env) -> const CellT* {
+        if (yy == -1 && p.halo_top) return reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
+        if (yy == H && p.halo_bottom) return reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
+        return filler;
+    };
 
     // chunks of ROWS_CHUNK consecutive tasks, dealt round-robin to the warps: consecutive tasks are
     // mostly consecutive rows of one env (two of the three rows of a task then come from L1),
@@ -747,20 +758,20 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
             const bool in_x = xl < pitch;
             const int hoff = lane == 0 ? x0 - 1 : x0 + WR;
             const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
-            const CellT* const envbase = state + (long long)env * p.plane;
+            const CellT* const envbase = state + (long long)env * plane;
+            // rows y-1, y, y+1: one 64-bit multiply; only the grid's first / last row takes the slow path
+            const CellT* rowp[3];
+            rowp[1] = envbase + (long long)y * pitch;
+            rowp[0] = y > 0 ? rowp[1] - pitch : edge_row(-1, env);
+            rowp[2] = y + 1 < H ? rowp[1] + pitch : edge_row(H, env);
             uint4 v[3];
             uint32_t h[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const int yy = y - 1 + r;
-                const CellT* rowp = filler;
-                if (yy >= 0 && yy < H) rowp = envbase + (long long)yy * pitch;
-                else if (yy == -1 && p.halo_top) rowp = reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane;
-                else if (yy == H && p.halo_bottom) rowp = reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane;
                 v[r] = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
                 h[r] = ST_BURNED;
-                if (in_x) v[r] = *reinterpret_cast<const uint4*>(rowp + xl);
-                if (hpred) h[r] = rowp[hoff];
+                if (in_x) v[r] = *reinterpret_cast<const uint4*>(rowp[r] + xl);
+                if (hpred) h[r] = rowp[r][hoff];
             }
             __syncwarp();  // the previous task's readers are done with the staging rows
 #pragma unroll
