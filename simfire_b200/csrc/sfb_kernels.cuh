@@ -1,12 +1,15 @@
-// Device side of the B200 fire-spread stepper: data layout + the two hot-path kernels.
+// Device side of the B200 fire-spread stepper: data layout + the three hot-path kernels.
 //
 // One timestep of RothermelFireManager.update (simfire/game/managers/fire.py:616-719) is
 //
-//   k_sweep   dense pass over the packed per-cell state (1 B/cell): prune expired sprites
-//             (fire.py:116-161), find every ignitable cell that has a burning neighbour
-//             and the neighbour whose pair the reference writes last (fire.py:163-234,
-//             :704-705), push (cell, direction) work items to a queue, raise the per-env
-//             flags the reference's early returns depend on (fire.py:637, :651).
+//   k_sweep   streaming pass over the packed per-cell state (1 B/cell, TMA-fed): lists the
+//             warp-rows whose 3-row window holds a Fire sprite (or, with attenuation, a
+//             control line) as 8-byte row tasks.  HBM-bound; writes nothing else.
+//   k_rows    one warp per row task: prune expired sprites (fire.py:116-161), find every
+//             ignitable cell that has a burning neighbour and the neighbour whose pair the
+//             reference writes last (fire.py:163-234, :704-705) with a warp-shuffle min, push
+//             (cell, direction) work items to a queue, raise the per-env flags the reference's
+//             early returns depend on (fire.py:637, :651).  Issue-bound, front-proportional.
 //   k_eval    one thread per work item: Rothermel rate of spread of the destination cell
 //             (rothermel.py:4-136), control-line attenuation (fire.py:236-284), burn
 //             accumulation in float64 (fire.py:710), ignition on burn > pixel_scale
