@@ -48,6 +48,8 @@ def workload_spec(name: str):
         "target": (2048, 2048, 1024, True, True),
         # BASELINE configs[2]/[3]: 512^2 x 1024 envs per GPU, per-env terrain replaced by shared
         "cfg3": (512, 512, 1024, True, False),
+        # the same with a terrain of its own for every env (16 distinct terrains, env i gets i % 16)
+        "cfg3_perenv": (512, 512, 1024, False, False),
         # BASELINE configs[1]
         "cfg2": (1024, 1024, 1, False, False),
         "small": (256, 256, 64, True, True),
@@ -333,8 +335,16 @@ def gpu_arm(args):
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
                      sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, env_groups=args.env_groups,
                      **wl.engine_kwargs())  # fmt: skip
-    eng.set_static(wl.planes)
-    starts = wl.burnable_starts(E, seed=1000 + rank)
+    if args.workload == "cfg3_perenv":
+        from simfire_b200.workloads import synthetic_operational
+
+        variants = [synthetic_operational(H, W, seed=k) for k in range(16)]
+        for e in range(E):
+            eng.set_static(variants[e % 16].planes, env=e)
+        starts = np.stack([variants[e % 16].burnable_starts(1, seed=1000 + rank * E + e)[0] for e in range(E)])
+    else:
+        eng.set_static(wl.planes)
+        starts = wl.burnable_starts(E, seed=1000 + rank)
     eng.reset(starts)
     eng.step(args.burn_in)  # untimed: let the fronts develop so the timed steps see real fires
 
@@ -475,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="target", choices=["target", "cfg3", "cfg2", "small", "cfg5"])
+    ap.add_argument("--workload", default="target", choices=["target", "cfg3", "cfg3_perenv", "cfg2", "small", "cfg5"])
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--burn-in", type=int, default=60)
     ap.add_argument("--rows-per-chunk", type=int, default=0)
