@@ -129,6 +129,11 @@ struct sfb_sim {
     EnvGroup all;                  // one view of every env (whole queue / row list); used when the
                                    // groups would not overlap anyway (kernel timing, change log on)
     int last_mode;                 // 0 none yet, 1 `all`, 2 `groups`
+    // two consecutive steps (parity 0 then 1) of the whole-handle view as a CUDA graph: small
+    // batches are launch-bound, and a graph replay costs less than six kernel launches
+    cudaGraphExec_t pair_graph;
+    unsigned pair_graph_epoch, view_epoch;  // the graph bakes the view's parameters in
+    int64_t pair_launches_all, pair_launches_step;
     cudaEvent_t fork_ev;
     int cell_bytes;   // 1 or 2
     int use_tma;      // sweep front end
@@ -492,6 +497,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
         if (gr.done) cudaEventDestroy(gr.done);
     }
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
+    if (s->pair_graph) cudaGraphExecDestroy(s->pair_graph);
     for (auto& m : s->log_mapped)
         if (m) cudaFreeHost(m);
     cudaFree(s->log_counts);
@@ -1029,6 +1035,7 @@ static void sync_group_views(sfb_sim* s) {
 }
 static void sync_one_view(sfb_sim* s, EnvGroup& gr) {
     {
+        const DevParams before = gr.d;
         // the whole-handle view of a multi-group handle does not log (its steps invalidate the logs)
         gr.d.track = (&gr == &s->all && !s->groups.empty()) ? 0 : s->d.track;
         gr.d.halo_top = s->d.halo_top;
@@ -1039,6 +1046,7 @@ static void sync_one_view(sfb_sim* s, EnvGroup& gr) {
         gr.d.slab_rank = s->d.slab_rank;
         gr.d.slab_world = s->d.slab_world;
         for (int q = 0; q < SLAB_MAX_WORLD; ++q) gr.d.peer_box[q] = s->d.peer_box[q];
+        if (memcmp(&before, &gr.d, sizeof(DevParams)) != 0) s->view_epoch++;  // captured graphs are stale
     }
 }
 
@@ -1092,6 +1100,35 @@ static int enter_mode(sfb_sim* s, int mode) {
     return 0;
 }
 
+// replay (capturing it first if needed) the graph of two steps of the whole-handle view; parity must be 0
+static int run_pair_graph(sfb_sim* s) {
+    if (!s->pair_graph || s->pair_graph_epoch != s->view_epoch) {
+        if (s->pair_graph) CU(cudaGraphExecDestroy(s->pair_graph));
+        s->pair_graph = nullptr;
+        const int64_t la = s->launches_all, ls = s->launches_step;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        for (int par = 0; par < 2; ++par) {
+            launch_sweep(s, s->all, s->stream, par);
+            launch_rows(s, s->all, s->stream, par);
+            launch_eval(s, s->all, s->stream, par);
+        }
+        CU(cudaStreamEndCapture(s->stream, &g));
+        s->pair_launches_all = s->launches_all - la;
+        s->pair_launches_step = s->launches_step - ls;
+        s->launches_all = la;
+        s->launches_step = ls;
+        cudaError_t e = cudaGraphInstantiate(&s->pair_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        s->pair_graph_epoch = s->view_epoch;
+    }
+    CU(cudaGraphLaunch(s->pair_graph, s->stream));
+    s->launches_all += s->pair_launches_all;
+    s->launches_step += s->pair_launches_step;
+    return 0;
+}
+
 static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
@@ -1100,7 +1137,19 @@ static int enqueue_steps(sfb_sim* s, int n) {
     if (s->groups.empty() || s->timing) {
         if ((rc = enter_mode(s, 1))) return rc;
         if (!s->groups.empty() && s->d.track) s->full_resync = 1;  // the whole-handle view does not log per group
-        for (int i = 0; i < n; ++i) {
+        int i = 0;
+        if (!s->timing && n >= 4 && s->stream == s->own_stream) {
+            if ((rc = derive_if_dirty(s))) return rc;
+            sync_group_views(s);
+            if (s->parity == 1) {  // the graph starts at parity 0
+                if ((rc = enqueue_sweep(s))) return rc;
+                if ((rc = enqueue_eval(s))) return rc;
+                i = 1;
+            }
+            for (; i + 1 < n; i += 2)
+                if ((rc = run_pair_graph(s))) return rc;
+        }
+        for (; i < n; ++i) {
             if ((rc = enqueue_sweep(s))) return rc;
             if ((rc = enqueue_eval(s))) return rc;
         }
