@@ -691,7 +691,13 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         }
         CU(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
         const long long need = (v.n_units + SWEEP_WARPS - 1) / SWEEP_WARPS;
-        gr.sweep_blocks = (int)std::min<long long>(need, (long long)sweep_per_sm * s->n_sm);
+        // The TMA sweep would fit four blocks per SM, but their rings would take all of the SM's
+        // shared memory and keep the k_rows / k_eval blocks of the other env groups out.  Two blocks
+        // (8 warps x 3 boxes = 104 KB in flight per SM) already stream at full HBM speed and leave
+        // room for them to co-reside: 0.764 -> 0.652 ms per step at the target.
+        int per_sm = (s->use_tma && G > 1) ? std::min(sweep_per_sm, 2) : sweep_per_sm;  // one group: nothing to co-reside with
+        if (const char* e = getenv("SFB_SWEEP_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(sweep_per_sm, atoi(e)));
+        gr.sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
         return 0;
