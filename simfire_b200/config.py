@@ -15,6 +15,7 @@ CFD) are outside the hot-path scope and ra
 from __future__ import annotations
 
 import re
+import warnings
 from dataclasses import dataclass, field
 from datetime import timedelta
 from math import exp
@@ -111,13 +112,22 @@ class _ArrayLayer:
 
 
 @dataclass
+class FunctionSpec:
+    """Name + keyword arguments of a functional layer generator (the reference keeps the
+    callable too; `.name` and `.kwargs` are what FireSimulation.get_seeds reads)."""
+
+    name: str
+    kwargs: Dict[str, Any]
+
+
+@dataclass
 class TerrainConfig:
     topography_type: str
     topography_layer: _ArrayLayer  # .data: (H, W, 1) elevations in ft
     fuel_type: str
     fuel_layer: _ArrayLayer  # .data: (H, W, 1) object array of Fuel
-    topography_function: Optional[Dict[str, Any]] = None
-    fuel_function: Optional[Dict[str, Any]] = None
+    topography_function: Optional[FunctionSpec] = None
+    fuel_function: Optional[FunctionSpec] = None
 
 
 @dataclass
@@ -137,8 +147,8 @@ class EnvironmentConfig:
 class WindConfig:
     speed: np.ndarray  # ft/min, (H, W) float64 (config.py:943-944)
     direction: np.ndarray  # degrees clockwise from north
-    speed_function: Optional[Dict[str, Any]] = None
-    direction_function: Optional[Dict[str, Any]] = None
+    speed_function: Optional[FunctionSpec] = None
+    direction_function: Optional[FunctionSpec] = None
 
 
 class Config:
@@ -203,24 +213,28 @@ class Config:
         fuels = np.empty((H, W), dtype=object)
         fuels.fill(the_fuel)
         return TerrainConfig("functional", _ArrayLayer(elev[..., None], fn), "functional",
-                             _ArrayLayer(fuels[..., None], ffn), {"name": fn, "kwargs": kwargs},
-                             {"name": ffn, "kwargs": fkw})  # fmt: skip
+                             _ArrayLayer(fuels[..., None], ffn), FunctionSpec(fn, kwargs),
+                             FunctionSpec(ffn, fkw))  # fmt: skip
 
-    def _load_fire(self) -> FireConfig:
+    def _load_fire(self, pos: Optional[Tuple[int, int]] = None) -> FireConfig:
+        """config.py:775-827"""
         f = self.yaml_data["fire"]
         max_dur, diag = int(f["max_fire_duration"]), bool(f["diagonal_spread"])
         kind = f["fire_initial_position"]["type"]
         if kind == "static":
-            pos = f["fire_initial_position"]["static"]["position"]
-            if isinstance(pos, str):
-                pos = pos[1:-1].split(",")
-            if len(pos) > 2:
-                raise ConfigError("`fire_initial_position` should only be a Tuple of length 2")
+            if pos is None:
+                pos = f["fire_initial_position"]["static"]["position"]
+                if isinstance(pos, str):
+                    pos = pos[1:-1].split(",")
+                if len(pos) > 2:
+                    raise ConfigError("`fire_initial_position` should only be a Tuple of length 2")
             return FireConfig((int(pos[0]), int(pos[1])), diag, max_dur)
         if kind == "random":
+            if pos is not None:
+                warnings.warn("`pos` is specified, but the initialization type is `random`. Ignoring `pos`.")
             seed = f["fire_initial_position"]["random"]["seed"]
             rng = np.random.default_rng(seed)  # config.py:808-812: x first, then y
-            H, W = self.area.screen_size
+            H, W = self.yaml_data["area"]["screen_size"]
             pos_x = int(rng.integers(W, dtype=int))
             pos_y = int(rng.integers(H, dtype=int))
             return FireConfig((pos_x, pos_y), diag, max_dur, seed)
@@ -234,7 +248,7 @@ class Config:
         shape = self.area.screen_size
         speed = np.full(shape, mph_to_ftpm(w["simple"]["speed"])).astype(np.float64)
         direction = np.full(shape, w["simple"]["direction"]).astype(np.float64)
-        return WindConfig(speed, direction)
+        return WindConfig(speed, direction)  # `simple` wind carries no function spec (config.py:864-865)
 
     # -- array entry point ------------------------------------------------------------------
     @classmethod
@@ -260,10 +274,60 @@ class Config:
             fire=FireConfig(tuple(int(v) for v in fire_initial_position), diagonal_spread, max_fire_duration),
             environment=EnvironmentConfig(moisture), wind=WindConfig(speed, direction),
         )  # fmt: skip
-        return cls(_sections=sections)
+        cfg = cls(_sections=sections)
+        # enough YAML for reset_fire() to work the way it does on a file-backed Config
+        cfg.yaml_data = {
+            "area": {"screen_size": [H, W], "pixel_scale": pixel_scale},
+            "fire": {"fire_initial_position": {"type": "static", "static": {"position": tuple(sections["fire"].fire_initial_position)},
+                                               "random": {"seed": None}},
+                     "max_fire_duration": max_fire_duration, "diagonal_spread": diagonal_spread},
+        }  # fmt: skip
+        return cfg
 
-    def reset_fire(self, pos: Optional[Tuple[int, int]] = None) -> None:
-        """config.py:reset_fire -- move the ignition point (static type only)."""
-        if pos is not None:
-            self.fire = FireConfig((int(pos[0]), int(pos[1])), self.fire.diagonal_spread,
-                                   self.fire.max_fire_duration, self.fire.seed)  # fmt: skip
+    # -- mutation between episodes (config.py:975-1133) -------------------------------------
+    def reset_terrain(self, topography_seed: Optional[int] = None, topography_type: Optional[str] = None,
+                      fuel_seed: Optional[int] = None, fuel_type: Optional[str] = None,
+                      location: Optional[Tuple[float, float]] = None) -> None:  # fmt: skip
+        """Rewrite the functional seeds / layer types in the YAML data and rebuild the terrain
+        (config.py:975-1046).  Array-backed configs have nothing to regenerate from."""
+        if "terrain" not in self.yaml_data:
+            raise ConfigError("reset_terrain: this Config was built from arrays; build a new one with from_arrays")
+        if location is not None:
+            raise ConfigError("reset_terrain(location=...): operational (LANDFIRE) layers are not built here")
+        t = self.yaml_data["terrain"]
+        if topography_seed is not None and self.terrain.topography_function is not None:
+            # KeyError for 'flat', which has no block in the YAML -- as in the reference (config.py:1010)
+            t["topography"]["functional"][self.terrain.topography_function.name]["seed"] = topography_seed
+        if fuel_seed is not None and self.terrain.fuel_function is not None:
+            t["fuel"]["functional"][self.terrain.fuel_function.name]["seed"] = fuel_seed
+        if topography_type is not None:
+            t["topography"]["type"] = topography_type
+        if fuel_type is not None:
+            t["fuel"]["type"] = fuel_type
+        self.area = AreaConfig(**self.yaml_data["area"])
+        self.terrain = self._load_terrain()
+
+    def reset_wind(self, speed_seed: Optional[int] = None, direction_seed: Optional[int] = None) -> None:
+        """config.py:1048-1086.  `simple` wind has no seed (speed_function is None), so the seeds
+        are ignored exactly as the reference ignores them and the same field is reloaded."""
+        if "wind" not in self.yaml_data:
+            raise ConfigError("reset_wind: this Config was built from arrays; build a new one with from_arrays")
+        self.wind = self._load_wind()
+
+    def reset_fire(self, seed: Optional[int] = None, pos: Optional[Tuple[int, int]] = None) -> None:
+        """config.py:1088-1133: `seed` re-draws a `random` start, `pos` moves a `static` one; the
+        other combination is ignored with a warning, both or neither is a ValueError."""
+        kind = self.yaml_data["fire"]["fire_initial_position"]["type"]
+        if seed is None and pos is None:
+            raise ValueError("Both `seed` and `pos` cannot be None")
+        if seed is not None and pos is not None:
+            raise ValueError("Both `seed` and `pos` cannot be specified together")
+        key, value = ("seed", seed) if seed is not None else ("position", pos)
+        section = self.yaml_data["fire"]["fire_initial_position"][kind]
+        if (kind == "random") != (key == "seed"):
+            # the reference stores the value, then _load_fire ignores it for this type
+            warnings.warn(f"Trying to set a {key} for fire initial position type ({kind}), which does not "
+                          f"support the use of a {key}. The {key} value will be ignored.")  # fmt: skip
+            return
+        section[key] = value
+        self.fire = self._load_fire(pos=pos)

@@ -184,10 +184,84 @@ class FireSimulation:
         self.active = self.fire_status == GameStatus.RUNNING
         return self.fire_map, self.active
 
-    # -- config mutation helpers the harness uses -------------------------------------------------------
+    # -- config mutation helpers the harness uses (simulation.py:574-829); like the reference they
+    # only rewrite `self.config`: the change takes effect at the next reset() ----------------------------
     def set_fire_initial_position(self, pos: Tuple[int, int]) -> None:
-        self.config.reset_fire(pos)
-        self.reset()
+        self.config.reset_fire(pos=pos)
+
+    def get_seeds(self) -> Dict[str, Optional[int]]:
+        """Seeds that exist for the configured layers; None-valued ones are left out (simulation.py:574-597)."""
+        seeds = {"elevation": self._get_topography_seed(), "fuel": self._get_fuel_seed(),
+                 "wind_speed": self._function_seed(self.config.wind.speed_function),
+                 "wind_direction": self._function_seed(self.config.wind.direction_function),
+                 "fire_initial_position": self.config.fire.seed}  # fmt: skip
+        return {k: v for k, v in seeds.items() if v is not None}
+
+    @staticmethod
+    def _function_seed(fn) -> Optional[int]:
+        return fn.kwargs["seed"] if fn is not None and fn.name == "perlin" else None
+
+    def _get_topography_seed(self) -> Optional[int]:
+        t = self.config.terrain
+        if t.topography_type != "functional":
+            return None  # array-backed layers: nothing to re-seed
+        if t.topography_function is None:
+            raise RuntimeError("The topography type is set as functional, but "
+                               "self.config.terrain.topography_function is not set")  # fmt: skip
+        if t.topography_function.name == "perlin":
+            return t.topography_function.kwargs["seed"]
+        if t.topography_function.name in ("flat", "gaussian"):  # the reference rejects 'gaussian' here (:617-622)
+            return None
+        raise RuntimeError(f"The topography function name {t.topography_function.name} is not valid")
+
+    def _get_fuel_seed(self) -> Optional[int]:
+        t = self.config.terrain
+        if t.fuel_type != "functional":
+            return None
+        if t.fuel_function is None:
+            raise RuntimeError("The fuel type is set as functional, but self.config.terrain.fuel_function is not set")
+        if t.fuel_function.name == "chaparral":
+            return t.fuel_function.kwargs["seed"]
+        raise RuntimeError(f"The fuel function name {t.fuel_function.name} is not valid")
+
+    def set_seeds(self, seeds: Dict[str, int]) -> bool:
+        """simulation.py:713-759: every recognised key is applied; any unknown key makes the
+        call report failure (after the known ones were applied, as in the reference)."""
+        success = False
+        if "elevation" in seeds:
+            self.config.reset_terrain(topography_seed=seeds["elevation"])
+            success = True
+        if "fuel" in seeds:
+            self.config.reset_terrain(fuel_seed=seeds["fuel"])
+            success = True
+        if "wind_speed" in seeds or "wind_direction" in seeds:
+            self.config.reset_wind(speed_seed=seeds.get("wind_speed"), direction_seed=seeds.get("wind_direction"))
+            success = True
+        if "fire_initial_position" in seeds:
+            self.config.reset_fire(seeds["fire_initial_position"])
+        valid_keys = list(self.get_seeds().keys())
+        for key in seeds:
+            if key not in valid_keys:
+                warnings.warn("No valid keys in the seeds dictionary were given to the set_seeds method. No seeds "
+                              f"will be changed. Valid keys are: {valid_keys}")  # fmt: skip
+                success = False
+        return success
+
+    def get_layer_types(self) -> Dict[str, str]:
+        return {"elevation": self.config.terrain.topography_type, "fuel": self.config.terrain.fuel_type}
+
+    def set_layer_types(self, types: Dict[str, str]) -> bool:
+        """simulation.py:784-829.  Only 'functional' layers are generated here; asking for
+        'operational' raises ConfigError from Config.reset_terrain (LANDFIRE ingest is out of scope)."""
+        valid_keys = list(self.get_layer_types().keys())
+        bad = [k for k in types if k not in valid_keys]
+        if bad or not types:
+            if bad:
+                warnings.warn("No valid keys in the types dictionary were given to the set_data_types method. No "
+                              f"data types will be changed. Valid keys are: {valid_keys}")  # fmt: skip
+            return False
+        self.config.reset_terrain(topography_type=types.get("elevation"), fuel_type=types.get("fuel"))
+        return True
 
     def rendering(self) -> bool:
         return False
@@ -210,6 +284,7 @@ class BatchedFireSimulation:
         self._planes, self._elevations = _static_planes(config)
         self._mirror: Optional[np.ndarray] = None
         self._engine.set_static(self._planes)
+        self._engine.set_elevation(self._elevations)  # slopes on the device (fire.py:436-449)
         pos = initial_positions if initial_positions is not None else [config.fire.fire_initial_position] * self.num_envs
         self._engine.reset(pos)
         H, W = config.area.screen_size

@@ -219,27 +219,71 @@ def test_load_mitigation_and_device_view():
     sim.close()
 
 
-def test_batched_simulation_matches_single_envs():
+@pytest.mark.parametrize("name,starts", [("flat64", [(20, 24), (40, 10), (5, 50)]),
+                                         ("gauss48", [(20, 24), (40, 10), (5, 40)])])
+def test_batched_simulation_matches_single_envs(name, starts):
+    """Also guards the slope planes of the batched class (gauss48 is not flat)."""
     from simfire_b200.config import Config
     from simfire_b200.simulation import BatchedFireSimulation, FireSimulation
 
-    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    z = np.load(f"{GOLDEN}/api_sequence_{name}.npz")
     y = yaml.safe_load(str(z["config_yaml"]))
-    starts = [(20, 24), (40, 10), (5, 50)]
+    W = y["area"]["screen_size"][1]
     batch = BatchedFireSimulation(Config(config_dict=y), 3, initial_positions=starts)
-    batch.update_mitigation([(e, x, 30, 3) for e in range(3) for x in range(0, 64)] + [(1, 2, 2, 9)])
+    batch.update_mitigation([(e, x, 30, 3) for e in range(3) for x in range(0, W)] + [(1, 2, 2, 9)])
     maps, active = batch.run(25)
     for e, pos in enumerate(starts):
         cfg = Config(config_dict=yaml.safe_load(str(z["config_yaml"])))
-        cfg.reset_fire(pos)
+        cfg.reset_fire(pos=pos)
         single = FireSimulation(cfg)
-        single.update_mitigation([(x, 30, 3) for x in range(0, 64)])
+        single.update_mitigation([(x, 30, 3) for x in range(0, W)])
         fm, act = single.run(25)
         assert np.array_equal(maps[e], fm), e
         assert bool(active[e]) == act
         assert batch.elapsed_time[e] == single.elapsed_time and batch.elapsed_steps[e] == single.elapsed_steps
         single.close()
     batch.close()
+
+
+def test_seed_and_layer_type_wrappers_match_reference():
+    """get_seeds / set_seeds / get_layer_types / set_fire_initial_position (simulation.py:574-829)
+    against what the reference FireSimulation returned (tests/golden/gen_config_golden.py)."""
+    import copy
+    import json
+
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    with open(f"{GOLDEN}/config_resets.json") as f:
+        g = json.load(f)
+    sim = FireSimulation(Config(config_dict=copy.deepcopy(g["config_dict"])))
+    assert sim.get_seeds() == g["sim_get_seeds"]
+    assert sim.get_layer_types() == g["sim_layer_types"]
+    assert sim.set_seeds({"fuel": 42}) is g["sim_set_seeds_fuel"]
+    assert sim.get_seeds() == g["sim_get_seeds_after"]
+    with pytest.warns(UserWarning, match="No valid keys"):
+        assert sim.set_seeds({"fuel": 43, "bogus": 1}) is g["sim_set_seeds_bad"]
+    assert sim.get_seeds() == g["sim_get_seeds_after_bad"]  # the valid key was applied all the same
+    with pytest.raises(KeyError):
+        sim.set_seeds({"elevation": 5})
+    with pytest.warns(UserWarning, match="No valid keys"):
+        assert sim.set_layer_types({"bogus": "functional"}) is False
+    assert sim.set_layer_types({"elevation": "functional", "fuel": "functional"}) is True
+
+    def bbox(fm):
+        ys, xs = np.nonzero(fm == 1)
+        return [int(xs.min()), int(xs.max()), int(ys.min()), int(ys.max())]
+
+    sim.set_fire_initial_position((40, 41))
+    fm, _ = sim.run(1)  # config changes wait for the next reset()
+    assert bbox(fm) == g["burning_bbox_before_reset"]
+    sim.reset()
+    fm, _ = sim.run(1)
+    assert [sim.elapsed_time, sim.elapsed_steps] == g["elapsed_after_reset_run1"]
+    attr = sim.get_attribute_data()
+    assert [float(attr["w_0"][0, 0]), int(attr["sigma"][0, 0])] == g["fuel_after_reset"]
+    assert bbox(fm) == g["burning_bbox_after_move"]
+    sim.close()
 
 
 def test_device_slopes_match_numpy_gradient():

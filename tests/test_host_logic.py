@@ -95,3 +95,75 @@ def test_compute_slopes_matches_oracle_helper():
     e = np.random.default_rng(0).uniform(0, 500, (17, 23))
     for a, b in zip(compute_slopes(e, 30.0), ref(e, 30.0)):
         assert np.array_equal(a, b)
+
+
+def _resets():
+    import json
+
+    with open(f"{GOLDEN}/config_resets.json") as f:
+        return json.load(f)
+
+
+def _fuel_of(cfg):
+    f = cfg.terrain.fuel_layer.data[0, 0, 0]
+    return [f.w_0, f.delta, f.M_x, f.sigma]
+
+
+def test_config_reset_fire_matches_reference():
+    """Config.reset_fire (config.py:1088-1133) against values recorded from the reference."""
+    import copy
+
+    from simfire_b200.config import Config
+
+    g = _resets()
+    c = Config(config_dict=copy.deepcopy(g["config_dict"]))
+    c.reset_fire(pos=(3, 9))
+    assert list(c.fire.fire_initial_position) == g["static_after_pos"]
+    with pytest.warns(UserWarning, match="does not support"):
+        c.reset_fire(77)  # a seed means nothing to a static start
+    assert list(c.fire.fire_initial_position) == g["static_after_seed"] and c.fire.seed == g["static_seed_attr"]
+    with pytest.raises(ValueError):
+        c.reset_fire()
+    with pytest.raises(ValueError):
+        c.reset_fire(1, (2, 3))
+
+    y = copy.deepcopy(g["config_dict"])
+    y["fire"]["fire_initial_position"]["type"] = "random"
+    y["area"]["screen_size"] = [48, 48]
+    c = Config(config_dict=y)
+    assert list(c.fire.fire_initial_position) + [c.fire.seed] == g["random_initial"]
+    for seed, want in sorted(g["random_draws_48x48"].items(), key=lambda kv: int(kv[0])):
+        c.reset_fire(int(seed))
+        assert list(c.fire.fire_initial_position) + [c.fire.seed] == want
+    with pytest.warns(UserWarning):
+        c.reset_fire(pos=(1, 2))
+    assert list(c.fire.fire_initial_position) == g["random_after_pos"]
+
+
+def test_config_reset_terrain_and_wind_match_reference():
+    import copy
+
+    from simfire_b200.config import Config, ConfigError
+
+    g = _resets()
+    c = Config(config_dict=copy.deepcopy(g["config_dict"]))
+    assert _fuel_of(c) == g["fuel_initial"]
+    for seed, want in g["fuel_by_seed"].items():
+        c.reset_terrain(fuel_seed=int(seed))
+        assert _fuel_of(c) == want
+        assert c.terrain.fuel_function.kwargs["seed"] == int(seed)
+    c.reset_wind(speed_seed=3, direction_seed=4)
+    assert [c.wind.speed[0, 0], c.wind.direction[0, 0]] == g["wind_after_reset"]
+    assert c.wind.speed_function is None and c.wind.direction_function is None
+    with pytest.raises(KeyError):  # the reference fails the same way: 'flat' has no YAML block to hold a seed
+        c.reset_terrain(topography_seed=5)
+    with pytest.raises(ConfigError):
+        c.reset_terrain(fuel_type="operational")
+    arr = Config.from_arrays(fuels=np.zeros((8, 8, 4)), elevations=np.zeros((8, 8)), wind_speed=1.0, wind_direction=0.0,
+                             pixel_scale=30, fire_initial_position=(1, 1))  # fmt: skip
+    arr.reset_fire(pos=(5, 6))
+    assert arr.fire.fire_initial_position == (5, 6)
+    with pytest.raises(ConfigError):
+        arr.reset_terrain(fuel_seed=1)
+    with pytest.raises(ConfigError):
+        arr.reset_wind()
