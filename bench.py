@@ -390,24 +390,42 @@ def gpu_arm(args):
     rng = np.random.default_rng(5 + rank)
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
 
-    def e2e_step():
-        pts_np[:, 0] = np.arange(E)
-        pts_np[:, 1] = rng.integers(0, W, E)
-        pts_np[:, 2] = rng.integers(0, H, E)
-        pts_np[:, 3] = 3  # BurnStatus.FIRELINE
-        eng.apply_points(pts_np)          # host -> device
-        eng.step(1, sync=False)
-        return eng.sync_fire_maps(maps_np)  # device -> host: changed cells only, patched into the mirror
+    # the caller's actions: one control-line point per env per step, (env, x, y, kind) rows
+    n_extra = 8
+    actions = np.empty((e2e_steps + 2 + n_extra, E, 4), dtype=np.int32)
+    actions[:, :, 0] = np.arange(E)
+    actions[:, :, 1] = rng.integers(0, W, actions.shape[:2])
+    actions[:, :, 2] = rng.integers(0, H, actions.shape[:2])
+    actions[:, :, 3] = 3  # BurnStatus.FIRELINE
+    e2e_calls = [0.0, 0.0, 0.0]
 
-    e2e_step()  # first call downloads every map once
-    e2e_step()
+    def e2e_step(i, timed=False):
+        ta = time.perf_counter()
+        pts_np[...] = actions[i]
+        eng.apply_points(pts_np)          # host -> device
+        tb = time.perf_counter()
+        eng.step(1, sync=False)
+        tc = time.perf_counter()
+        n = eng.sync_fire_maps(maps_np)   # device -> host: changed cells only, patched into the mirror
+        if timed:
+            td = time.perf_counter()
+            e2e_calls[0] += tb - ta
+            e2e_calls[1] += tc - tb
+            e2e_calls[2] += td - tc
+        return n
+
+    e2e_step(0)  # first call downloads every map once
+    e2e_step(1)
     barrier()
     t0 = time.perf_counter()
     e2e_changes = 0
-    for _ in range(e2e_steps):
-        e2e_changes += max(0, e2e_step())
+    for i in range(e2e_steps):
+        e2e_changes += max(0, e2e_step(2 + i))
     barrier()
     e2e_s = time.perf_counter() - t0
+    for i in range(n_extra):  # where a step's wall time goes, call by call (outside the timed region)
+        e2e_step(2 + e2e_steps + i, timed=True)
+    e2e_calls = [round(1e3 * v / n_extra, 4) for v in e2e_calls]
     # the patched mirror must equal a full download (checked outside the timed region)
     e2e_ok = bool(np.array_equal(maps_np[: min(E, 16)], eng.fire_map(0, min(E, 16))))
     e2e_value = cells_per_step * e2e_steps / ctx.max(e2e_s)
@@ -453,6 +471,7 @@ def gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes) * world,
                 "d2h_bytes_per_step": (int(8 * e2e_changes / e2e_steps) + 12 if not args.no_track else int(maps_np.nbytes)) * world,
                 "steps": e2e_steps, "host_mirror_bytes": int(maps_np.nbytes) * world, "mirror_matches_download": e2e_ok,
+                "ms_per_call": {"apply_points": e2e_calls[0], "step_enqueue": e2e_calls[1], "sync_fire_maps": e2e_calls[2]},
                 "api": "FireEngine.apply_points (pinned H2D) + step + sync_fire_maps: every env's int8 fire_map is "
                        "brought up to date in host memory each step" + (" by patching the cells the device logged "
                        "as changed (8 B each)" if not args.no_track else " by a full download")},

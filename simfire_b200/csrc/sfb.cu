@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -45,6 +46,9 @@ static int fail(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------
 // host worker pool (patching the host mirror from the change log)
 // ---------------------------------------------------------------------------------------
+// Workers spin for a short while after a job before they go to sleep on the condition variable:
+// sfb_sync_fire_maps issues one job per env group per step, a fraction of a millisecond apart,
+// and a futex wake-up per job would cost more than the patching itself.
 class HostPool {
   public:
     explicit HostPool(unsigned n) : n_(std::max(1u, n)) {
@@ -53,8 +57,8 @@ class HostPool {
     ~HostPool() {
         {
             std::lock_guard<std::mutex> g(m_);
-            stop_ = true;
-            ++gen_;
+            stop_.store(true, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto& w : workers_) w.join();
@@ -62,46 +66,63 @@ class HostPool {
     unsigned size() const { return n_; }
     // runs fn(t) for t in [0, size()) and returns when all are done
     void run(const std::function<void(unsigned)>& fn) {
+        fn_ = &fn;
+        pending_.store(n_ - 1, std::memory_order_relaxed);
         {
-            std::lock_guard<std::mutex> g(m_);
-            fn_ = &fn;
-            pending_ = n_ - 1;
-            ++gen_;
+            std::lock_guard<std::mutex> g(m_);  // a worker about to sleep re-checks gen_ under this mutex
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         fn(0);
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return pending_ == 0; });
+        for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0;) relax(++spins);
         fn_ = nullptr;
+    }
+    // all size() threads of the running job meet here (call it the same number of times in each)
+    void barrier() {
+        const unsigned g = bar_gen_.load(std::memory_order_acquire);
+        if (bar_count_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+            bar_count_.store(0, std::memory_order_relaxed);
+            bar_gen_.fetch_add(1, std::memory_order_release);
+        } else {
+            for (unsigned spins = 0; bar_gen_.load(std::memory_order_acquire) == g;) relax(++spins);
+        }
     }
 
   private:
+    static void relax(unsigned spins) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFFu) == 0) std::this_thread::yield();  // more threads than cores: let the others run
+    }
     void loop(unsigned t) {
+        using clock = std::chrono::steady_clock;
         unsigned long long seen = 0;
         for (;;) {
-            const std::function<void(unsigned)>* fn;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                fn = fn_;
+            const auto idle_since = clock::now();
+            for (unsigned spins = 1; gen_.load(std::memory_order_acquire) == seen; ++spins) {
+                relax(spins);
+                if ((spins & 0x3FFu) == 0 && clock::now() - idle_since > std::chrono::microseconds(SPIN_US)) {
+                    std::unique_lock<std::mutex> l(m_);
+                    cv_.wait(l, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                    break;
+                }
             }
-            (*fn)(t);
-            {
-                std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0) done_.notify_one();
-            }
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_.load(std::memory_order_relaxed)) return;
+            (*fn_)(t);
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
+    static constexpr int SPIN_US = 1000;
     unsigned n_;
     std::vector<std::thread> workers_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
+    std::condition_variable cv_;
     const std::function<void(unsigned)>* fn_ = nullptr;
-    unsigned pending_ = 0;
-    unsigned long long gen_ = 0;
-    bool stop_ = false;
+    std::atomic<unsigned> pending_{0}, bar_count_{0}, bar_gen_{0};
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<bool> stop_{false};
 };
 
 // ---------------------------------------------------------------------------------------
@@ -168,6 +189,7 @@ struct sfb_sim {
     const int8_t* mirror;      // buffer the last sync wrote, nullptr = none valid
     int full_resync;           // something changed that the log does not describe
     unsigned long long* log_head;    // pinned: {count, overflow} of every log, read back each sync
+    int head_valid;                  // the step that ran last already copied every group's head into log_head
     unsigned long long* log_mapped[MAX_ENV_GROUPS];  // the change logs (mapped host memory)
     unsigned long long* log_counts;  // device: {count, overflow} x n_logs
     HostPool* pool;
@@ -176,6 +198,7 @@ struct sfb_sim {
 
 static int use(sfb_sim* s) {
     CU(cudaSetDevice(s->prm.device));
+    s->head_valid = 0;  // any call may append to the change logs; only a grouped step re-validates
     return 0;
 }
 
@@ -1179,10 +1202,18 @@ static int enqueue_steps(sfb_sim* s, int n) {
         par ^= 1;
     }
     s->parity = par;
-    for (auto& gr : s->groups) {
+    const bool heads = s->d.track && s->log_head && (int)s->groups.size() == s->d.n_logs;
+    for (size_t g = 0; g < s->groups.size(); ++g) {
+        auto& gr = s->groups[g];
+        // the group's {count, overflow} rides behind its last kernel, so that sfb_sync_fire_maps
+        // finds it in host memory as soon as the group's event has fired
+        if (heads)
+            CU(cudaMemcpyAsync(s->log_head + 2 * g, s->d.logs[g].count, 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, gr.last_stream));
         CU(cudaEventRecord(gr.done, gr.last_stream));
         CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
     }
+    s->head_valid = heads;
     return 0;
 }
 
@@ -1451,6 +1482,7 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
     const unsigned long long span = (total + T - 1) / T;  // cells per owner
     if (s->buckets.size() != (size_t)T * T) s->buckets.assign((size_t)T * T, {});
     s->pool->run([&](unsigned k) {
+        // pass 1: chunk k of the log -> buckets (k, owner)
         for (unsigned o = 0; o < T; ++o) s->buckets[(size_t)k * T + o].clear();
         const long long i0 = n * k / T, i1 = n * (k + 1) / T;
         for (long long i = i0; i < i1; ++i) {
@@ -1463,11 +1495,12 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
                 s->buckets[(size_t)k * T + std::min<unsigned>(T - 1, (unsigned)((idx - base) / span))].push_back(e);
             }
         }
-    });
-    s->pool->run([&](unsigned o) {
+        s->pool->barrier();
+        // pass 2: this thread owns cells [lo, hi)
+        const unsigned o = k;
         const unsigned long long lo = base + (unsigned long long)o * span, hi = std::min(base + total, lo + span);
-        for (unsigned k = 0; k < T; ++k)
-            for (const unsigned long long e : s->buckets[(size_t)k * T + o]) {
+        for (unsigned c = 0; c < T; ++c)
+            for (const unsigned long long e : s->buckets[(size_t)c * T + o]) {
                 const unsigned long long idx = e & 0xFFFFFFFFFFFFull;
                 const int st = (int)(e >> 48) & 7;
                 if (st == LOG_ENV_RESET) clear_env_part((long long)idx, lo, hi);
@@ -1483,6 +1516,7 @@ static double now_ms() {
 extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes) {
     if (!s || !mirror) return fail(SFB_ERR_INVALID, "sfb_sync_fire_maps: null argument");
     int rc;
+    const bool heads_ready = s->head_valid != 0;  // nothing ran since the grouped step that fetched them
     if ((rc = use(s))) return rc;
     DevParams& d = s->d;
     static const bool debug = getenv("SFB_DEBUG_TIMING") != nullptr;
@@ -1518,8 +1552,10 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
             CU(cudaEventSynchronize(s->groups[g].done));
             st = s->groups[g].last_stream ? s->groups[g].last_stream : s->groups[g].stream;
         }
-        CU(cudaMemcpyAsync(s->log_head + 2 * g, d.logs[g].count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (!(grouped && heads_ready)) {
+            CU(cudaMemcpyAsync(s->log_head + 2 * g, d.logs[g].count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         const unsigned long long cnt = s->log_head[2 * g];
         if ((s->log_head[2 * g + 1] & 0xFFFFFFFFull) != 0 || cnt > (unsigned long long)d.logs[g].cap) {
             overflow = true;
