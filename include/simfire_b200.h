@@ -156,7 +156,9 @@ int sfb_set_elevation(sfb_sim* sim, int32_t env, const double* elevations);
 int sfb_reset(sfb_sim* sim, const int32_t* envs, int32_t n, const int32_t* xy);
 
 /* ControlLineManager.update (mitigation.py:60-80) batched: points are (env, x, y, kind)
- * int32 quadruples, kind = BurnStatus value; fire_map[y, x] = kind unconditionally. */
+ * int32 quadruples, kind = BurnStatus value; fire_map[y, x] = kind unconditionally.
+ * `points` is copied before the call returns; the writes themselves are enqueued on the
+ * handle's stream, ahead of whatever is called next. */
 int sfb_apply_points(sfb_sim* sim, const int32_t* points, int64_t n);
 
 /* FireSimulation.load_mitigation (simulation.py:425-447) / the fire_map argument of

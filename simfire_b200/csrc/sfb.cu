@@ -177,6 +177,9 @@ struct sfb_sim {
     void* obs;            // int8 [E][H][W] observation buffer (sfb_fire_map_device)
     int32_t* small;       // device scratch for env lists / points
     size_t small_bytes;
+    int32_t* pts_host[2];    // pinned staging for sfb_apply_points: the caller's buffer is free again on return
+    cudaEvent_t pts_ev[2];   // ... without waiting for the device (the slot's previous copy is waited for instead)
+    int pts_slot;
     // accounting
     int64_t launches_all, launches_step;
     int64_t dev_bytes;
@@ -222,6 +225,8 @@ static int ensure_stage(sfb_sim* s, size_t bytes) {
     s->stage_bytes = bytes;
     return 0;
 }
+
+static constexpr size_t PTS_STAGE_BYTES = 64 << 10;
 
 static int ensure_small(sfb_sim* s, size_t bytes) {
     if (s->small_bytes >= bytes) return 0;
@@ -530,6 +535,10 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->stage);
     cudaFree(s->obs);
     cudaFree(s->small);
+    for (int i = 0; i < 2; ++i) {
+        if (s->pts_host[i]) cudaFreeHost(s->pts_host[i]);
+        if (s->pts_ev[i]) cudaEventDestroy(s->pts_ev[i]);
+    }
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : s->span)
@@ -948,8 +957,20 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     }
     int rc;
     if ((rc = use(s))) return rc;
-    if ((rc = ensure_small(s, (size_t)n * 4 * sizeof(int32_t)))) return rc;
-    CU(cudaMemcpyAsync(s->small, pts, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    const size_t bytes = (size_t)n * 4 * sizeof(int32_t);
+    if ((rc = ensure_small(s, bytes))) return rc;
+    const bool staged = bytes <= PTS_STAGE_BYTES;  // per-step mitigation points: no device round trip
+    if (staged) {
+        const int slot = s->pts_slot ^= 1;
+        if (!s->pts_host[slot]) {
+            CU(cudaMallocHost((void**)&s->pts_host[slot], PTS_STAGE_BYTES));
+            CU(cudaEventCreateWithFlags(&s->pts_ev[slot], cudaEventDisableTiming));
+        }
+        CU(cudaEventSynchronize(s->pts_ev[slot]));  // the copy that used this slot two calls ago
+        memcpy(s->pts_host[slot], pts, bytes);
+        pts = s->pts_host[slot];
+    }
+    CU(cudaMemcpyAsync(s->small, pts, bytes, cudaMemcpyHostToDevice, s->stream));
     // one launch per kind in BurnStatus order: FireSimulation.update_mitigation applies the
     // fireline, scratchline and wetline managers in that order (simulation.py:468-478), so
     // when two points name one cell the later kind wins, as it does there
@@ -959,7 +980,8 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
                  s->prm.slab_y0);
     }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s->stream));
+    if (staged) CU(cudaEventRecord(s->pts_ev[s->pts_slot], s->stream));
+    else CU(cudaStreamSynchronize(s->stream));  // `pts` is borrowed for the call only
     return 0;
 }
 
