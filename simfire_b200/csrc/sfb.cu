@@ -1,7 +1,14 @@
 // libsimfire_b200.so -- host side of the C ABI declared in include/simfire_b200.h.
 // Plain CUDA runtime; no torch, no CPU fallback: every entry point that computes launches
 // kernels on the handle's device and fails with SFB_ERR_CUDA if it cannot.
+#ifdef SFB_EMU
+// test-only build with g++ (tests/emu): the fiber emulator stands in for the CUDA runtime
+#include "cuda_emu.h"
+#define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), kernel, __VA_ARGS__)
+#else
 #include <cuda_runtime.h>
+#define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -486,8 +493,8 @@ __global__ void k_rate_of_spread(const int8_t* dir, const float* rec, SfbParticl
 // ---------------------------------------------------------------------------------------
 #define DISPATCH(s, KERNEL, grid, block, ...)                                              \
     do {                                                                                   \
-        if ((s)->cell_bytes == 1) KERNEL<uint8_t><<<(grid), (block), 0, (s)->stream>>>(__VA_ARGS__); \
-        else KERNEL<uint16_t><<<(grid), (block), 0, (s)->stream>>>(__VA_ARGS__);          \
+        if ((s)->cell_bytes == 1) SFB_LAUNCH(KERNEL<uint8_t>, (grid), (block), 0, (s)->stream, __VA_ARGS__); \
+        else SFB_LAUNCH(KERNEL<uint16_t>, (grid), (block), 0, (s)->stream, __VA_ARGS__);          \
         (s)->launches_all++;                                                               \
     } while (0)
 
@@ -849,7 +856,7 @@ static int set_static_range(sfb_sim* s, int env, int plane, const float* dev_src
         n = d.E;
     }
     const long long total = (long long)n * d.H * d.W;
-    k_set_static<<<cap_grid(s, total, 256), 256, 0, s->stream>>>(d, first, n, plane, dev_src);
+    SFB_LAUNCH(k_set_static, cap_grid(s, total, 256), 256, 0, s->stream, d, first, n, plane, dev_src);
     s->launches_all++;
     s->static_dirty = 1;
     CU(cudaGetLastError());
@@ -898,8 +905,7 @@ extern "C" int sfb_set_elevation(sfb_sim* s, int32_t env, const double* elevatio
     int first = env, n = 1;
     if (d.shared_static) { first = 0; n = 1; }
     else if (env < 0) { first = 0; n = d.E; }
-    k_slopes<<<cap_grid(s, (long long)n * d.H * d.W, 256), 256, 0, s->stream>>>(d, first, n, (const double*)s->stage,
-                                                                              s->prm.pixel_scale);
+    SFB_LAUNCH(k_slopes, cap_grid(s, (long long)n * d.H * d.W, 256), 256, 0, s->stream, d, first, n, (const double*)s->stage, s->prm.pixel_scale);
     s->launches_all++;
     s->static_dirty = 1;
     CU(cudaGetLastError());
@@ -930,7 +936,7 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (envs) CU(cudaMemcpyAsync(d_envs, envs, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (linear_bytes(s) && d.plane % 16 == 0) {
-        k_clear_envs_v16<<<cap_grid(s, (long long)n * (d.plane / 16), 256), 256, 0, s->stream>>>(d, (const int32_t*)d_envs, n, d.plane / 16);
+        SFB_LAUNCH(k_clear_envs_v16, cap_grid(s, (long long)n * (d.plane / 16), 256), 256, 0, s->stream, d, (const int32_t*)d_envs, n, d.plane / 16);
         s->launches_all++;
     } else {
         DISPATCH(s, k_clear_envs, cap_grid(s, (long long)n * d.plane, 256), 256, d, (const int32_t*)d_envs, n, 1);
@@ -999,8 +1005,7 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     if ((rc = ensure_stage(s, bytes))) return rc;
     CU(cudaMemcpyAsync(s->stage, maps, bytes, cudaMemcpyHostToDevice, s->stream));
     if (linear_bytes(s)) {
-        k_set_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>(
-            reinterpret_cast<uint4*>((uint8_t*)d.state + (size_t)env0 * d.plane), (const uint4*)s->stage, (long long)bytes / 16);
+        SFB_LAUNCH(k_set_map_v16, cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream,  reinterpret_cast<uint4*>((uint8_t*)d.state + (size_t)env0 * d.plane), (const uint4*)s->stage, (long long)bytes / 16);
         s->launches_all++;
     } else {
         DISPATCH(s, k_set_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (const int8_t*)s->stage);
@@ -1015,8 +1020,7 @@ static int download_maps(sfb_sim* s, int env0, int n, int8_t* out) {
     int rc;
     if ((rc = ensure_stage(s, bytes))) return rc;
     if (linear_bytes(s)) {
-        k_get_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>(
-            reinterpret_cast<const uint4*>((const uint8_t*)d.state + (size_t)env0 * d.plane), (uint4*)s->stage, (long long)bytes / 16);
+        SFB_LAUNCH(k_get_map_v16, cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream,  reinterpret_cast<const uint4*>((const uint8_t*)d.state + (size_t)env0 * d.plane), (uint4*)s->stage, (long long)bytes / 16);
         s->launches_all++;
     } else {
         DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (int8_t*)s->stage);
@@ -1043,7 +1047,7 @@ static int derive_if_dirty(sfb_sim* s) {
     if (!s->static_dirty) return 0;
     const DevParams& d = s->d;
     const long long cells = d.shared_static ? d.plane : (long long)d.E * d.plane;
-    k_derive_static<<<cap_grid(s, cells, 128), 128, 0, s->stream>>>(d, cells);
+    SFB_LAUNCH(k_derive_static, cap_grid(s, cells, 128), 128, 0, s->stream, d, cells);
     s->launches_all++;
     s->static_dirty = 0;
     CU(cudaGetLastError());
@@ -1052,28 +1056,28 @@ static int derive_if_dirty(sfb_sim* s) {
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (s->use_tma) {
-        if (s->cell_bytes == 1) k_sweep_tma<uint8_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st>>>(gr.tmap, gr.d, par);
-        else k_sweep_tma<uint16_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st>>>(gr.tmap, gr.d, par);
+        if (s->cell_bytes == 1) SFB_LAUNCH(k_sweep_tma<uint8_t>, gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st, gr.tmap, gr.d, par);
+        else SFB_LAUNCH(k_sweep_tma<uint16_t>, gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st, gr.tmap, gr.d, par);
     } else {
-        if (s->cell_bytes == 1) k_sweep_ldg<uint8_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, 0, st>>>(gr.d, par);
-        else k_sweep_ldg<uint16_t><<<gr.sweep_blocks, SWEEP_WARPS * 32, 0, st>>>(gr.d, par);
+        if (s->cell_bytes == 1) SFB_LAUNCH(k_sweep_ldg<uint8_t>, gr.sweep_blocks, SWEEP_WARPS * 32, 0, st, gr.d, par);
+        else SFB_LAUNCH(k_sweep_ldg<uint16_t>, gr.sweep_blocks, SWEEP_WARPS * 32, 0, st, gr.d, par);
     }
     s->launches_all++;
     s->launches_step++;
 }
 static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
-    if (s->cell_bytes == 1) k_rows<uint8_t><<<gr.rows_blocks, ROWS_WARPS * 32, 0, st>>>(gr.d, par);
-    else k_rows<uint16_t><<<gr.rows_blocks, ROWS_WARPS * 32, 0, st>>>(gr.d, par);
+    if (s->cell_bytes == 1) SFB_LAUNCH(k_rows<uint8_t>, gr.rows_blocks, ROWS_WARPS * 32, 0, st, gr.d, par);
+    else SFB_LAUNCH(k_rows<uint16_t>, gr.rows_blocks, ROWS_WARPS * 32, 0, st, gr.d, par);
     s->launches_all++;
     s->launches_step++;
 }
 static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (gr.d.keep_ros) {
-        k_clear_ros<<<cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st>>>(gr.d, par);
+        SFB_LAUNCH(k_clear_ros, cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st, gr.d, par);
         s->launches_all++;
     }
-    if (s->cell_bytes == 1) k_eval<uint8_t><<<s->n_sm * 8, 256, 0, st>>>(gr.d, par);
-    else k_eval<uint16_t><<<s->n_sm * 8, 256, 0, st>>>(gr.d, par);
+    if (s->cell_bytes == 1) SFB_LAUNCH(k_eval<uint8_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
+    else SFB_LAUNCH(k_eval<uint16_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
     s->launches_all++;
     s->launches_step++;
 }
@@ -1300,9 +1304,9 @@ extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
     for (int i = 0; i < n_steps; ++i) {
         const uint32_t g = ++s->slab_step;
         if ((rc = enqueue_sweep(s))) return rc;
-        k_slab_exchange_flags<<<1, 32, 0, s->stream>>>(s->all.d, s->parity, g);
+        SFB_LAUNCH(k_slab_exchange_flags, 1, 32, 0, s->stream, s->all.d, s->parity, g);
         if ((rc = enqueue_eval(s))) return rc;
-        k_slab_step_done<<<1, 32, 0, s->stream>>>(s->all.d, g);
+        SFB_LAUNCH(k_slab_step_done, 1, 32, 0, s->stream, s->all.d, g);
         s->launches_all += 2;
     }
     CU(cudaGetLastError());
@@ -1653,8 +1657,7 @@ extern "C" int sfb_fire_map_device(sfb_sim* s, void** dev) {
     const size_t bytes = (size_t)s->d.E * s->d.H * s->d.W;
     if (!s->obs && (rc = dmalloc(s, (char**)&s->obs, bytes))) return rc;
     if (linear_bytes(s)) {
-        k_get_map_v16<<<cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream>>>((const uint4*)s->d.state, (uint4*)s->obs,
-                                                                                      (long long)bytes / 16);
+        SFB_LAUNCH(k_get_map_v16, cap_grid(s, (long long)bytes / 16, 256), 256, 0, s->stream, (const uint4*)s->d.state, (uint4*)s->obs, (long long)bytes / 16);
         s->launches_all++;
     } else
         DISPATCH(s, k_get_map, cap_grid(s, (long long)bytes, 256), 256, s->d, 0, s->d.E, (int8_t*)s->obs);
@@ -1769,7 +1772,7 @@ extern "C" int sfb_rate_of_spread(int32_t device, const int8_t* dir, const float
         CU(cudaMemcpy(d_dir, dir, (size_t)n, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d_rec, rec, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice));
         SfbParticle fp{particle[0], particle[1], particle[2], particle[3], particle[4]};
-        k_rate_of_spread<<<nblocks(n, 128), 128>>>(d_dir, d_rec, fp, (long long)n, d_out);
+        SFB_LAUNCH(k_rate_of_spread, nblocks(n, 128), 128, 0, nullptr, d_dir, d_rec, fp, (long long)n, d_out);
         CU(cudaGetLastError());
         CU(cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
         return 0;

@@ -33,8 +33,13 @@
 // (fire.py:633) is recovered as (t - 1 - ign) mod M, so the code never has to be
 // rewritten while the sprite burns, and a cell's byte changes exactly twice in its life.
 #pragma once
+#ifdef SFB_EMU
+// test-only build of these sources with g++ (tests/emu): cuda_emu.h stands in for the CUDA headers
+#include "cuda_emu.h"
+#else
 #include <cuda.h>
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "sfb_rothermel.cuh"
@@ -513,6 +518,16 @@ constexpr int TMA_WARP_SMEM = TMA_RING_ROWS * TMA_ROW_BYTES + WQ_CAP * 8 + 128; 
 static_assert(TMA_WARP_SMEM % 128 == 0 && TMA_BOX_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
 constexpr int TMA_BLOCK_SMEM = SWEEP_WARPS * TMA_WARP_SMEM + 128;              // + alignment slack
 
+#ifdef SFB_EMU
+using emu::smem_u32;
+using emu::mbar_init;
+using emu::mbar_init_fence;
+using emu::mbar_expect_tx;
+using emu::mbar_wait;
+using emu::tma_load_3d;
+#define SFB_DYNAMIC_SMEM(name) unsigned char* const name = emu::st().dyn_smem
+#else
+#define SFB_DYNAMIC_SMEM(name) extern __shared__ unsigned char name[]
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -538,6 +553,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
         ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+#endif
 
 // The tensor map describes the state plane as uint32 [E][H][pitch_bytes / 4]; a box is
 // 136 x 8 x 1 elements = 8 rows of 544 bytes starting 16 bytes left of the strip.
@@ -550,7 +570,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
     constexpr uint32_t CELL_ALL = sizeof(CellT) == 1 ? 0xFFu : 0xFFFFu;
     static_assert(RS * sizeof(CellT) == TMA_ROW_BYTES, "row bytes");
     static_assert(B <= 16, "halo ballot uses lanes 0 .. 2B-1");
-    extern __shared__ unsigned char smem_raw[];
+    SFB_DYNAMIC_SMEM(smem_raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127) + warp * TMA_WARP_SMEM;
@@ -562,8 +582,7 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
 
     if (lane == 0) {
         for (int s = 0; s < TMA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     __syncwarp();
     uint32_t boxes_done = 0;  // boxes consumed by this warp so far: fixes ring slot and mbarrier phase
