@@ -4,7 +4,7 @@
 #ifdef SFB_EMU
 // test-only build with g++ (tests/emu): the fiber emulator stands in for the CUDA runtime
 #include "cuda_emu.h"
-#define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), kernel, __VA_ARGS__)
+#define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(#kernel, (grid), (block), (smem), kernel, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>
 #define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)

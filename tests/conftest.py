@@ -21,8 +21,8 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:  # pragma: no cover
         has_gpu = False
-    if has_gpu:
-        return
+    if has_gpu or os.environ.get("SFB_EMULATED") == "1":
+        return  # (SFB_EMULATED: tests/test_emu_parity.py re-runs GPU tests against the fiber emulator build)
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
         if "gpu" in item.keywords:

@@ -1,0 +1,31 @@
+"""TEST-ONLY: builds tests/emu/_build/libsfb_emu.so = the product sources (C ABI, host glue,
+kernels) compiled with g++ against the fiber emulator in cuda_emu.h.  The result is never
+loaded by the package; tests point SFB_LIB at it in a subprocess (tests/test_emu_parity.py)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build", "libsfb_emu.so")
+DEPS = [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "emu_lib.cpp")] + [
+    os.path.join(ROOT, "simfire_b200", "csrc", f) for f in ("sfb.cu", "sfb_kernels.cuh", "sfb_rothermel.cuh")
+] + [os.path.join(ROOT, "include", "simfire_b200.h")]
+
+
+def build(force: bool = False) -> str:
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    # -ffp-contract=off mirrors nvcc --fmad=false (the Rothermel arithmetic rounds after every operation)
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, "-o", OUT,
+           os.path.join(HERE, "emu_lib.cpp"), "-lpthread"]  # fmt: skip
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -90,6 +90,7 @@ struct Warp {
     unsigned gen = 0;
     uint32_t alive_mask = 0;
     uint64_t slot[2][32];
+    uint32_t vote[2] = {0, 0};  // ballot of the lanes that took part, fixed when the collective completes
     int tag[2] = {0, 0};
 };
 
@@ -130,20 +131,20 @@ void warp_sync(int tag);
 void block_sync();
 uint64_t exchange(uint64_t v, int src_lane, int tag);
 uint32_t ballot(bool pred, int tag);
-void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void run_grid(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 
 // kernel launch: arguments are evaluated and copied NOW (as cudaLaunchKernel does), the call is
 // executed now or, during stream capture, recorded
 template <class... P, class... A>
-static inline void launch(dim3 grid, dim3 block, size_t smem, void (*kernel)(P...), A&&... a) {
+static inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, void (*kernel)(P...), A&&... a) {
     std::tuple<typename std::decay<P>::type...> args(std::forward<A>(a)...);
     std::function<void()> body = [kernel, args]() { std::apply(kernel, args); };
     State& s = st();
     if (s.capturing) {
-        s.capture_into->push_back([grid, block, smem, body]() { run_grid(grid, block, smem, body); });
+        s.capture_into->push_back([name, grid, block, smem, body]() { run_grid(name, grid, block, smem, body); });
         return;
     }
-    run_grid(grid, block, smem, body);
+    run_grid(name, grid, block, smem, body);
 }
 
 // ---- TMA / mbarrier stand-ins (see header comment) ----
@@ -160,7 +161,9 @@ static inline void* smem_ptr(uint32_t a) { return st().dyn_smem + (a - 4096u); }
 static inline void mbar_init(uint32_t, uint32_t) {}
 static inline void mbar_init_fence() {}
 static inline void mbar_expect_tx(uint32_t, uint32_t) {}
-static inline void mbar_wait(uint32_t, uint32_t) {}
+// the copy was made when the elected lane issued it; the wait only has to order the other
+// lanes behind that lane (on the device the mbarrier does)
+static inline void mbar_wait(uint32_t, uint32_t) { warp_sync(8); }
 static inline void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t) {
     const TensorMap& t = *reinterpret_cast<const TensorMap*>(tmap);
     uint32_t* out = reinterpret_cast<uint32_t*>(smem_ptr(dst));
@@ -436,6 +439,11 @@ static constexpr size_t STACK_BYTES = 256 << 10;
 
 static void release_if_complete(Warp* w) {
     if (w->arrived > 0 && w->arrived == w->live) {
+        const int par = w->gen & 1;
+        uint32_t m = 0;
+        for (int l = 0; l < 32; ++l)
+            if (((w->alive_mask >> l) & 1u) && (w->slot[par][l] & 1u)) m |= 1u << l;
+        w->vote[par] = m;
         w->arrived = 0;
         w->gen++;
     }
@@ -445,6 +453,8 @@ static void fiber_exit() {
     State& s = g_state;
     Fiber* f = s.cur;
     f->done = true;
+    static const bool trace = getenv("SFB_EMU_TRACE") != nullptr && atoi(getenv("SFB_EMU_TRACE")) >= 3;
+    if (trace) fprintf(stderr, "[emu] exit block %u thread %u (warp gen %u)\n", s.block_idx.x, f->tid.x, f->warp->gen);
     Warp* w = f->warp;
     w->live--;
     w->alive_mask &= ~(1u << f->lane);
@@ -466,6 +476,12 @@ extern "C" void emu_fiber_entry() {
 void yield() {
     State& s = g_state;
     s.switches++;
+    static const bool trace = getenv("SFB_EMU_TRACE") != nullptr && atoi(getenv("SFB_EMU_TRACE")) >= 2;
+    if (trace && (s.switches % 2000000) == 0) {
+        Warp* w = s.cur->warp;
+        fprintf(stderr, "[emu] %lld switches; block %u thread %u parked at collective tag %d (warp gen %u, arrived %d of %d live)\n",
+                s.switches, s.block_idx.x, s.cur->tid.x, w->tag[w->gen & 1], w->gen, w->arrived, w->live);
+    }
     emu_switch(&s.cur->sp, s.sched_sp);
 }
 
@@ -497,8 +513,8 @@ uint64_t exchange(uint64_t v, int src_lane, int tag) {
     const int par = w->gen & 1;
     w->slot[par][f->lane] = v;
     warp_sync(tag);
-    // a lane that has left the kernel reads as the caller's own value (undefined on the device)
-    return ((w->alive_mask >> src_lane) & 1u) ? w->slot[par][src_lane] : v;
+    // (a lane may leave the kernel right after a collective: its slot stays readable)
+    return w->slot[par][src_lane];
 }
 
 uint32_t ballot(bool pred, int tag) {
@@ -507,14 +523,13 @@ uint32_t ballot(bool pred, int tag) {
     const int par = w->gen & 1;
     w->slot[par][f->lane] = pred ? 1 : 0;
     warp_sync(tag);
-    uint32_t m = 0;
-    for (int l = 0; l < 32; ++l)
-        if (((w->alive_mask >> l) & 1u) && w->slot[par][l]) m |= 1u << l;
-    return m;
+    return w->vote[par];
 }
 
-void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+void run_grid(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     State& s = g_state;
+    static const bool trace = getenv("SFB_EMU_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[emu] %s <<<%u, %u, %zu>>>\n", name, grid.x, block.x, smem);
     if (s.cur) die("nested launch");
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads < 1 || nthreads > 1024) die("block size");

@@ -9,3 +9,25 @@
 
 extern "C" int sfb_emu_marker(void) { return 1; }
 extern "C" long long sfb_emu_launches(void) { return emu::st().launches; }
+
+// introspection for the emulator tests: the row tasks the last sweep emitted (whole-handle view
+// or every group), as (env, y, strip) triples; returns the number of tasks
+extern "C" long long sfb_emu_row_tasks(sfb_sim* s, int32_t* out, long long cap) {
+    const int par = s->parity ^ 1;
+    std::vector<EnvGroup*> views;
+    if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
+    else views.push_back(&s->all);
+    long long n = 0;
+    for (EnvGroup* gr : views) {
+        const long long cnt = (long long)gr->d.rows_count[par];
+        const int e0 = (int)(gr->d.idx_base / s->d.plane);
+        for (long long i = 0; i < cnt; ++i, ++n) {
+            if (n >= cap) continue;
+            const unsigned long long t = gr->d.rows[i];
+            out[3 * n] = (int32_t)(t >> 28) + e0;
+            out[3 * n + 1] = (int32_t)(t & 0xFFFFFu);
+            out[3 * n + 2] = (int32_t)((t >> 20) & 0xFFu);
+        }
+    }
+    return n;
+}
