@@ -139,6 +139,7 @@ class HostPool {
 // group is in its issue-bound kernels (k_rows, k_eval) another one streams (k_sweep), and the
 // hardware overlaps the two.  Each group sees its envs through a DevParams view with offset
 // plane pointers and its own work queue, row-task list and counters.
+constexpr int N_COUNTERS = 12;
 struct EnvGroup {
     DevParams d;
     CUtensorMap tmap;
@@ -146,8 +147,8 @@ struct EnvGroup {
     cudaStream_t stream_prio;  // descending priority: groups finish one after the other (change log on)
     cudaStream_t last_stream;  // the one the last steps ran on
     cudaEvent_t done;
-    unsigned long long* counters;  // qcount[2] | unit_next[2] | rows_count[2] | rows_next[2]
-    int sweep_blocks, rows_blocks;
+    unsigned long long* counters;  // qcount[2] | unit_next[2] | rows_count[2] | rows_next[2] | overflow | - | units_count[2]
+    int sweep_blocks, rows_blocks, units_blocks;
 };
 
 struct sfb_sim {
@@ -167,6 +168,7 @@ struct sfb_sim {
     int use_tma;      // sweep front end
     int sweep_blocks; // persistent grid of the sweep kernel
     int rows_blocks;  // persistent grid of k_rows
+    int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
@@ -288,6 +290,7 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
         reinterpret_cast<CellT*>(p.state)[(long long)env * p.plane + (long long)y * p.pitch + x] =
             (CellT)(ST_BURNING | (1 << 3));  // sprite created before update() call 1: ign = 0
         if (p.ign) p.ign[(long long)env * p.plane + (long long)y * p.pitch + x] = 0;
+        if (p.unit_act) mark_units_around<CellT>(p, env, y, x);
     }
     EnvMeta m;
     m.t = 1;
@@ -318,6 +321,7 @@ __global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int
     const long long idx = (long long)env * p.plane + (long long)y * p.pitch + x;
     CellT* c = reinterpret_cast<CellT*>(p.state) + idx;
     *c = (CellT)((*c & ~7) | to_internal(k));
+    if (p.unit_act) mark_units_around<CellT>(p, env, y, x);  // a control line is work under attenuation
     if (p.track) {
         const LogRef& L = log_of_env(p, env);
         log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48));
@@ -524,6 +528,8 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.meta);
     cudaFree(s->d.queue);
     cudaFree(s->d.rows);
+    cudaFree(s->d.unit_act);
+    cudaFree(s->d.units);
     s->groups.push_back(s->all);
     for (auto& gr : s->groups) {
         cudaFree(gr.counters);
@@ -672,6 +678,17 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
     if ((rc = dmalloc(s, &d.queue, (size_t)d.qcap * 8))) return rc;
     if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
+    // unit skipping: on for handles with enough units to make a list worth its launch, never in slab
+    // mode (a neighbour slab's fire enters through the halo rows, which nobody here would flag)
+    s->unit_skip = prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31) &&
+                   ((prm->flags & SFB_UNIT_SKIP_ON) || (!(prm->flags & SFB_UNIT_SKIP_OFF) && d.n_units >= 1024));
+    if (const char* e = getenv("SFB_UNIT_SKIP"))
+        if (prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
+    if (s->unit_skip) {
+        if ((rc = dmalloc(s, &d.unit_act, (size_t)d.n_units))) return rc;
+        if ((rc = dmalloc(s, &d.units, (size_t)d.n_units * sizeof(uint32_t)))) return rc;
+        CU(cudaMemsetAsync(d.unit_act, 0, (size_t)d.n_units, s->stream));
+    }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
 
     // second set of streams with descending priority: the kernels of earlier groups are scheduled
@@ -701,14 +718,19 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.qcap = q_cap;
         v.rows = d.rows + (int64_t)e0 * d.H * d.strips;
         v.rows_cap = (int64_t)cnt * d.H * d.strips;
+        if (d.unit_act) {
+            v.unit_act = d.unit_act + (int64_t)e0 * d.chunks * d.strips;
+            v.units = d.units + (int64_t)e0 * d.chunks * d.strips;
+        }
         int rc2;
-        if ((rc2 = dmalloc(s, &gr.counters, 10 * sizeof(unsigned long long)))) return rc2;
-        CU(cudaMemsetAsync(gr.counters, 0, 10 * sizeof(unsigned long long), s->stream));
+        if ((rc2 = dmalloc(s, &gr.counters, N_COUNTERS * sizeof(unsigned long long)))) return rc2;
+        CU(cudaMemsetAsync(gr.counters, 0, N_COUNTERS * sizeof(unsigned long long), s->stream));
         v.qcount = gr.counters;
         v.unit_next = gr.counters + 2;
         v.rows_count = gr.counters + 4;
         v.rows_next = gr.counters + 6;
         v.overflow = reinterpret_cast<int32_t*>(gr.counters + 8);
+        v.units_count = d.unit_act ? gr.counters + 10 : nullptr;
         if (s->use_tma) {
             const cuuint64_t row_bytes = (cuuint64_t)d.pitch * s->cell_bytes;
             const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)d.H, (cuuint64_t)cnt};
@@ -739,6 +761,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
+        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((v.n_units + 255) / 256, (long long)4 * s->n_sm));
         return 0;
     };
     if ((rc = make_view(s->all, 0, d.E, 0, d.qcap, false))) return rc;
@@ -796,6 +819,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     d.rows_count = s->all.d.rows_count;
     d.rows_next = s->all.d.rows_next;
     d.overflow = s->all.d.overflow;
+    d.units_count = s->all.d.units_count;
 
     CU(cudaMemsetAsync((void*)d.stat, 0, (size_t)stat_cells * sizeof(StaticRec), s->stream));
     CU(cudaMemsetAsync(d.meta, 0, (size_t)2 * d.E * sizeof(EnvMeta), s->stream));  // running = 0
@@ -1010,6 +1034,9 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     } else {
         DISPATCH(s, k_set_map, cap_grid(s, (long long)bytes, 256), 256, d, env0, n, (const int8_t*)s->stage);
     }
+    // wholesale replacement: any cell may have become a control line or ignitable next to a sprite
+    if (d.unit_act)
+        CU(cudaMemsetAsync(d.unit_act + (size_t)env0 * d.chunks * d.strips, 1, (size_t)n * d.chunks * d.strips, s->stream));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1055,6 +1082,11 @@ static int derive_if_dirty(sfb_sim* s) {
 }
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (gr.d.unit_act) {  // this step's list of flagged units; the sweep draws from it
+        SFB_LAUNCH(k_units, gr.units_blocks, 256, 0, st, gr.d, par);
+        s->launches_all++;
+        s->launches_step++;
+    }
     if (s->use_tma) {
         if (s->cell_bytes == 1) SFB_LAUNCH(k_sweep_tma<uint8_t>, gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st, gr.tmap, gr.d, par);
         else SFB_LAUNCH(k_sweep_tma<uint16_t>, gr.sweep_blocks, SWEEP_WARPS * 32, TMA_BLOCK_SMEM, st, gr.tmap, gr.d, par);
@@ -1148,8 +1180,8 @@ static int enqueue_eval(sfb_sim* s) {
 static int enter_mode(sfb_sim* s, int mode) {
     if (s->last_mode == mode) return 0;
     if (s->last_mode != 0) {
-        CU(cudaMemsetAsync(s->all.counters, 0, 10 * sizeof(unsigned long long), s->stream));
-        for (auto& gr : s->groups) CU(cudaMemsetAsync(gr.counters, 0, 10 * sizeof(unsigned long long), s->stream));
+        CU(cudaMemsetAsync(s->all.counters, 0, N_COUNTERS * sizeof(unsigned long long), s->stream));
+        for (auto& gr : s->groups) CU(cudaMemsetAsync(gr.counters, 0, N_COUNTERS * sizeof(unsigned long long), s->stream));
     }
     s->last_mode = mode;
     return 0;
@@ -1748,6 +1780,29 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
     }
     if (tasks) *tasks = tot;
     if (capacity) *capacity = cap;
+    return 0;
+}
+
+extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_get_unit_stats: null handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    const int par = s->parity ^ 1;
+    CU(cudaStreamSynchronize(s->stream));
+    int64_t tot = s->d.n_units, act = s->d.n_units;
+    if (s->unit_skip) {
+        act = 0;
+        std::vector<EnvGroup*> views;
+        if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
+        else views.push_back(&s->all);
+        for (EnvGroup* grp : views) {
+            unsigned long long c[N_COUNTERS];
+            CU(cudaMemcpy(c, grp->counters, sizeof(c), cudaMemcpyDeviceToHost));
+            act += (int64_t)c[10 + par];
+        }
+    }
+    if (listed) *listed = act;
+    if (total) *total = tot;
     return 0;
 }
 

@@ -117,6 +117,15 @@ struct DevParams {
     unsigned long long* rows_count; // [2]
     unsigned long long* rows_next;  // [2] next row task to hand out
     int64_t rows_cap;
+    // unit skipping: unit_act[u] != 0 <=> the sweep has to read unit u = (env, chunk, strip).  Invariant:
+    // a unit whose rows / columns, or the one-cell frame around them, hold a sprite code (or, with
+    // attenuation, a control line) is flagged.  Flags are raised wherever a cell ignites or a control
+    // line is drawn (process_item, k_reset_meta, k_apply_points; sfb_set_fire_map flags whole envs) and
+    // lowered by the sweep itself when a flagged unit yields no row task.  k_units compacts the
+    // flagged units of running envs into `units`; the sweep then only draws from that list.
+    uint8_t* unit_act;                // [E * chunks * strips], nullptr = dense sweep over every unit
+    uint32_t* units;                  // [n_units] this step's active units
+    unsigned long long* units_count;  // [2]
     // slab mode: rows -1 and H of this slab live in a neighbour slab (peer device memory)
     const void* halo_top;     // row (slab_y0 - 1) of the slab above, or nullptr
     const void* halo_bottom;  // row (slab_y0 + H) of the slab below, or nullptr
@@ -183,6 +192,41 @@ __device__ __forceinline__ int sprite_age(int code, int tm1) {
     return a < 0 ? a + Cell<CellT>::M : a;
 }
 
+// raise the activity flag of every unit that holds cell (y, x) of `env` in its rows / columns or in
+// the one-cell frame around them (at most 2 x 2 units)
+template <typename CellT>
+__device__ __forceinline__ void mark_units_around(const DevParams& p, int env, int y, int x) {
+    constexpr int WR = 32 * Cell<CellT>::CPL;
+    const int R = p.rows_per_chunk;
+    const int y0 = y > 0 ? y - 1 : 0, y1 = y + 1 < p.H ? y + 1 : p.H - 1;
+    const int x0 = x > 0 ? x - 1 : 0, x1 = x + 1 < p.W ? x + 1 : p.W - 1;
+    const int c0 = y0 / R, c1 = y1 >= (c0 + 1) * R ? c0 + 1 : c0;  // y1 - y0 <= 2 <= R
+    const int s0 = x0 / WR, s1 = x1 / WR;
+    uint8_t* f0 = p.unit_act + ((long long)env * p.chunks + c0) * p.strips;
+    f0[s0] = 1;
+    if (s1 != s0) f0[s1] = 1;
+    if (c1 != c0) {
+        uint8_t* f1 = f0 + p.strips;
+        f1[s0] = 1;
+        if (s1 != s0) f1[s1] = 1;
+    }
+}
+// the same from a cell index relative to the view's first cell
+template <typename CellT>
+__device__ __forceinline__ void mark_units_of_cell(const DevParams& p, int env, long long idx) {
+    const long long cell = idx - (long long)env * p.plane;
+    int y, x;
+    if (p.plane <= 0x7fffffffll) {  // warp-uniform; 32-bit division
+        const uint32_t c = (uint32_t)cell;
+        y = (int)(c / (uint32_t)p.pitch);
+        x = (int)(c - (uint32_t)y * (uint32_t)p.pitch);
+    } else {
+        y = (int)(cell / p.pitch);
+        x = (int)(cell - (long long)y * p.pitch);
+    }
+    mark_units_around<CellT>(p, env, y, x);
+}
+
 __device__ __forceinline__ unsigned long long make_item(long long idx, int dir, int s) {
     return (unsigned long long)idx | ((unsigned long long)dir << 48) | ((unsigned long long)s << 52);
 }
@@ -237,6 +281,7 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
         const int code = 1 + (m.t % Cell<CellT>::M);
         reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(ST_BURNING | (code << 3));  // fire.py:571-587
         if (p.ign) p.ign[idx] = m.t;
+        if (p.unit_act) mark_units_of_cell<CellT>(p, env, idx);
         return true;
     }
     return false;
@@ -285,13 +330,14 @@ struct RowTaskList {
     int count = 0;            // warp-uniform
     __device__ __forceinline__ RowTaskList(const DevParams& p_, int par_, int lane_, unsigned long long* buf_)
         : p(p_), par(par_), lane(lane_), buf(buf_) {}
-    // every lane calls; lanes with `have` contribute one task
-    __device__ __forceinline__ void push(bool have, unsigned long long task) {
+    // every lane calls; lanes with `have` contribute one task; returns the ballot of `have`
+    __device__ __forceinline__ uint32_t push(bool have, unsigned long long task) {
         const uint32_t m = __ballot_sync(0xffffffffu, have);
-        if (!m) return;
+        if (!m) return 0;
         if (have) buf[count + __popc(m & ((1u << lane) - 1))] = task;
         count += __popc(m);
         if (count > WQ_CAP - 32) flush();
+        return m;
     }
     __device__ __forceinline__ void flush() {
         if (count == 0) return;
@@ -490,16 +536,45 @@ struct RowWorker {
 
 // Warps are persistent: each pulls the next (env, chunk, strip) unit from a device counter,
 // so a warp that drew a short unit immediately takes another one.
-__device__ __forceinline__ bool next_unit(const DevParams& p, int par, int lane, int& strip, int& chunk, int& env) {
-    unsigned long long unit = 0;
-    if (lane == 0) unit = atomicAdd(p.unit_next + par, 1ULL);
+__device__ __forceinline__ bool next_unit(const DevParams& p, int par, int lane, int& strip, int& chunk, int& env,
+                                          long long& unit_id) {
+    unsigned long long unit = ~0ull;
+    if (lane == 0) {
+        const unsigned long long i = atomicAdd(p.unit_next + par, 1ULL);
+        if (!p.unit_act) unit = i;                               // dense: every unit in turn
+        else if (i < p.units_count[par]) unit = p.units[i];      // only the units k_units listed
+    }
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= (unsigned long long)p.n_units) return false;
+    unit_id = (long long)unit;
     strip = (int)(unit % p.strips);
     const long long u2 = unit / p.strips;
     chunk = (int)(u2 % p.chunks);
     env = (int)(u2 / p.chunks);
     return true;
+}
+// a flagged unit that yielded no row task has nothing to look at within one cell of its rows and
+// columns: the sweep skips it from the next step on, until a neighbouring ignition flags it again
+__device__ __forceinline__ void retire_unit(const DevParams& p, int lane, long long unit_id, uint32_t emitted) {
+    if (p.unit_act && !emitted && lane == 0) p.unit_act[unit_id] = 0;
+}
+
+// k_units: compacts the flagged units of running envs into this step's unit list
+__global__ void __launch_bounds__(256) k_units(const DevParams p, const int par) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long upe = (long long)p.chunks * p.strips;  // units per env
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < p.n_units; base += stride) {
+        const long long u = base + lane;
+        bool act = false;
+        if (u < p.n_units && p.unit_act[u]) act = p.meta[(long long)par * p.meta_stride + (int)(u / upe)].running != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, act);
+        if (!m) continue;
+        unsigned long long slot = 0;
+        if (lane == __ffs(m) - 1) slot = atomicAdd(p.units_count + par, (unsigned long long)__popc(m));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+        if (act) p.units[slot + __popc(m & ((1u << lane) - 1))] = (uint32_t)u;
+    }
 }
 
 // ---- front end 1: TMA ring --------------------------------------------------------------
@@ -588,8 +663,10 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
     uint32_t boxes_done = 0;  // boxes consumed by this warp so far: fixes ring slot and mbarrier phase
 
     int strip, chunk, env;
-    while (next_unit(p, par, lane, strip, chunk, env)) {
+    long long unit_id;
+    while (next_unit(p, par, lane, strip, chunk, env, unit_id)) {
         if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
+        uint32_t emitted = 0;
         const int x0 = strip * WR;
         const int y_begin = chunk * p.rows_per_chunk;
         const int n_rows = min(y_begin + p.rows_per_chunk, p.H) - y_begin;  // rows this unit owns
@@ -638,10 +715,11 @@ k_sweep_tma(const __grid_constant__ CUtensorMap tmap, const DevParams p, const i
             const uint32_t rows = (nz | (nz >> 1) | (nz >> 2)) & ((1u << B) - 1u);
             if (rows) {  // warp-uniform
                 const int j = k * B - 1 + lane;
-                tasks.push(lane < B && ((rows >> lane) & 1u) && j >= 1 && j <= n_rows, make_row_task(env, y_begin - 1 + j, strip));
+                emitted |= tasks.push(lane < B && ((rows >> lane) & 1u) && j >= 1 && j <= n_rows, make_row_task(env, y_begin - 1 + j, strip));
             }
         }
         boxes_done += (uint32_t)n_box;
+        retire_unit(p, lane, unit_id, emitted);
     }
     tasks.flush();
 }
@@ -661,8 +739,10 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
     const uint32_t look_mask = p.attenuate ? (C::CODE_MASK | C::LINE_MASK) : C::CODE_MASK;
 
     int strip, chunk, env;
-    while (next_unit(p, par, lane, strip, chunk, env)) {
+    long long unit_id;
+    while (next_unit(p, par, lane, strip, chunk, env, unit_id)) {
         if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
+        uint32_t emitted = 0;
         const CellT* const envbase = reinterpret_cast<const CellT*>(p.state) + (long long)env * p.plane;
         const int x0 = strip * WR;
         const int xl = x0 + lane * CPL;
@@ -716,11 +796,12 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, SFB_LDG_MIN_BLOCKS) k_sweep_
             // rows y .. y+3: lane i decides row y + i
             const uint32_t rows = ((b0 | b1 | b2) ? 1u : 0u) | ((b1 | b2 | b3) ? 2u : 0u) | ((b2 | b3 | b4) ? 4u : 0u) |
                                   ((b3 | b4 | b5) ? 8u : 0u);
-            if (rows) tasks.push(lane < 4 && ((rows >> lane) & 1u) && y + lane < y_end, make_row_task(env, y + lane, strip));
+            if (rows) emitted |= tasks.push(lane < 4 && ((rows >> lane) & 1u) && y + lane < y_end, make_row_task(env, y + lane, strip));
             b0 = b4;
             b1 = b5;
             rowp = q4;
         }
+        retire_unit(p, lane, unit_id, emitted);
     }
     tasks.flush();
 }
@@ -908,6 +989,7 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
         p.overflow[par ^ 1] = 0;
         p.unit_next[par ^ 1] = 0;
         p.rows_count[par ^ 1] = 0;
+        if (p.units_count) p.units_count[par ^ 1] = 0;
     }
 }
 

@@ -57,6 +57,7 @@ class FireEngine:
         track_changes: bool = False,
         keep_ignition: bool = False,
         env_groups: int = 0,
+        unit_skip: Optional[bool] = None,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -76,6 +77,9 @@ class FireEngine:
         flags |= _lib.SWEEP_LDG if sweep_ldg else 0
         flags |= _lib.TRACK_CHANGES if track_changes else 0
         flags |= _lib.KEEP_IGNITION if keep_ignition else 0
+        # None: the library decides (on from 1024 sweep units up); results do not depend on it
+        if unit_skip is not None:
+            flags |= _lib.UNIT_SKIP_ON if unit_skip else _lib.UNIT_SKIP_OFF
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -335,6 +339,12 @@ class FireEngine:
     def row_tasks(self):
         a, b = C.c_int64(), C.c_int64()
         _lib.check(self._lib.sfb_get_row_tasks(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def unit_stats(self):
+        """(sweep units the last step listed, units of the handle); equal without unit skipping."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
     def queue_stats(self):

@@ -103,7 +103,8 @@ def test_golden_trajectory(name):
 
 @pytest.mark.parametrize("name", ["scenario_a_models_diag_att", "scenario_d_midrun_mitigation",
                                   "scenario_b_models_4nbr_noatt", "scenario_f_max_time"])  # fmt: skip
-@pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8"])
+@pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8",
+                                     "skip", "skip_wide", "skip_ldg_rows8", "skip_overflow", "noskip"])
 def test_golden_trajectory_variants(name, variant):
     """The 16-bit cell layout, the dense fallback taken on queue overflow, other chunk
     heights and the non-TMA streaming front end must give the same trajectories."""
@@ -111,7 +112,11 @@ def test_golden_trajectory_variants(name, variant):
     kw = {"wide_cells": dict(wide_cells=True), "queue_overflow": dict(queue_capacity=3),
           "rows4": dict(rows_per_chunk=4), "rows64": dict(rows_per_chunk=64), "ldg": dict(sweep_ldg=True),
           "ldg_wide": dict(sweep_ldg=True, wide_cells=True),
-          "ldg_rows8": dict(sweep_ldg=True, rows_per_chunk=8)}[variant]  # fmt: skip
+          "ldg_rows8": dict(sweep_ldg=True, rows_per_chunk=8),
+          # unit skipping (sweep only the flagged (env, rows, columns) units), forced on for these small grids
+          "skip": dict(unit_skip=True), "skip_wide": dict(unit_skip=True, wide_cells=True),
+          "skip_ldg_rows8": dict(unit_skip=True, sweep_ldg=True, rows_per_chunk=8),
+          "skip_overflow": dict(unit_skip=True, queue_capacity=3), "noskip": dict(unit_skip=False)}[variant]  # fmt: skip
     with engine_for(sc, **kw) as eng:
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
@@ -185,6 +190,76 @@ def test_env_groups_on_streams_equal_one_group(groups):
     assert np.array_equal(a[0], b[0])
     assert all(np.array_equal(x, y) for x, y in zip(a[1], b[1])) and np.array_equal(a[2], b[2])
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
+
+
+@pytest.mark.parametrize("front_end", ["tma", "ldg"])
+@pytest.mark.parametrize("attenuate", [True, False])
+def test_unit_skipping_changes_nothing(front_end, attenuate):
+    """Sweeping only the flagged units must give the same fire maps, burn planes, clocks and
+    change logs as sweeping every unit, through ignitions that cross unit borders, control lines
+    drawn mid-run, a map upload, a reset of some envs and envs that burn out; and it must really
+    skip: far fewer units are listed than the handle has."""
+    from oracle.dense_numpy import DenseFire, DenseParams
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    H, W, E = 150, 1100, 5  # three 512-cell strips, 19+ chunks of rows
+    wl = synthetic_operational(H, W, seed=9, patch=16)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=attenuate, max_fire_duration=4)
+    rng = np.random.default_rng(2)
+    starts = wl.burnable_starts(E, seed=5, margin=3)
+    starts[0] = (511, 75)   # on a strip border
+    starts[1] = (1030, 6)
+    lines0 = [(e, x, 60, 3 + (x % 3)) for e in range(E) for x in range(400, 700)]
+    engines = []
+    for skip in (False, True):
+        eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, sweep_ldg=(front_end == "ldg"), rows_per_chunk=8,
+                         track_changes=True, env_groups=2, **kw)  # fmt: skip
+        eng.set_static(wl.planes)
+        eng.reset(starts)
+        eng.apply_points(lines0)
+        engines.append(eng)
+    oracle = DenseFire(wl.planes, DenseParams(**kw), tuple(int(v) for v in starts[0]))
+    oracle.apply_points([(x, y, k) for e, x, y, k in lines0 if e == 0])
+    mirrors = [np.zeros((E, H, W), np.int8) for _ in engines]
+    listed = []
+    try:
+        for phase in range(6):
+            n = 9
+            for eng, mir in zip(engines, mirrors):
+                eng.step(n)
+                eng.sync_fire_maps(mir)
+            for _ in range(n):
+                oracle.step()
+            a, b = engines[0].fire_map(), engines[1].fire_map()
+            assert np.array_equal(a, b), f"phase {phase}: fire maps differ with unit skipping"
+            assert np.array_equal(mirrors[1], b) and np.array_equal(mirrors[0], a)
+            assert np.array_equal(a[0], oracle.status), f"phase {phase}: env 0 differs from the oracle"
+            for e in (0, 3):
+                assert np.array_equal(engines[0].plane("burn", e), engines[1].plane("burn", e))
+            for x, y in zip(engines[0].status(), engines[1].status()):
+                assert np.array_equal(x, y)
+            listed.append(engines[1].unit_stats())
+            assert engines[0].unit_stats()[0] == engines[0].unit_stats()[1]
+            # between-step mutations of every kind
+            if phase == 1:  # a control line near the fire of env 1 and one far from any fire
+                pts = [(1, x, 12, 4) for x in range(900, 1090)] + [(2, x, 140, 5) for x in range(5, 60)]
+                for eng in engines:
+                    eng.apply_points(pts)
+            if phase == 2:  # upload a map: burnt cells next to the front become fuel again
+                m = engines[0].fire_map(3, 1)
+                m[m == 2] = 0
+                m[0, 100:110, 200:260] = 3
+                for eng in engines:
+                    eng.set_fire_map(m, env0=3)
+            if phase == 3:
+                for eng in engines:
+                    eng.reset(np.array([[20, 20], [1000, 140]]), envs=[2, 4])
+        total = listed[0][1]
+        assert all(l < total // 4 for l, _ in listed), listed
+    finally:
+        for eng in engines:
+            eng.close()
 
 
 def test_multi_step_launch_equals_single_steps():
