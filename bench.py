@@ -334,7 +334,7 @@ def gpu_arm(args):
     H, W = wl.H, wl.W
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
                      sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, env_groups=args.env_groups,
-                     **wl.engine_kwargs())  # fmt: skip
+                     unit_skip={"auto": None, "on": True, "off": False}[args.unit_skip], **wl.engine_kwargs())  # fmt: skip
     if args.workload == "cfg3_perenv":
         from simfire_b200.workloads import synthetic_operational
 
@@ -375,6 +375,7 @@ def gpu_arm(args):
     eng.set_kernel_timing(False)
     q_entries, q_cap, q_ovf = eng.queue_stats()
     row_tasks, _ = eng.row_tasks()
+    units_listed, units_total = eng.unit_stats()  # of the same (last) step of the roofline pass
     sweep_s = sweep_ms / n_t * 1e-3
     rows_s = rows_ms / n_t * 1e-3
     eval_s = eval_ms / n_t * 1e-3
@@ -449,13 +450,21 @@ def gpu_arm(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
 
-    # algorithmic bytes per launch of k_sweep in THIS design (DESIGN.md "Kernels"): every cell's
-    # packed state is read once (1 B/cell-update; halo rows and pads are re-read from L2) and
-    # an 8-byte row task is written per warp-row that needs a closer look.  The survey's figure
-    # (a kernel that streams all planes) is kept beside it.
+    # algorithmic bytes per launch of k_sweep in THIS design (DESIGN.md "Kernels"): the packed state
+    # of every cell of every LISTED unit is read once (1 B/cell; halo rows and pads are re-read
+    # from L2; without unit skipping every unit is listed, i.e. 1 B per cell-update) and an 8-byte
+    # row task is written per warp-row that needs a closer look; with unit skipping k_units also
+    # reads one flag byte per unit and the list costs 4 B per listed unit, written and read.
+    # The survey's figure (a kernel that streams all planes) is kept beside it.
     cells_rank = H * W * E
-    sweep_bytes = cells_rank * 1.0 + row_tasks * 8.0
+    skipping = units_listed < units_total
+    sweep_cells = cells_rank * (units_listed / max(1, units_total))
+    sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
     achieved = sweep_bytes / sweep_s / 1e9
+    # k_rows re-reads three 512-byte rows per task (L2 hits) and writes 8 B per work item
+    rows_bytes = row_tasks * (3 * 512 + 8.0) + q_entries * 8.0
+    kernel_ms = {"k_sweep_" + args.sweep: sweep_s * 1e3, "k_rows": rows_s * 1e3, "k_eval": eval_s * 1e3}
+    dominant = max(kernel_ms, key=kernel_ms.get)
     survey_b = SURVEY_BYTES_SHARED(E) if shared else SURVEY_BYTES_PER_ENV_STATIC
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -479,7 +488,17 @@ def gpu_arm(args):
         "roofline": {
             "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-            "traffic": load_traffic_note(args.workload),
+            "traffic": None if skipping else load_traffic_note(args.workload),
+            "unit_skipping": {"on": skipping, "units_listed": units_listed, "units_total": units_total,
+                              "cells_swept_per_step": sweep_cells, "cells_per_step": cells_rank,
+                              "note": "the sweep reads only units flagged as holding fire or control lines; "
+                                      "bytes_per_launch counts the listed units' cells, so `achieved` is the "
+                                      "bandwidth of what is actually streamed"},
+            "longest_kernel": dominant, "kernel_ms_per_launch": kernel_ms,
+            "k_rows": {"bytes_per_launch": rows_bytes, "achieved": rows_bytes / rows_s / 1e9 if rows_s > 0 else None,
+                       "frac": rows_bytes / rows_s / 1e9 / peak_gbs if rows_s > 0 else None,
+                       "note": "issue-bound (ncu: ~74 % of issue slots); its row re-reads are L2 hits, so this "
+                               "is not an HBM figure"},
             "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,
             "ms_per_launch": sweep_s * 1e3, "k_rows_ms_per_launch": rows_s * 1e3, "k_eval_ms_per_launch": eval_s * 1e3,
             "sweep_share_of_step": sweep_s / (sweep_s + rows_s + eval_s),
@@ -510,6 +529,8 @@ def main():
     ap.add_argument("--rows-per-chunk", type=int, default=0)
     ap.add_argument("--env-groups", type=int, default=0, help="env groups stepped on separate streams (0 = auto)")
     ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
+    ap.add_argument("--unit-skip", default="auto", choices=["auto", "on", "off"],
+                    help="sweep only the units flagged as active (auto: the library decides)")
     ap.add_argument("--roofline-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0)

@@ -67,3 +67,42 @@ def test_small_scale_cases_under_emulation():
     out = _run(["tests/test_gpu_scale.py", "-k",
                 "degenerate_and_ragged or fire_duration_limits or cell_life_cycle"])  # fmt: skip
     assert " passed" in out
+
+
+def _emu_env():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    from build_emu import build
+
+    return dict(os.environ, SFB_LIB=build(), SFB_EMULATED="1")
+
+
+def test_bench_gpu_arm_dry_run_under_emulation():
+    """bench.py's GPU arm, every phase (device-timed steps, per-kernel pass, e2e with the patched
+    host mirror), on a tiny workload against the emulator: catches Python-level mistakes in the
+    bench before the GPU box does.  The numbers mean nothing; the line's shape is checked."""
+    import json
+
+    for skip in ("on", "off"):
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dry_run.py"), "--workload", "small",
+                              "--steps", "3", "--warmup", "3", "--burn-in", "5", "--roofline-steps", "2", "--e2e-steps", "3",
+                              "--no-cpu-baseline", "--unit-skip", skip],
+                             cwd=ROOT, env=_emu_env(), capture_output=True, text=True, timeout=600)  # fmt: skip
+        assert res.returncode == 0, res.stderr[-2000:]
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in line, key
+        assert line["e2e"]["mirror_matches_download"] is True
+        assert line["gpu_launches"] > 0
+        rf = line["roofline"]
+        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "unit_skipping", "kernel_ms_per_launch"):
+            assert key in rf, key
+        assert rf["unit_skipping"]["on"] == (skip == "on")
+        if skip == "off":
+            assert rf["unit_skipping"]["units_listed"] == rf["unit_skipping"]["units_total"]
+
+
+def test_smoke_under_emulation():
+    res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_emu_env(),
+                         capture_output=True, text=True, timeout=600)  # fmt: skip
+    assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
