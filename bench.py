@@ -334,7 +334,8 @@ def gpu_arm(args):
     H, W = wl.H, wl.W
     eng = FireEngine(H, W, E, shared_static=shared, device=local, rows_per_chunk=args.rows_per_chunk,
                      sweep_ldg=(args.sweep == "ldg"), track_changes=not args.no_track, env_groups=args.env_groups,
-                     unit_skip={"auto": None, "on": True, "off": False}[args.unit_skip], **wl.engine_kwargs())  # fmt: skip
+                     unit_skip={"auto": None, "on": True, "off": False}[args.unit_skip],
+                     unit_chunks=(args.units == "chunks"), **wl.engine_kwargs())  # fmt: skip
     if args.workload == "cfg3_perenv":
         from simfire_b200.workloads import synthetic_operational
 
@@ -457,13 +458,20 @@ def gpu_arm(args):
     # reads one flag byte per unit and the list costs 4 B per listed unit, written and read.
     # The survey's figure (a kernel that streams all planes) is kept beside it.
     cells_rank = H * W * E
-    skipping = units_listed < units_total
-    sweep_cells = cells_rank * (units_listed / max(1, units_total))
-    sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
+    unit_mode = eng.unit_mode()
+    skipping = unit_mode != "dense"
+    if unit_mode == "rows":  # nothing is swept: k_row_list reads one flag byte per (env, row, strip)
+        sweep_cells = 0.0
+        sweep_bytes = units_total * 1.0 + row_tasks * 8.0
+        front_kernel = "k_row_list"
+    else:
+        sweep_cells = cells_rank * (units_listed / max(1, units_total))
+        sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
+        front_kernel = "k_sweep_" + args.sweep
     achieved = sweep_bytes / sweep_s / 1e9
     # k_rows re-reads three 512-byte rows per task (L2 hits) and writes 8 B per work item
     rows_bytes = row_tasks * (3 * 512 + 8.0) + q_entries * 8.0
-    kernel_ms = {"k_sweep_" + args.sweep: sweep_s * 1e3, "k_rows": rows_s * 1e3, "k_eval": eval_s * 1e3}
+    kernel_ms = {front_kernel: sweep_s * 1e3, "k_rows": rows_s * 1e3, "k_eval": eval_s * 1e3}
     dominant = max(kernel_ms, key=kernel_ms.get)
     survey_b = SURVEY_BYTES_SHARED(E) if shared else SURVEY_BYTES_PER_ENV_STATIC
     line = {
@@ -486,14 +494,15 @@ def gpu_arm(args):
                        "as changed (8 B each)" if not args.no_track else " by a full download")},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_sweep_" + args.sweep, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "bound": "hbm", "kernel": front_kernel, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "traffic": None if skipping else load_traffic_note(args.workload),
-            "unit_skipping": {"on": skipping, "units_listed": units_listed, "units_total": units_total,
+            "unit_skipping": {"on": skipping, "mode": unit_mode, "units_listed": units_listed, "units_total": units_total,
                               "cells_swept_per_step": sweep_cells, "cells_per_step": cells_rank,
-                              "note": "the sweep reads only units flagged as holding fire or control lines; "
-                                      "bytes_per_launch counts the listed units' cells, so `achieved` is the "
-                                      "bandwidth of what is actually streamed"},
+                              "note": "only units flagged as holding fire or control lines are looked at: chunks of "
+                                      "rows that are then swept (bytes_per_launch counts their cells), or single "
+                                      "rows that are the row tasks themselves (bytes_per_launch = one flag byte "
+                                      "per row and strip; no state is swept)"},
             "longest_kernel": dominant, "kernel_ms_per_launch": kernel_ms,
             "k_rows": {"bytes_per_launch": rows_bytes, "achieved": rows_bytes / rows_s / 1e9 if rows_s > 0 else None,
                        "frac": rows_bytes / rows_s / 1e9 / peak_gbs if rows_s > 0 else None,
@@ -530,7 +539,9 @@ def main():
     ap.add_argument("--env-groups", type=int, default=0, help="env groups stepped on separate streams (0 = auto)")
     ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
     ap.add_argument("--unit-skip", default="auto", choices=["auto", "on", "off"],
-                    help="sweep only the units flagged as active (auto: the library decides)")
+                    help="look only at the units flagged as active (auto: the library decides)")
+    ap.add_argument("--units", default="rows", choices=["rows", "chunks"],
+                    help="with unit skipping: single rows (no sweep) or chunks of rows (swept)")
     ap.add_argument("--roofline-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0)

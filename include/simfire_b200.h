@@ -72,10 +72,14 @@ enum sfb_flags {
                                   cell: enough to rebuild the fire-spread graph the reference
                                   maintains per step (graph.py:84-150, called at fire.py:584)   */,
     SFB_UNIT_SKIP_OFF = 512,   /* always sweep every (env, rows, columns) unit                      */
-    SFB_UNIT_SKIP_ON = 1024    /* keep per-unit activity flags and sweep only the flagged units even
+    SFB_UNIT_SKIP_ON = 1024,   /* keep per-unit activity flags and look only at the flagged units even
                                   for small handles (default: on from 1024 units up, off in slab
                                   mode).  Results are identical either way; the reference has no
                                   counterpart (it walks its sprite list, fire.py:655-690)          */
+    SFB_UNIT_CHUNKS = 2048     /* with unit skipping: a unit is a chunk of rows of one strip and the
+                                  flagged units are swept (k_units + k_sweep).  Default: a unit is a
+                                  single row of a strip, the flagged units are the row tasks
+                                  themselves and nothing is swept (k_row_list)                     */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the
@@ -274,9 +278,10 @@ int sfb_set_kernel_timing(sfb_sim* sim, int32_t enabled);
 int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* eval_ms, int64_t* n_steps);
 /* Row tasks (warp-rows that needed a cell-by-cell look) emitted by the last completed step. */
 int sfb_get_row_tasks(sfb_sim* sim, int64_t* tasks, int64_t* capacity);
-/* Sweep units = (env, chunk of rows, strip of columns) the last completed step listed for its
- * sweep, and the number of units of the handle.  Without unit skipping the two are equal. */
-int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total);
+/* Units = (env, chunk of rows or single row, strip of columns) the last completed step listed,
+ * and the number of units of the handle; mode: 0 = no unit skipping (every unit is swept, the two
+ * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks. */
+int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total, int32_t* mode);
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and
  * whether the step overflowed the queue and ran the dense fallback. */
 int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32_t* overflowed);

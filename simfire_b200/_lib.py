@@ -13,7 +13,7 @@ ABI_VERSION = 1
 DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
 TRACK_CHANGES = 128
 KEEP_IGNITION = 256
-UNIT_SKIP_OFF, UNIT_SKIP_ON = 512, 1024
+UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS = 512, 1024, 2048
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS, PLANE_IGNITION = 0, 1, 2, 3, 4
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")
@@ -103,7 +103,7 @@ def load() -> C.CDLL:
         "sfb_get_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                         C.POINTER(i64)]),
         "sfb_get_row_tasks": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
-        "sfb_get_unit_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "sfb_get_unit_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_get_queue_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_device_bytes": (C.c_int, [vp, C.POINTER(i64)]),
         "sfb_rate_of_spread": (C.c_int, [i32, vp, vp, vp, i64, vp]),

@@ -169,6 +169,7 @@ struct sfb_sim {
     int sweep_blocks; // persistent grid of the sweep kernel
     int rows_blocks;  // persistent grid of k_rows
     int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
+    int unit_rows;    // ... and a unit is a single row of a strip: no sweep at all (k_row_list)
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
@@ -684,10 +685,22 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
                    ((prm->flags & SFB_UNIT_SKIP_ON) || (!(prm->flags & SFB_UNIT_SKIP_OFF) && d.n_units >= 1024));
     if (const char* e = getenv("SFB_UNIT_SKIP"))
         if (prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
+    s->unit_rows = s->unit_skip && !(prm->flags & SFB_UNIT_CHUNKS);
+    if (const char* e = getenv("SFB_UNIT_ROWS")) s->unit_rows = s->unit_skip && atoi(e) != 0;
+    d.unit_stride = (int64_t)d.chunks * d.strips;
+    if (s->unit_rows) {
+        // one row of one strip per unit: the flagged units are the row tasks, the state is never swept
+        d.unit_rows = 1;
+        d.rows_per_chunk = 1;
+        d.chunks = d.H;
+        d.n_units = (int64_t)d.E * d.H * d.strips;
+        d.unit_stride = ((int64_t)d.H * d.strips + 3) / 4 * 4;
+    }
     if (s->unit_skip) {
-        if ((rc = dmalloc(s, &d.unit_act, (size_t)d.n_units))) return rc;
-        if ((rc = dmalloc(s, &d.units, (size_t)d.n_units * sizeof(uint32_t)))) return rc;
-        CU(cudaMemsetAsync(d.unit_act, 0, (size_t)d.n_units, s->stream));
+        const size_t flag_bytes = (size_t)d.E * d.unit_stride;
+        if ((rc = dmalloc(s, &d.unit_act, flag_bytes))) return rc;
+        if (!s->unit_rows && (rc = dmalloc(s, &d.units, (size_t)d.n_units * sizeof(uint32_t)))) return rc;
+        CU(cudaMemsetAsync(d.unit_act, 0, flag_bytes, s->stream));
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
 
@@ -719,8 +732,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.rows = d.rows + (int64_t)e0 * d.H * d.strips;
         v.rows_cap = (int64_t)cnt * d.H * d.strips;
         if (d.unit_act) {
-            v.unit_act = d.unit_act + (int64_t)e0 * d.chunks * d.strips;
-            v.units = d.units + (int64_t)e0 * d.chunks * d.strips;
+            v.unit_act = d.unit_act + (int64_t)e0 * d.unit_stride;
+            if (d.units) v.units = d.units + (int64_t)e0 * d.chunks * d.strips;
         }
         int rc2;
         if ((rc2 = dmalloc(s, &gr.counters, N_COUNTERS * sizeof(unsigned long long)))) return rc2;
@@ -761,7 +774,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
-        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((v.n_units + 255) / 256, (long long)4 * s->n_sm));
+        const long long unit_items = d.unit_rows ? (long long)cnt * d.unit_stride / 4 : v.n_units;  // words / flags
+        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((unit_items + 255) / 256, (long long)(d.unit_rows ? 8 : 4) * s->n_sm));
         return 0;
     };
     if ((rc = make_view(s->all, 0, d.E, 0, d.qcap, false))) return rc;
@@ -1036,7 +1050,7 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     }
     // wholesale replacement: any cell may have become a control line or ignitable next to a sprite
     if (d.unit_act)
-        CU(cudaMemsetAsync(d.unit_act + (size_t)env0 * d.chunks * d.strips, 1, (size_t)n * d.chunks * d.strips, s->stream));
+        CU(cudaMemsetAsync(d.unit_act + (size_t)env0 * d.unit_stride, 1, (size_t)n * d.unit_stride, s->stream));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1082,6 +1096,12 @@ static int derive_if_dirty(sfb_sim* s) {
 }
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (gr.d.unit_rows) {  // the flagged rows are this step's row tasks: nothing is swept
+        SFB_LAUNCH(k_row_list, gr.units_blocks, 256, 0, st, gr.d, par);
+        s->launches_all++;
+        s->launches_step++;
+        return;
+    }
     if (gr.d.unit_act) {  // this step's list of flagged units; the sweep draws from it
         SFB_LAUNCH(k_units, gr.units_blocks, 256, 0, st, gr.d, par);
         s->launches_all++;
@@ -1783,7 +1803,7 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
     return 0;
 }
 
-extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total) {
+extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, int32_t* mode) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_get_unit_stats: null handle");
     int rc;
     if ((rc = use(s))) return rc;
@@ -1798,11 +1818,12 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total) {
         for (EnvGroup* grp : views) {
             unsigned long long c[N_COUNTERS];
             CU(cudaMemcpy(c, grp->counters, sizeof(c), cudaMemcpyDeviceToHost));
-            act += (int64_t)c[10 + par];
+            act += (int64_t)c[(s->unit_rows ? 4 : 10) + par];  // row units: the listed units are the row tasks
         }
     }
     if (listed) *listed = act;
     if (total) *total = tot;
+    if (mode) *mode = !s->unit_skip ? 0 : (s->unit_rows ? 2 : 1);
     return 0;
 }
 

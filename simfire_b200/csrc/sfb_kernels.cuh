@@ -123,6 +123,11 @@ struct DevParams {
     // line is drawn (process_item, k_reset_meta, k_apply_points; sfb_set_fire_map flags whole envs) and
     // lowered by the sweep itself when a flagged unit yields no row task.  k_units compacts the
     // flagged units of running envs into `units`; the sweep then only draws from that list.
+    // Row units (unit_rows != 0): a unit is one row of one strip (rows_per_chunk = 1, chunks = H).  Then the
+    // flags ARE the row-task list: k_row_list compacts them straight into `rows`, no state is swept at
+    // all, and k_rows lowers the flag of a row whose 3-row window holds nothing to look at.
+    int32_t unit_rows, pad_units;
+    int64_t unit_stride;              // flags per env: chunks * strips (row units: rounded up to 4, pad flags unused)
     uint8_t* unit_act;                // [E * chunks * strips], nullptr = dense sweep over every unit
     uint32_t* units;                  // [n_units] this step's active units
     unsigned long long* units_count;  // [2]
@@ -200,15 +205,12 @@ __device__ __forceinline__ void mark_units_around(const DevParams& p, int env, i
     const int R = p.rows_per_chunk;
     const int y0 = y > 0 ? y - 1 : 0, y1 = y + 1 < p.H ? y + 1 : p.H - 1;
     const int x0 = x > 0 ? x - 1 : 0, x1 = x + 1 < p.W ? x + 1 : p.W - 1;
-    const int c0 = y0 / R, c1 = y1 >= (c0 + 1) * R ? c0 + 1 : c0;  // y1 - y0 <= 2 <= R
+    const int c0 = R == 1 ? y0 : y0 / R, c1 = R == 1 ? y1 : (y1 >= (c0 + 1) * R ? c0 + 1 : c0);  // y1 - y0 <= 2
     const int s0 = x0 / WR, s1 = x1 / WR;
-    uint8_t* f0 = p.unit_act + ((long long)env * p.chunks + c0) * p.strips;
-    f0[s0] = 1;
-    if (s1 != s0) f0[s1] = 1;
-    if (c1 != c0) {
-        uint8_t* f1 = f0 + p.strips;
-        f1[s0] = 1;
-        if (s1 != s0) f1[s1] = 1;
+    uint8_t* f = p.unit_act + (long long)env * p.unit_stride + (long long)c0 * p.strips;
+    for (int c = c0; c <= c1; ++c, f += p.strips) {  // at most three rows of flags (row units), else two
+        f[s0] = 1;
+        if (s1 != s0) f[s1] = 1;
     }
 }
 // the same from a cell index relative to the view's first cell
@@ -485,13 +487,26 @@ struct RowWorker {
             const int cp = rp[xi], cc = rc[xi], cn = rn[xi];
             if (!__any_sync(0xffffffffu, ((cp | cc | cn) & (int)(look_mask & CELL_ALL)) != 0)) continue;
             const int kp = source_key(cp), kc = source_key(cc), kn = source_key(cn);
-            // keys of the eight neighbours, rank in the low three bits (0 = written last)
+            // keys of the eight neighbours, rank in the low three bits (0 = written last).  Each lane first
+            // folds its own column as it looks from the cell to its west (ranks SE 0, E 3, NE 5) and from
+            // the cell to its east (SW 2, W 4, NW 7); the neighbours then fetch one value each: two
+            // shuffles instead of six.
+#ifdef SFB_ROWS_SHFL6
             int best = min(__shfl_down_sync(0xffffffffu, kc, 1) + 3, __shfl_up_sync(0xffffffffu, kc, 1) + 4);
             best = min(best, min(kn + 1, kp + 6));
             if (diagonal) {
                 best = min(best, min(__shfl_down_sync(0xffffffffu, kn, 1) + 0, __shfl_up_sync(0xffffffffu, kn, 1) + 2));
                 best = min(best, min(__shfl_down_sync(0xffffffffu, kp, 1) + 5, __shfl_up_sync(0xffffffffu, kp, 1) + 7));
             }
+#else
+            int as_east = kc + 3, as_west = kc + 4;
+            if (diagonal) {
+                as_east = min(as_east, min(kn + 0, kp + 5));
+                as_west = min(as_west, min(kn + 2, kp + 7));
+            }
+            int best = min(__shfl_down_sync(0xffffffffu, as_east, 1), __shfl_up_sync(0xffffffffu, as_west, 1));
+            best = min(best, min(kn + 1, kp + 6));
+#endif
             const int x = x0 + col;
             const bool owner = lane_owner && col < cells;
             int s = cc & 7;
@@ -574,6 +589,49 @@ __global__ void __launch_bounds__(256) k_units(const DevParams p, const int par)
         if (lane == __ffs(m) - 1) slot = atomicAdd(p.units_count + par, (unsigned long long)__popc(m));
         slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
         if (act) p.units[slot + __popc(m & ((1u << lane) - 1))] = (uint32_t)u;
+    }
+}
+
+// k_row_list (row units): the flags are per (env, row, strip), so the flagged units ARE this step's row
+// tasks.  Each lane takes four flags (one 32-bit load), the warp scans the counts, one atomic per warp.
+__global__ void __launch_bounds__(256) k_row_list(const DevParams p, const int par) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = (long long)p.E * p.unit_stride / 4;  // unit_stride is a multiple of 4
+    const long long upe = p.unit_stride, used = (long long)p.H * p.strips;
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(p.unit_act);
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n4; base += stride) {
+        const long long w = base + lane;
+        uint32_t f = w < n4 ? flags[w] : 0u;
+        if (!__any_sync(0xffffffffu, f != 0)) continue;
+        unsigned long long task[4];
+        int cnt = 0;
+        if (f) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (!((f >> (8 * b)) & 0xFFu)) continue;
+                const long long u = 4 * w + b;
+                const int env = (int)(u / upe);
+                if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
+                const long long r = u - (long long)env * upe;
+                if (r >= used) continue;  // pad flag (a map upload sets whole envs, pads included)
+                const int y = (int)(r / p.strips), strip = (int)(r - (long long)y * p.strips);
+                task[cnt++] = make_row_task(env, y, strip);
+            }
+        }
+        int incl = cnt;  // inclusive scan of the per-lane counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long slot = 0;
+        if (lane == 0) slot = atomicAdd(p.rows_count + par, (unsigned long long)total);
+        slot = __shfl_sync(0xffffffffu, slot, 0) + (unsigned long long)(incl - cnt);
+        for (int i = 0; i < cnt; ++i)
+            if (slot + i < (unsigned long long)p.rows_cap) p.rows[slot + i] = task[i];
     }
 }
 
@@ -887,6 +945,9 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
             const uint4 vo = make_uint4(v[0].x | v[1].x | v[2].x, v[0].y | v[1].y | v[2].y, v[0].z | v[1].z | v[2].z,
                                         v[0].w | v[1].w | v[2].w);
             const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, h[0] | h[1] | h[2]));
+            // row units: nothing to look at in the 3-row window -> the row leaves the list until an
+            // ignition, a control line or a map upload next to it flags it again
+            if (p.unit_rows && act == 0 && lane == 0) p.unit_act[(long long)env * p.unit_stride + (long long)y * p.strips + strip] = 0;
             rw.detail_row(y, sm[0], sm[1], sm[2], act);
         }
     }

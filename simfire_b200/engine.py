@@ -58,6 +58,7 @@ class FireEngine:
         keep_ignition: bool = False,
         env_groups: int = 0,
         unit_skip: Optional[bool] = None,
+        unit_chunks: bool = False,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -80,6 +81,7 @@ class FireEngine:
         # None: the library decides (on from 1024 sweep units up); results do not depend on it
         if unit_skip is not None:
             flags |= _lib.UNIT_SKIP_ON if unit_skip else _lib.UNIT_SKIP_OFF
+        flags |= _lib.UNIT_CHUNKS if unit_chunks else 0  # chunk-of-rows units + sweep instead of row units
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -342,10 +344,16 @@ class FireEngine:
         return int(a.value), int(b.value)
 
     def unit_stats(self):
-        """(sweep units the last step listed, units of the handle); equal without unit skipping."""
-        a, b = C.c_int64(), C.c_int64()
-        _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b)))
+        """(units the last step listed, units of the handle); equal without unit skipping."""
+        a, b, m = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
         return int(a.value), int(b.value)
+
+    def unit_mode(self) -> str:
+        """'dense' (every unit swept), 'chunks' (flagged chunks swept) or 'rows' (flagged rows are the row tasks)."""
+        a, b, m = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
+        return ("dense", "chunks", "rows")[int(m.value)]
 
     def queue_stats(self):
         a, b, o = C.c_int64(), C.c_int64(), C.c_int32()

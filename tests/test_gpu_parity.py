@@ -104,7 +104,8 @@ def test_golden_trajectory(name):
 @pytest.mark.parametrize("name", ["scenario_a_models_diag_att", "scenario_d_midrun_mitigation",
                                   "scenario_b_models_4nbr_noatt", "scenario_f_max_time"])  # fmt: skip
 @pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8",
-                                     "skip", "skip_wide", "skip_ldg_rows8", "skip_overflow", "noskip"])
+                                     "skip", "skip_wide", "skip_ldg_rows8", "skip_overflow", "noskip",
+                                     "rowunits", "rowunits_wide", "rowunits_overflow"])
 def test_golden_trajectory_variants(name, variant):
     """The 16-bit cell layout, the dense fallback taken on queue overflow, other chunk
     heights and the non-TMA streaming front end must give the same trajectories."""
@@ -114,9 +115,12 @@ def test_golden_trajectory_variants(name, variant):
           "ldg_wide": dict(sweep_ldg=True, wide_cells=True),
           "ldg_rows8": dict(sweep_ldg=True, rows_per_chunk=8),
           # unit skipping (sweep only the flagged (env, rows, columns) units), forced on for these small grids
-          "skip": dict(unit_skip=True), "skip_wide": dict(unit_skip=True, wide_cells=True),
-          "skip_ldg_rows8": dict(unit_skip=True, sweep_ldg=True, rows_per_chunk=8),
-          "skip_overflow": dict(unit_skip=True, queue_capacity=3), "noskip": dict(unit_skip=False)}[variant]  # fmt: skip
+          "skip": dict(unit_skip=True, unit_chunks=True), "skip_wide": dict(unit_skip=True, unit_chunks=True, wide_cells=True),
+          "skip_ldg_rows8": dict(unit_skip=True, unit_chunks=True, sweep_ldg=True, rows_per_chunk=8),
+          "skip_overflow": dict(unit_skip=True, unit_chunks=True, queue_capacity=3), "noskip": dict(unit_skip=False),
+          # ... with one row per unit: the flagged rows are the row tasks, nothing is swept
+          "rowunits": dict(unit_skip=True), "rowunits_wide": dict(unit_skip=True, wide_cells=True),
+          "rowunits_overflow": dict(unit_skip=True, queue_capacity=3)}[variant]  # fmt: skip
     with engine_for(sc, **kw) as eng:
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
@@ -192,13 +196,14 @@ def test_env_groups_on_streams_equal_one_group(groups):
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
 
 
-@pytest.mark.parametrize("front_end", ["tma", "ldg"])
+@pytest.mark.parametrize("front_end", ["tma", "ldg", "rows"])
 @pytest.mark.parametrize("attenuate", [True, False])
 def test_unit_skipping_changes_nothing(front_end, attenuate):
-    """Sweeping only the flagged units must give the same fire maps, burn planes, clocks and
-    change logs as sweeping every unit, through ignitions that cross unit borders, control lines
-    drawn mid-run, a map upload, a reset of some envs and envs that burn out; and it must really
-    skip: far fewer units are listed than the handle has."""
+    """Looking only at the flagged units (chunks of rows that are then swept with either front end,
+    or single rows that are the row tasks themselves) must give the same fire maps, burn planes,
+    clocks and change logs as sweeping every unit, through ignitions that cross unit borders,
+    control lines drawn mid-run, a map upload, a reset of some envs and envs that burn out; and
+    it must really skip: far fewer units are listed than the handle has."""
     from oracle.dense_numpy import DenseFire, DenseParams
     from simfire_b200 import FireEngine
     from simfire_b200.workloads import synthetic_operational
@@ -213,8 +218,8 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
     lines0 = [(e, x, 60, 3 + (x % 3)) for e in range(E) for x in range(400, 700)]
     engines = []
     for skip in (False, True):
-        eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, sweep_ldg=(front_end == "ldg"), rows_per_chunk=8,
-                         track_changes=True, env_groups=2, **kw)  # fmt: skip
+        eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, unit_chunks=(front_end != "rows"),
+                         sweep_ldg=(front_end == "ldg"), rows_per_chunk=8, track_changes=True, env_groups=2, **kw)  # fmt: skip
         eng.set_static(wl.planes)
         eng.reset(starts)
         eng.apply_points(lines0)
