@@ -385,8 +385,19 @@ def gpu_arm(args):
         eng.set_tracking(True)
 
     # ---- end to end through the batched API with host buffers
-    pinned_maps = torch.empty((E, H, W), dtype=torch.int8, pin_memory=True)
-    maps_np = pinned_maps.numpy()
+    if args.mirror == "thp":
+        # the mirror is only written by host threads (patches) and by one initial download: ordinary
+        # memory on transparent huge pages keeps the scattered patch writes out of the page walker
+        import mmap
+
+        mirror_mm = mmap.mmap(-1, E * H * W, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        if hasattr(mmap, "MADV_HUGEPAGE"):
+            mirror_mm.madvise(mmap.MADV_HUGEPAGE)
+        maps_np = np.frombuffer(mirror_mm, dtype=np.int8).reshape(E, H, W)
+        maps_np[...] = 0  # touch every page before the timed region
+    else:
+        pinned_maps = torch.empty((E, H, W), dtype=torch.int8, pin_memory=True)
+        maps_np = pinned_maps.numpy()
     pinned_pts = torch.empty((E, 4), dtype=torch.int32, pin_memory=True)
     pts_np = pinned_pts.numpy()
     rng = np.random.default_rng(5 + rank)
@@ -488,6 +499,7 @@ def gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes) * world,
                 "d2h_bytes_per_step": (int(8 * e2e_changes / e2e_steps) + 12 if not args.no_track else int(maps_np.nbytes)) * world,
                 "steps": e2e_steps, "host_mirror_bytes": int(maps_np.nbytes) * world, "mirror_matches_download": e2e_ok,
+                "host_mirror_memory": "pinned" if args.mirror == "pinned" else "pageable, MADV_HUGEPAGE",
                 "ms_per_call": {"apply_points": e2e_calls[0], "step_enqueue": e2e_calls[1], "sync_fire_maps": e2e_calls[2]},
                 "api": "FireEngine.apply_points (pinned H2D) + step + sync_fire_maps: every env's int8 fire_map is "
                        "brought up to date in host memory each step" + (" by patching the cells the device logged "
@@ -548,6 +560,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slab-sync", default="p2p", choices=["p2p", "nccl"], help="cfg5: how the slabs agree per step")
     ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
+    ap.add_argument("--mirror", default="pinned", choices=["pinned", "thp"],
+                    help="memory of the host fire_map mirror in the e2e phase")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -76,10 +76,12 @@ enum sfb_flags {
                                   for small handles (default: on from 1024 units up, off in slab
                                   mode).  Results are identical either way; the reference has no
                                   counterpart (it walks its sprite list, fire.py:655-690)          */
-    SFB_UNIT_CHUNKS = 2048     /* with unit skipping: a unit is a chunk of rows of one strip and the
+    SFB_UNIT_CHUNKS = 2048,    /* with unit skipping: a unit is a chunk of rows of one strip and the
                                   flagged units are swept (k_units + k_sweep).  Default: a unit is a
                                   single row of a strip, the flagged units are the row tasks
                                   themselves and nothing is swept (k_row_list)                     */
+    SFB_NO_STEP_GRAPH = 4096   /* multi-group handles: enqueue every kernel of sfb_step(n) directly
+                                  instead of replaying pairs of steps as one CUDA graph            */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the

@@ -162,6 +162,12 @@ struct sfb_sim {
     // batches are launch-bound, and a graph replay costs less than six kernel launches
     cudaGraphExec_t pair_graph;
     unsigned pair_graph_epoch, view_epoch;  // the graph bakes the view's parameters in
+    // the same for multi-group handles: two steps of every group, forked over the group streams
+    // (used while the change log is off; with it on the host waits for the groups one by one)
+    cudaGraphExec_t group_graph;
+    unsigned group_graph_epoch;
+    int group_graph_on;
+    int64_t group_launches_all, group_launches_step;
     int64_t pair_launches_all, pair_launches_step;
     cudaEvent_t fork_ev;
     int cell_bytes;   // 1 or 2
@@ -540,6 +546,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     }
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     if (s->pair_graph) cudaGraphExecDestroy(s->pair_graph);
+    if (s->group_graph) cudaGraphExecDestroy(s->group_graph);
     for (auto& m : s->log_mapped)
         if (m) cudaFreeHost(m);
     cudaFree(s->log_counts);
@@ -703,6 +710,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(d.unit_act, 0, flag_bytes, s->stream));
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+    s->group_graph_on = (prm->flags & SFB_NO_STEP_GRAPH) ? 0 : 1;
+    if (const char* e = getenv("SFB_GROUP_GRAPH")) s->group_graph_on = atoi(e) != 0;
 
     // second set of streams with descending priority: the kernels of earlier groups are scheduled
     // first, so the groups finish one after the other and the host can patch the change log of a
@@ -1236,6 +1245,74 @@ static int run_pair_graph(sfb_sim* s) {
     return 0;
 }
 
+// n steps of every group, kernel by kernel, each group on its own stream
+static int enqueue_group_steps(sfb_sim* s, int n) {
+    CU(cudaEventRecord(s->fork_ev, s->stream));
+    for (auto& gr : s->groups) {
+        gr.last_stream = s->d.track ? gr.stream_prio : gr.stream;
+        CU(cudaStreamWaitEvent(gr.last_stream, s->fork_ev, 0));
+    }
+    int par = s->parity;
+    for (int i = 0; i < n; ++i) {
+        for (auto& gr : s->groups) {
+            launch_sweep(s, gr, gr.last_stream, par);
+            launch_rows(s, gr, gr.last_stream, par);
+            launch_eval(s, gr, gr.last_stream, par);
+        }
+        par ^= 1;
+    }
+    s->parity = par;
+    const bool heads = s->d.track && s->log_head && (int)s->groups.size() == s->d.n_logs;
+    for (size_t g = 0; g < s->groups.size(); ++g) {
+        auto& gr = s->groups[g];
+        // the group's {count, overflow} rides behind its last kernel, so that sfb_sync_fire_maps
+        // finds it in host memory as soon as the group's event has fired
+        if (heads)
+            CU(cudaMemcpyAsync(s->log_head + 2 * g, s->d.logs[g].count, 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, gr.last_stream));
+        CU(cudaEventRecord(gr.done, gr.last_stream));
+        CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
+    }
+    s->head_valid = heads;
+    return 0;
+}
+
+// replay (capturing it first if needed) two steps of every env group as one graph; parity must be 0
+static int run_group_graph(sfb_sim* s) {
+    if (!s->group_graph || s->group_graph_epoch != s->view_epoch) {
+        if (s->group_graph) CU(cudaGraphExecDestroy(s->group_graph));
+        s->group_graph = nullptr;
+        const int64_t la = s->launches_all, ls = s->launches_step;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        CU(cudaEventRecord(s->fork_ev, s->stream));
+        for (auto& gr : s->groups) CU(cudaStreamWaitEvent(gr.stream, s->fork_ev, 0));
+        for (int par = 0; par < 2; ++par)
+            for (auto& gr : s->groups) {
+                launch_sweep(s, gr, gr.stream, par);
+                launch_rows(s, gr, gr.stream, par);
+                launch_eval(s, gr, gr.stream, par);
+            }
+        for (auto& gr : s->groups) {
+            CU(cudaEventRecord(gr.done, gr.stream));
+            CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
+        }
+        CU(cudaStreamEndCapture(s->stream, &g));
+        s->group_launches_all = s->launches_all - la;
+        s->group_launches_step = s->launches_step - ls;
+        s->launches_all = la;
+        s->launches_step = ls;
+        cudaError_t e = cudaGraphInstantiate(&s->group_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        s->group_graph_epoch = s->view_epoch;
+    }
+    CU(cudaGraphLaunch(s->group_graph, s->stream));
+    s->launches_all += s->group_launches_all;
+    s->launches_step += s->group_launches_step;
+    return 0;
+}
+
 static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
@@ -1265,34 +1342,19 @@ static int enqueue_steps(sfb_sim* s, int n) {
     if ((rc = enter_mode(s, 2))) return rc;
     if ((rc = derive_if_dirty(s))) return rc;
     sync_group_views(s);
-    CU(cudaEventRecord(s->fork_ev, s->stream));
-    for (auto& gr : s->groups) {
-        gr.last_stream = s->d.track ? gr.stream_prio : gr.stream;
-        CU(cudaStreamWaitEvent(gr.last_stream, s->fork_ev, 0));
-    }
-    int par = s->parity;
-    for (int i = 0; i < n; ++i) {
-        for (auto& gr : s->groups) {
-            launch_sweep(s, gr, gr.last_stream, par);
-            launch_rows(s, gr, gr.last_stream, par);
-            launch_eval(s, gr, gr.last_stream, par);
+    // device-resident stepping (no change log to drain group by group): pairs of steps as one graph
+    if (s->group_graph_on && !s->d.track && n >= 4 && s->stream == s->own_stream) {
+        if (s->parity == 1) {  // the graph starts at parity 0
+            if ((rc = enqueue_group_steps(s, 1))) return rc;
+            --n;
         }
-        par ^= 1;
+        for (auto& gr : s->groups) gr.last_stream = gr.stream;
+        for (; n >= 2; n -= 2)
+            if ((rc = run_group_graph(s))) return rc;  // parity is 0 again after each pair
+        s->head_valid = 0;
+        if (n == 0) return 0;  // the graph joined every group back into the handle's stream
     }
-    s->parity = par;
-    const bool heads = s->d.track && s->log_head && (int)s->groups.size() == s->d.n_logs;
-    for (size_t g = 0; g < s->groups.size(); ++g) {
-        auto& gr = s->groups[g];
-        // the group's {count, overflow} rides behind its last kernel, so that sfb_sync_fire_maps
-        // finds it in host memory as soon as the group's event has fired
-        if (heads)
-            CU(cudaMemcpyAsync(s->log_head + 2 * g, s->d.logs[g].count, 2 * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, gr.last_stream));
-        CU(cudaEventRecord(gr.done, gr.last_stream));
-        CU(cudaStreamWaitEvent(s->stream, gr.done, 0));
-    }
-    s->head_valid = heads;
-    return 0;
+    return enqueue_group_steps(s, n);
 }
 
 static int enqueue_step(sfb_sim* s) { return enqueue_steps(s, 1); }

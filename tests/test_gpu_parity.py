@@ -267,6 +267,37 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
             eng.close()
 
 
+@pytest.mark.parametrize("unit_skip", [False, True])
+def test_grouped_multi_step_launch_equals_single_steps(unit_skip):
+    """Multi-group handles replay pairs of steps as one CUDA graph forked over the group streams
+    (change log off, n >= 4, from either parity); single steps are enqueued kernel by kernel.
+    Same state either way, also across a control line drawn between two launches."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    wl = synthetic_operational(64, 200, seed=6, patch=8)
+    E = 7
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True)
+    starts = wl.burnable_starts(E, seed=1, margin=3)
+    res = []
+    for plan in ([1] * 27, [5, 9, 4, 1, 8]):
+        with FireEngine(64, 200, E, shared_static=True, env_groups=3, unit_skip=unit_skip, keep_ros=True, **kw) as eng:
+            eng.set_static(wl.planes)
+            eng.reset(starts)
+            done = 0
+            for n in plan:
+                eng.step(n)
+                done += n
+                if done == 14:
+                    eng.apply_points([(e, x, 30, 3) for e in range(E) for x in range(20, 180)])
+            assert done == 27
+            res.append((eng.fire_map(), [eng.plane("burn", e) for e in (0, 3, 6)], eng.status()))
+    a, b = res
+    assert np.array_equal(a[0], b[0])
+    assert all(np.array_equal(x, y) for x, y in zip(a[1], b[1]))
+    assert all(np.array_equal(x, y) for x, y in zip(a[2], b[2]))
+
+
 def test_multi_step_launch_equals_single_steps():
     sc = load_scenario("scenario_c_random_fuel_hills")
     with engine_for(sc) as a, engine_for(sc) as b:
