@@ -229,17 +229,26 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
-def load_traffic_note(workload: str):
-    """Per-launch DRAM bytes of k_sweep from the committed ncu capture, if it matches."""
-    path = os.path.join(ROOT, "profiles", "ncu_sweep_summary.json")
+def load_traffic_note(workload: str, kernel: str):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu captures, if they match the workload:
+    (bytes, note).  profiles/ncu_sweep_summary.json: the dense sweep; profiles/ncu_kernel_traffic.json:
+    the front-proportional kernels, captured earlier in the run than the bench times them."""
     try:
-        with open(path) as f:
-            j = json.load(f)
-        if j.get("workload") == workload:
-            return j.get("dram_bytes_per_launch")
+        if kernel.startswith("k_sweep"):
+            with open(os.path.join(ROOT, "profiles", "ncu_sweep_summary.json")) as f:
+                j = json.load(f)
+            if j.get("workload") == workload:
+                return j.get("dram_bytes_per_launch"), "ncu --set full, same launch shape"
+        else:
+            with open(os.path.join(ROOT, "profiles", "ncu_kernel_traffic.json")) as f:
+                j = json.load(f)
+            if j.get("workload") == workload and kernel in j.get("kernels", {}):
+                return (j["kernels"][kernel]["dram_bytes_per_launch"],
+                        f"ncu --set full at ~{j.get('row_tasks_at_capture')} row tasks / {j.get('work_items_at_capture')} work "
+                        "items per launch (younger fires than in the timed pass: scale by the task counts)")
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def gpu_arm_slab(args):
@@ -479,11 +488,24 @@ def gpu_arm(args):
         sweep_cells = cells_rank * (units_listed / max(1, units_total))
         sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
         front_kernel = "k_sweep_" + args.sweep
-    achieved = sweep_bytes / sweep_s / 1e9
-    # k_rows re-reads three 512-byte rows per task (L2 hits) and writes 8 B per work item
+    # k_rows reads its 8-byte task and three 512-byte rows per task and writes 8 B per work item;
+    # k_eval reads the 8-byte item, a 48-byte derived record and the float64 burn, writes the burn
     rows_bytes = row_tasks * (3 * 512 + 8.0) + q_entries * 8.0
+    eval_bytes = q_entries * (8.0 + 48.0 + 8.0 + 8.0)
     kernel_ms = {front_kernel: sweep_s * 1e3, "k_rows": rows_s * 1e3, "k_eval": eval_s * 1e3}
+    kernel_bytes = {front_kernel: sweep_bytes, "k_rows": rows_bytes, "k_eval": eval_bytes}
     dominant = max(kernel_ms, key=kernel_ms.get)
+    dom_s = kernel_ms[dominant] * 1e-3
+    achieved = kernel_bytes[dominant] / dom_s / 1e9
+    traffic, traffic_note = load_traffic_note(args.workload, dominant)
+    if dominant.startswith("k_sweep") and skipping:
+        traffic, traffic_note = None, None  # the committed capture is of the dense sweep
+    bound_note = {
+        "k_rows": "issue-bound, not HBM-bound: ncu shows ~76 % of the issue slots busy and DRAM at 12-14 % "
+                  "(profiles/r01b_kernels.json); consecutive row tasks share two of their three rows, so the "
+                  "measured DRAM traffic is about half the algorithmic bytes.  The lever is instructions per task.",
+        "k_eval": "latency-bound gather/scatter on a work queue (DRAM ~30 %, issue slots ~38 %)",
+    }.get(dominant, "streaming kernel: the roofline that matters is HBM bandwidth")
     survey_b = SURVEY_BYTES_SHARED(E) if shared else SURVEY_BYTES_PER_ENV_STATIC
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -506,23 +528,24 @@ def gpu_arm(args):
                        "as changed (8 B each)" if not args.no_track else " by a full download")},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": front_kernel, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "bound": "hbm", "kernel": dominant, "env_groups_timed_one_after_the_other": True, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-            "traffic": None if skipping else load_traffic_note(args.workload),
+            "traffic": traffic, "traffic_note": traffic_note, "note": bound_note,
+            "kernels": {k: {"ms_per_launch": kernel_ms[k], "bytes_per_launch": kernel_bytes[k],
+                            "achieved": kernel_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 if kernel_ms[k] > 0 else None,
+                            "frac": kernel_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peak_gbs if kernel_ms[k] > 0 else None}
+                        for k in kernel_ms},
             "unit_skipping": {"on": skipping, "mode": unit_mode, "units_listed": units_listed, "units_total": units_total,
                               "cells_swept_per_step": sweep_cells, "cells_per_step": cells_rank,
                               "note": "only units flagged as holding fire or control lines are looked at: chunks of "
                                       "rows that are then swept (bytes_per_launch counts their cells), or single "
                                       "rows that are the row tasks themselves (bytes_per_launch = one flag byte "
                                       "per row and strip; no state is swept)"},
-            "longest_kernel": dominant, "kernel_ms_per_launch": kernel_ms,
-            "k_rows": {"bytes_per_launch": rows_bytes, "achieved": rows_bytes / rows_s / 1e9 if rows_s > 0 else None,
-                       "frac": rows_bytes / rows_s / 1e9 / peak_gbs if rows_s > 0 else None,
-                       "note": "issue-bound (ncu: ~74 % of issue slots); its row re-reads are L2 hits, so this "
-                               "is not an HBM figure"},
-            "bytes_per_launch": sweep_bytes, "bytes_per_cell_update": sweep_bytes / cells_rank,
-            "ms_per_launch": sweep_s * 1e3, "k_rows_ms_per_launch": rows_s * 1e3, "k_eval_ms_per_launch": eval_s * 1e3,
-            "sweep_share_of_step": sweep_s / (sweep_s + rows_s + eval_s),
+            "kernel_ms_per_launch": kernel_ms,
+            "bytes_per_launch": kernel_bytes[dominant], "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank,
+            "ms_per_launch": dom_s * 1e3, "share_of_step": dom_s / (sweep_s + rows_s + eval_s),
+            "dense_sweep_reference": "without unit skipping the step is one 1 B/cell TMA sweep at 1.08 of the measured "
+                                     "HBM copy bandwidth (profiles/r01b_bench_target_dense.json, r01_kernels.json)",
             "row_tasks_per_step": row_tasks, "work_items_per_step": q_entries, "queue_overflowed": q_ovf,
             "survey_model": {"bytes_per_cell_update": survey_b,
                              "achieved": cells_rank * survey_b / (sweep_s + rows_s + eval_s) / 1e9,

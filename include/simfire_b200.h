@@ -80,8 +80,11 @@ enum sfb_flags {
                                   flagged units are swept (k_units + k_sweep).  Default: a unit is a
                                   single row of a strip, the flagged units are the row tasks
                                   themselves and nothing is swept (k_row_list)                     */
-    SFB_NO_STEP_GRAPH = 4096   /* multi-group handles: enqueue every kernel of sfb_step(n) directly
-                                  instead of replaying pairs of steps as one CUDA graph            */
+    SFB_STEP_GRAPH = 4096      /* multi-group handles: replay pairs of steps of sfb_step(n) as one CUDA
+                                  graph forked over the group streams instead of enqueueing every
+                                  kernel (single-group handles always replay a graph).  Off by
+                                  default: the join after every pair costs more overlap between the
+                                  groups than the saved launches give back (measured)               */
 };
 
 /* The eight static per-cell inputs of the Rothermel evaluation, in the order of the

@@ -13,7 +13,7 @@ ABI_VERSION = 1
 DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
 TRACK_CHANGES = 128
 KEEP_IGNITION = 256
-UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS = 512, 1024, 2048
+UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS, STEP_GRAPH = 512, 1024, 2048, 4096
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS, PLANE_IGNITION = 0, 1, 2, 3, 4
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")

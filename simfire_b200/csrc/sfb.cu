@@ -162,8 +162,8 @@ struct sfb_sim {
     // batches are launch-bound, and a graph replay costs less than six kernel launches
     cudaGraphExec_t pair_graph;
     unsigned pair_graph_epoch, view_epoch;  // the graph bakes the view's parameters in
-    // the same for multi-group handles: two steps of every group, forked over the group streams
-    // (used while the change log is off; with it on the host waits for the groups one by one)
+    // the same for multi-group handles (opt-in, SFB_STEP_GRAPH): two steps of every group, forked over the
+    // group streams (only while the change log is off; with it on the host waits for the groups one by one)
     cudaGraphExec_t group_graph;
     unsigned group_graph_epoch;
     int group_graph_on;
@@ -710,7 +710,9 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(d.unit_act, 0, flag_bytes, s->stream));
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-    s->group_graph_on = (prm->flags & SFB_NO_STEP_GRAPH) ? 0 : 1;
+    // measured (profiles/r01b_bench_target_groupgraph.json): the graph joins the groups after every pair of
+    // steps, which costs more overlap between groups than the saved launches give back -> opt-in
+    s->group_graph_on = (prm->flags & SFB_STEP_GRAPH) ? 1 : 0;
     if (const char* e = getenv("SFB_GROUP_GRAPH")) s->group_graph_on = atoi(e) != 0;
 
     // second set of streams with descending priority: the kernels of earlier groups are scheduled

@@ -59,6 +59,7 @@ class FireEngine:
         env_groups: int = 0,
         unit_skip: Optional[bool] = None,
         unit_chunks: bool = False,
+        step_graph: bool = False,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -82,6 +83,7 @@ class FireEngine:
         if unit_skip is not None:
             flags |= _lib.UNIT_SKIP_ON if unit_skip else _lib.UNIT_SKIP_OFF
         flags |= _lib.UNIT_CHUNKS if unit_chunks else 0  # chunk-of-rows units + sweep instead of row units
+        flags |= _lib.STEP_GRAPH if step_graph else 0    # multi-group handles: pairs of steps as one CUDA graph
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,

@@ -269,8 +269,8 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
 
 @pytest.mark.parametrize("unit_skip", [False, True])
 def test_grouped_multi_step_launch_equals_single_steps(unit_skip):
-    """Multi-group handles replay pairs of steps as one CUDA graph forked over the group streams
-    (change log off, n >= 4, from either parity); single steps are enqueued kernel by kernel.
+    """Multi-group handles can replay pairs of steps as one CUDA graph forked over the group streams
+    (opt-in; change log off, n >= 4, from either parity); single steps are enqueued kernel by kernel.
     Same state either way, also across a control line drawn between two launches."""
     from simfire_b200 import FireEngine
     from simfire_b200.workloads import synthetic_operational
@@ -281,7 +281,8 @@ def test_grouped_multi_step_launch_equals_single_steps(unit_skip):
     starts = wl.burnable_starts(E, seed=1, margin=3)
     res = []
     for plan in ([1] * 27, [5, 9, 4, 1, 8]):
-        with FireEngine(64, 200, E, shared_static=True, env_groups=3, unit_skip=unit_skip, keep_ros=True, **kw) as eng:
+        with FireEngine(64, 200, E, shared_static=True, env_groups=3, unit_skip=unit_skip, keep_ros=True,
+                        step_graph=True, **kw) as eng:
             eng.set_static(wl.planes)
             eng.reset(starts)
             done = 0

@@ -97,7 +97,7 @@ def main():
         total = sum(tot.values())
         shares = {k: {"launches": cnt[k], "total_ms": 1e3 * tot[k], "avg_us": 1e6 * tot[k] / cnt[k], "share": tot[k] / total}
                   for k in sorted(tot, key=lambda k: -tot[k])}  # fmt: skip
-        step = {k: v for k, v in tot.items() if "k_sweep" in k or "k_rows" in k or "k_eval" in k}
+        step = {k: v for k, v in tot.items() if any(t in k for t in ("k_sweep", "k_rows", "k_eval", "k_row_list", "k_units"))}
         st = sum(step.values())
         doc = {"source": os.path.basename(a.launches), "workload": a.workload, "command": a.command,
                "note": "ncu --metrics gpu__time_duration.sum: serialised, cold-cache launch times; compare shares",
