@@ -5,8 +5,9 @@
 stepper, plus `BatchedFireSimulation`, the same surface vectorised over E independent envs
 (one engine, one kernel launch per step for all of them).
 
-Always headless: rendering, GIF recording, spread-graph drawing and `save_data` are display /
-IO features outside the hot-path scope.
+Always headless: rendering, GIF recording and spread-graph drawing are display features
+outside the hot-path scope.  `save_data`
+(simulation.py:887-959) is kept: the per-update fire_map history is what downstream tooling reads.
 
 Unlike the drop-in manager (`fire_manager.RothermelFireManager.update`, which round-trips the
 caller's fire_map every call exactly like the reference), the simulation classes keep the map
@@ -15,7 +16,10 @@ one call, and the int64 host `fire_map` is materialised lazily when it is read.
 """
 from __future__ import annotations
 
+import json
 import warnings
+from datetime import datetime
+from pathlib import Path
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -57,6 +61,8 @@ class FireSimulation:
         self._rendering = False
         self.agents: Dict[int, Tuple[int, int]] = {}
         self._engine: Optional[FireEngine] = None
+        self.start_time = datetime.now().strftime("%Y-%m-%d_%H-%M-%S")  # simulation.py:56
+        self.sf_home = Path(self.config.simulation.sf_home).expanduser()
         self.reset()
 
     # -- lifecycle (simulation.py:202-214) ----------------------------------------------------
@@ -137,7 +143,9 @@ class FireSimulation:
         p = self._planes
         return {"w_0": p["w_0"].astype(np.float32), "sigma": p["sigma"].astype(np.uint32),
                 "delta": p["delta"].astype(np.float32), "M_x": p["M_x"].astype(np.float32),
-                "elevation": self._elevations, "wind_speed": self.config.wind.speed,
+                # the layer's own array, dtype included (simulation.py:401: int64 for `flat`, whose function returns 0)
+                "elevation": np.asarray(self.config.terrain.topography_layer.data).reshape(self._elevations.shape),
+                "wind_speed": self.config.wind.speed,
                 "wind_direction": self.config.wind.direction}  # fmt: skip
 
     # -- between-step mutations -------------------------------------------------------------------
@@ -173,7 +181,19 @@ class FireSimulation:
             total_updates = round(str_to_minutes(time) / self.config.simulation.update_rate)
         else:
             total_updates = int(time)
-        if self.fire_status == GameStatus.RUNNING and total_updates > 0:
+        if self.fire_status == GameStatus.RUNNING and total_updates > 0 and self.config.simulation.save_data:
+            # the history is written after every update (simulation.py:546-549): one step per launch
+            for _ in range(total_updates):
+                if self.fire_status != GameStatus.RUNNING:
+                    break
+                self._engine.step(1)
+                st, el, n = self._engine.status()
+                self.fire_status = GameStatus(int(st[0]))
+                self.elapsed_time = float(el[0])
+                self.elapsed_steps += 1  # counts update() calls, the one that returns QUIT included (:543)
+                self._fire_map = None
+                self._save_data()
+        elif self.fire_status == GameStatus.RUNNING and total_updates > 0:
             # envs that return QUIT stop advancing on the device, like the `while` loop of the reference
             self._engine.step(total_updates)
             st, el, n = self._engine.status()
@@ -183,6 +203,69 @@ class FireSimulation:
             self._fire_map = None
         self.active = self.fire_status == GameStatus.RUNNING
         return self.fire_map, self.active
+
+    # -- save_data (simulation.py:887-1106): metadata.json, the static layers once, and the fire_map
+    # history under <sf_home>/data/<start_time>/ in the configured data type ---------------------------
+    def _load_static_data(self, datapath: Path) -> Dict[str, object]:
+        dtype = self.config.simulation.data_type
+        data = self.get_attribute_data()
+        ext = {"npy": "npy", "h5": "h5", "json": "json", "jsonl": "json"}.get(dtype)
+        if ext is None:
+            raise ValueError(f"Invalid data type '{dtype}' given. Valid types are 'npy', 'h5', 'json', and 'jsonl'.")
+        data_locs = {k: f"{k}.{ext}" for k in data}
+        shape = data[list(data.keys())[0]].shape
+        for key, loc in data_locs.items():
+            path = datapath / loc
+            if path.is_file():
+                continue
+            if dtype == "npy":
+                np.save(path, data[key])
+            elif dtype == "h5":
+                import h5py  # optional, like in the reference's environment
+
+                with h5py.File(path, "w") as f:
+                    f.create_dataset("data", data=data[key])
+            else:
+                with open(path, "w") as f:
+                    json.dump({"data": data[key].tolist()}, f)
+        return {"data": data_locs, "shape": shape}
+
+    def _save_data(self) -> None:
+        dtype = self.config.simulation.data_type
+        ext = {"npy": "npy", "h5": "h5", "json": "jsonl", "jsonl": "jsonl"}.get(dtype)
+        if ext is None:
+            raise ValueError(f"Invalid data type '{dtype}' given. Valid types are 'npy', 'h5', 'json', and 'jsonl'.")
+        datapath = self.sf_home / "data" / self.start_time
+        datapath.mkdir(parents=True, exist_ok=True)
+        fire_map_path = datapath / f"fire_map.{ext}"
+        static = self._load_static_data(datapath)
+        metadata = {"config": self.config.yaml_data, "seeds": self.get_seeds(), "layer_types": self.get_layer_types(),
+                    "shape": static["shape"], "static_data": static, "fire_map": fire_map_path.name}  # fmt: skip
+        with open(datapath / "metadata.json", "w") as f:
+            json.dump(metadata, f, indent=2)
+        current = np.expand_dims(self.fire_map, axis=0)
+        if dtype in ("npy", "h5"):
+            previous = None
+            if fire_map_path.is_file():
+                if dtype == "npy":
+                    previous = np.load(fire_map_path)
+                else:
+                    import h5py
+
+                    previous = np.array(h5py.File(fire_map_path)["data"])
+                if previous.ndim == 2:
+                    previous = np.expand_dims(previous, axis=0)
+            history = current if previous is None else np.append(previous, current, axis=0)
+            if dtype == "npy":
+                np.save(fire_map_path, history.astype(np.int8))
+            else:
+                import h5py
+
+                with h5py.File(fire_map_path, "w") as f:
+                    f.create_dataset("data", data=history)
+        else:  # JSON Lines: one {elapsed_steps: fire_map} object per update
+            with open(fire_map_path, "a") as f:
+                f.write(json.dumps({self.elapsed_steps: self.fire_map.tolist()}) + "\n")
 
     # -- config mutation helpers the harness uses (simulation.py:574-829); like the reference they
     # only rewrite `self.config`: the change takes effect at the next reset() ----------------------------

@@ -94,6 +94,53 @@ def test_update_ignites_all_neighbours_when_pixel_scale_is_tiny():
         mgr.close()
 
 
+def test_new_locations_bounds_and_blocked_neighbours():
+    """test_fire.py:61-122 (`_get_new_locs`): a fire in a corner only reaches its in-bounds
+    neighbours, and a neighbour that is BURNED (or BURNING) is not a destination while UNBURNED
+    and the three control-line kinds are (`_filter_function`, fire.py:192-205).  The reference
+    test calls `_get_new_locs` directly; here one update with a tiny pixel_scale ignites exactly
+    the destinations, read back from the new Fire sprites in the reference's order
+    (sorted by (y, x), fire.py:566)."""
+    from simfire_b200.config import chaparral
+    from simfire_b200.fire_manager import RothermelFireManager
+    from simfire_b200.parameters import Environment, FuelParticle
+
+    size = 9
+
+    def run(init, blocked=(), lines=(), diagonal=True):
+        fuels = np.empty((size, size), dtype=object)
+        fuels.fill(chaparral(1113))
+        mgr = RothermelFireManager(init, 2, 4, 1e-3, 1.0, FuelParticle(), _terrain(size, size, fuels, np.zeros((size, size))),
+                                   Environment(0.03, 88.0, 135.0), headless=True, diagonal_spread=diagonal)  # fmt: skip
+        fm = np.zeros((size, size), dtype=np.int64)
+        fm[init[1], init[0]] = 1
+        for (x, y), k in list(blocked) + list(lines):
+            fm[y, x] = k
+        fm, _ = mgr.update(fm)
+        new = [xy for xy in mgr.sprites if tuple(xy) != tuple(init)]
+        mgr.close()
+        return new, fm
+
+    # too small: (0, 0) -> (x+1, y), (x+1, y+1), (x, y+1); listed in (y, x) order
+    new, _ = run((0, 0))
+    assert new == [(1, 0), (0, 1), (1, 1)]
+    # far corner -> its three in-bounds neighbours
+    new, _ = run((size - 1, size - 1))
+    assert new == [(size - 2, size - 2), (size - 1, size - 2), (size - 2, size - 1)]
+    # the cell at (x+1, y) is BURNED: all 8-connected points except that one
+    x = y = size // 2
+    new, fm = run((x, y), blocked=[((x + 1, y), 2)])
+    want = {(x + 1, y + 1), (x, y + 1), (x - 1, y + 1), (x - 1, y), (x - 1, y - 1), (x, y - 1), (x + 1, y - 1)}
+    assert set(new) == want and len(new) == 7 and fm[y, x + 1] == 2
+    # control lines of every kind are destinations (and ignite once their burn exceeds pixel_scale)
+    new, fm = run((x, y), lines=[((x + 1, y), 3), ((x, y + 1), 4), ((x - 1, y), 5)], diagonal=False)
+    assert set(new) == {(x, y - 1)}  # the three lines were attenuated below the threshold ...
+    assert fm[y, x + 1] == 3 and fm[y + 1, x] == 4 and fm[y, x - 1] == 5  # ... and stay lines
+    # 4-neighbour variant (fire.py:223-228)
+    new, _ = run((x, y), diagonal=False)
+    assert set(new) == {(x + 1, y), (x, y + 1), (x - 1, y), (x, y - 1)}
+
+
 def test_prune_after_max_fire_duration():
     """fire.py:116-161 timeline: the initial fire turns BURNED at the start of update max_dur + 1."""
     mgr = _simple_manager(pixel_scale=1e9, max_fire_duration=3)  # nothing else ever ignites
@@ -192,6 +239,52 @@ def test_simulation_run_until_burned_out():
     assert sim.elapsed_time == y["simulation"]["update_rate"] and active
     fm, active = sim.run("1h")
     assert fm.max() == 2 and not active
+    sim.close()
+
+
+def test_save_data_history_matches_reference(tmp_path):
+    """simulation.py:887-959 with `save_data: true`: the files written under
+    <sf_home>/data/<start_time>/ -- names, metadata.json, static layers, the int8 fire_map history
+    appended after every update -- against what the unmodified reference wrote for the same
+    config and calls (tests/golden/gen_savedata_golden.py); then the JSON-lines variant."""
+    import json
+
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/savedata_npy.npz")
+    cfg = yaml.safe_load(str(z["config_yaml"]))
+    cfg["simulation"]["sf_home"] = str(tmp_path / "home")
+    sim = FireSimulation(Config(config_dict=cfg))
+    sim.run(3)
+    sim.update_mitigation([(x, 30, 3) for x in range(5, 40)])
+    sim.run(4)
+    datapath = tmp_path / "home" / "data" / sim.start_time
+    assert sorted(p.name for p in datapath.iterdir()) == list(z["files"])
+    history = np.load(datapath / "fire_map.npy")
+    assert history.dtype == np.int8 and np.array_equal(history, z["fire_map"])
+    want, got = json.loads(str(z["metadata_json"])), json.load(open(datapath / "metadata.json"))
+    assert sorted(got) == sorted(want)
+    for key in ("fire_map", "layer_types", "seeds", "shape", "static_data"):
+        assert got[key] == want[key], key
+    for name in ("w_0", "sigma", "delta", "M_x", "elevation", "wind_speed", "wind_direction"):
+        a, b = np.load(datapath / f"{name}.npy"), z[f"static_{name}"]
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), name
+    sim.close()
+
+    cfg["simulation"]["data_type"] = "jsonl"
+    cfg["simulation"]["sf_home"] = str(tmp_path / "home2")
+    sim = FireSimulation(Config(config_dict=cfg))
+    sim.run(2)
+    lines = open(tmp_path / "home2" / "data" / sim.start_time / "fire_map.jsonl").read().splitlines()
+    assert [list(json.loads(ln))[0] for ln in lines] == ["1", "2"]
+    assert np.array_equal(np.array(json.loads(lines[1])["2"]), z["fire_map"][1])
+    assert json.load(open(tmp_path / "home2" / "data" / sim.start_time / "w_0.json"))["data"][0][0] == pytest.approx(float(z["static_w_0"][0, 0]))
+    sim.close()
+    cfg["simulation"]["data_type"] = "csv"
+    sim = FireSimulation(Config(config_dict=cfg))
+    with pytest.raises(ValueError, match="Invalid data type"):
+        sim.run(1)
     sim.close()
 
 
