@@ -141,6 +141,45 @@ def test_new_locations_bounds_and_blocked_neighbours():
     assert set(new) == {(x + 1, y), (x, y + 1), (x - 1, y), (x, y - 1)}
 
 
+def test_wind_conversion():
+    """test_fire.py:205-260: wind speed / direction given as a float, a nested sequence or an
+    array all become (H, W) arrays on the manager."""
+    size = 11
+    for U, U_dir in ((7.0, 90.0), ([[7.0] * size for _ in range(size)], [[90.0] * size for _ in range(size)]),
+                     (np.full((size, size), 7.0), np.full((size, size), 90.0))):  # fmt: skip
+        mgr = _simple_manager(size=size, U=U, U_dir=U_dir)
+        assert isinstance(mgr.U, np.ndarray) and isinstance(mgr.U_dir, np.ndarray)
+        assert mgr.U.shape == (size, size) and mgr.U_dir.shape == (size, size)
+        assert np.all(mgr.U == 7.0) and np.all(mgr.U_dir == 90.0)
+        mgr.close()
+
+
+def test_mitigation_points_land_in_fire_map_and_run_semantics():
+    """test_mitigation.py:65-100 (the points given to a control-line manager are exactly the cells
+    of that kind in the fire_map) and test_simulation.py:84-121 (`run("1h")` leaves burnt cells,
+    after `reset()` one update advances `elapsed_time` by `update_rate`)."""
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    cfg = yaml.safe_load(str(z["config_yaml"]))
+    sim = FireSimulation(Config(config_dict=cfg))
+    H, W = sim.config.area.screen_size
+    pts = [(i, H // 4 - i) for i in range(H // 4 + 1)]  # skimage.draw.line(H // 4, 0, 0, W // 4) as (x, y)
+    for kind in (3, 4, 5):
+        sim.reset()
+        sim.update_mitigation([(x, y, kind) for x, y in pts])
+        got = [(int(x), int(y)) for y, x in np.argwhere(sim.fire_map == kind)]
+        assert sorted(got) == sorted(pts)
+    sim.reset()
+    fire_map, _ = sim.run("1h")
+    assert fire_map.max() == 2 and fire_map.dtype == np.int64
+    sim.reset()
+    sim.run(1)
+    assert sim.elapsed_time == sim.config.simulation.update_rate and sim.elapsed_steps == 1
+    sim.close()
+
+
 def test_prune_after_max_fire_duration():
     """fire.py:116-161 timeline: the initial fire turns BURNED at the start of update max_dur + 1."""
     mgr = _simple_manager(pixel_scale=1e9, max_fire_duration=3)  # nothing else ever ignites
