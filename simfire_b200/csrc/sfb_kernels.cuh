@@ -1,10 +1,15 @@
 // Device side of the B200 fire-spread stepper: data layout + the three hot-path kernels.
 //
-// One timestep of RothermelFireManager.update (simfire/game/managers/fire.py:616-719) is
+// One timestep of RothermelFireManager.update (simfire/game/managers/fire.py:616-719) is a
+// front end followed by two front-proportional kernels:
 //
-//   k_sweep   streaming pass over the packed per-cell state (1 B/cell, TMA-fed): lists the
-//             warp-rows whose 3-row window holds a Fire sprite (or, with attenuation, a
-//             control line) as 8-byte row tasks.  HBM-bound; writes nothing else.
+//   front end lists the warp-rows (one row of one 512-byte strip of one env) whose 3-row window
+//             holds a Fire sprite (or, with attenuation, a control line) as 8-byte row tasks:
+//     k_row_list  (default from 1024 units up) compacts per-(env, row, strip) activity flags that
+//                 the other kernels keep up to date; no cell state is read at all;
+//     k_sweep     streaming pass over the packed per-cell state (1 B/cell, TMA-fed), over every
+//                 unit (dense: HBM-bound, at the copy roofline) or over the flagged chunks of
+//                 rows only (k_units compacts those flags first).  Writes nothing else.
 //   k_rows    one warp per row task: prune expired sprites (fire.py:116-161), find every
 //             ignitable cell that has a burning neighbour and the neighbour whose pair the
 //             reference writes last (fire.py:163-234, :704-705) with a warp-shuffle min, push
@@ -126,7 +131,7 @@ struct DevParams {
     // Row units (unit_rows != 0): a unit is one row of one strip (rows_per_chunk = 1, chunks = H).  Then the
     // flags ARE the row-task list: k_row_list compacts them straight into `rows`, no state is swept at
     // all, and k_rows lowers the flag of a row whose 3-row window holds nothing to look at.
-    int32_t unit_rows, pad_units;
+    int32_t unit_rows, unit_pad_;
     int64_t unit_stride;              // flags per env: chunks * strips (row units: rounded up to 4, pad flags unused)
     uint8_t* unit_act;                // [E * chunks * strips], nullptr = dense sweep over every unit
     uint32_t* units;                  // [n_units] this step's active units
