@@ -205,6 +205,9 @@ struct sfb_sim {
     int64_t last_entries;
     int last_overflow;
     // host mirror bookkeeping (sfb_sync_fire_maps)
+    long long patch_parallel_min;  // logs shorter than this are patched by the calling thread alone
+    int steps_since_sync;      // update() calls enqueued since the change logs were last drained
+    int setup_after_step;      // ... and a reset / mitigation call came after one of them
     const int8_t* mirror;      // buffer the last sync wrote, nullptr = none valid
     int full_resync;           // something changed that the log does not describe
     unsigned long long* log_head;    // pinned: {count, overflow} of every log, read back each sync
@@ -309,12 +312,12 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
     if (p.track) {  // "env was cleared", then its first burning cell, in this order
         const LogRef& L = log_of_env(p, env);
         const unsigned long long slot = atomicAdd(L.count, 2ULL);
-        const unsigned long long reset = (unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48);
+        const unsigned long long reset = (unsigned long long)env | ((unsigned long long)LOG_ENV_RESET << 48) | LOG_SETUP_BIT;
         const bool inside = y >= 0 && y < p.H;
         const long long idx = (long long)env * p.plane + (long long)(inside ? y : 0) * p.pitch + x;
         log_put(L, slot, reset);
         // a slab that does not hold the ignition row logs the reset twice (harmless)
-        log_put(L, slot + 1, inside ? ((unsigned long long)idx | (1ULL << 48)) : reset);
+        log_put(L, slot + 1, inside ? ((unsigned long long)idx | (1ULL << 48) | LOG_SETUP_BIT) : reset);
     }
 }
 
@@ -331,7 +334,7 @@ __global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int
     if (p.unit_act) mark_units_around<CellT>(p, env, y, x);  // a control line is work under attenuation
     if (p.track) {
         const LogRef& L = log_of_env(p, env);
-        log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48));
+        log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48) | LOG_SETUP_BIT);
     }
 }
 
@@ -712,6 +715,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
     // measured (profiles/r01b_bench_target_groupgraph.json): the graph joins the groups after every pair of
     // steps, which costs more overlap between groups than the saved launches give back -> opt-in
+    s->patch_parallel_min = 16384;
+    if (const char* e = getenv("SFB_PATCH_PARALLEL_MIN")) s->patch_parallel_min = std::max(1, atoi(e));  // tests
     s->group_graph_on = (prm->flags & SFB_STEP_GRAPH) ? 1 : 0;
     if (const char* e = getenv("SFB_GROUP_GRAPH")) s->group_graph_on = atoi(e) != 0;
 
@@ -978,6 +983,7 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     }
     int rc;
     if ((rc = use(s))) return rc;
+    if (s->steps_since_sync > 0) s->setup_after_step = 1;  // its log entries follow a step's
     const size_t need = (size_t)n * 3 * sizeof(int32_t);
     if ((rc = ensure_small(s, need))) return rc;
     int32_t* d_xy = s->small;
@@ -1012,6 +1018,7 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     }
     int rc;
     if ((rc = use(s))) return rc;
+    if (s->steps_since_sync > 0) s->setup_after_step = 1;  // its log entries follow a step's
     const size_t bytes = (size_t)n * 4 * sizeof(int32_t);
     if ((rc = ensure_small(s, bytes))) return rc;
     const bool staged = bytes <= PTS_STAGE_BYTES;  // per-step mitigation points: no device round trip
@@ -1318,6 +1325,7 @@ static int run_group_graph(sfb_sim* s) {
 static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
+    s->steps_since_sync = s->steps_since_sync > (1 << 20) ? s->steps_since_sync : s->steps_since_sync + n;
     int rc;
     // one view of all envs on the handle's stream: single-group handles and per-kernel timing
     if (s->groups.empty() || s->timing) {
@@ -1368,6 +1376,7 @@ extern "C" int sfb_step_sweep(sfb_sim* s) {
     { int rcm = enter_mode(s, 1); if (rcm) return rcm; }
     int rc;
     if ((rc = use(s))) return rc;
+    s->steps_since_sync += 2;  // half-steps driven from outside: always the ordered patch path
     if ((rc = enqueue_sweep(s))) return rc;
     CU(cudaGetLastError());
     return 0;
@@ -1417,6 +1426,7 @@ extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
     { int rcm = enter_mode(s, 1); if (rcm) return rcm; }
     int rc;
     if ((rc = use(s))) return rc;
+    s->steps_since_sync += 2;  // (see sfb_step_sweep)
     for (int i = 0; i < n_steps; ++i) {
         const uint32_t g = ++s->slab_step;
         if ((rc = enqueue_sweep(s))) return rc;
@@ -1586,8 +1596,11 @@ extern "C" int sfb_get_fire_map(sfb_sim* s, int32_t env0, int32_t n, int8_t* out
 // cell indices), keeping the order; (2) owner o applies bucket (0, o), (1, o), ... in chunk
 // order.  Each entry is touched twice in total, whatever T is.
 // [base, base + total): the cells this log can name (its env group); the owners split that range.
+// single_step: the log holds between-step entries (LOG_SETUP_BIT) followed by the entries of exactly one
+// step.  The step's entries name every cell at most once, so after the (few) setup entries have been
+// applied in order they are patched in parallel chunks, unsorted: one pass, no buckets, no barrier.
 static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, int8_t* mirror, unsigned long long base,
-                      unsigned long long total) {
+                      unsigned long long total, bool single_step = false) {
     const DevParams& d = s->d;
     const long long hw = (long long)d.H * d.W;
     const bool linear = d.pitch == d.W;
@@ -1611,7 +1624,24 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
                 if ((long long)((i - e0) % d.pitch) < d.W) put(i, 0);
         }
     };
-    const unsigned T = (n < 16384 || !s->pool) ? 1u : s->pool->size();
+    const unsigned T = (n < s->patch_parallel_min || !s->pool) ? 1u : s->pool->size();
+    if (single_step && T > 1) {
+        long long n_setup = 0;
+        bool resets = false;
+        while (n_setup < n && (log[n_setup] & LOG_SETUP_BIT)) {
+            resets |= ((int)(log[n_setup] >> 48) & 7) == LOG_ENV_RESET;
+            ++n_setup;
+        }
+        if (!resets) {  // (whole-env clears are spread over the owners by the ordered path below)
+            for (long long i = 0; i < n_setup; ++i) put(log[i] & 0xFFFFFFFFFFFFull, (int)(log[i] >> 48) & 7);
+            const long long m = n - n_setup;
+            s->pool->run([&](unsigned k) {
+                const long long i0 = n_setup + m * k / T, i1 = n_setup + m * (k + 1) / T;
+                for (long long i = i0; i < i1; ++i) put(log[i] & 0xFFFFFFFFFFFFull, (int)(log[i] >> 48) & 7);
+            });
+            return;
+        }
+    }
     if (T == 1) {
         for (long long i = 0; i < n; ++i) {
             const unsigned long long e = log[i], idx = e & 0xFFFFFFFFFFFFull;
@@ -1665,6 +1695,9 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     const double t0 = debug ? now_ms() : 0.0;
     const int nl = d.track ? d.n_logs : 0;
     const bool grouped = !s->groups.empty() && s->last_mode == 2;
+    const bool single_step = s->steps_since_sync == 1 && !s->setup_after_step;
+    s->steps_since_sync = 0;
+    s->setup_after_step = 0;
 
     if (!d.track || s->full_resync || s->mirror != mirror) {
         CU(cudaStreamSynchronize(s->stream));
@@ -1706,7 +1739,7 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
         const double tb = debug ? now_ms() : 0.0;
         if (cnt > 0)
             apply_log(s, s->log_mapped[g], (long long)cnt, mirror, (unsigned long long)d.log_e0[g] * d.plane,
-                      (unsigned long long)(d.log_e0[g + 1] - d.log_e0[g]) * d.plane);
+                      (unsigned long long)(d.log_e0[g + 1] - d.log_e0[g]) * d.plane, single_step);
         total += (long long)cnt;
         if (debug) {
             wait_ms += tb - ta;
@@ -1724,8 +1757,9 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     s->mirror = mirror;
     s->full_resync = 0;
     if (debug)
-        fprintf(stderr, "[sfb_sync] %d logs, %lld entries: waiting for the device %.3f ms, patching %.3f ms%s\n", nl, total,
-                wait_ms, patch_ms, overflow ? " (overflow: full download)" : "");
+        fprintf(stderr, "[sfb_sync] %d logs, %lld entries (%s): waiting for the device %.3f ms, patching %.3f ms%s\n", nl, total,
+                single_step ? "one step: one-pass patch" : "ordered two-pass patch", wait_ms, patch_ms,
+                overflow ? " (overflow: full download)" : "");
     return 0;
 }
 

@@ -246,6 +246,10 @@ __device__ __forceinline__ unsigned long long make_item(long long idx, int dir, 
 // idx | BurnStatus << 48 so that a host mirror of fire_map can be patched instead of
 // re-downloaded (sfb_sync_fire_maps).  BurnStatus 7 = "env idx was reset".  Warp-wide call.
 constexpr int LOG_ENV_RESET = 7;
+// bit 56 of a log entry: written by a between-step kernel (reset, mitigation) rather than by a step.
+// When one step follows them the host applies these few entries first, in order, and then patches
+// the step's entries -- no cell appears twice among those -- in parallel without sorting them.
+constexpr unsigned long long LOG_SETUP_BIT = 1ull << 56;
 __device__ __forceinline__ void log_append(const DevParams& p, bool have, long long idx, int burn_status) {
     const uint32_t m = __ballot_sync(0xffffffffu, have);
     if (!m) return;

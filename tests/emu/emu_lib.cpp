@@ -31,3 +31,26 @@ extern "C" long long sfb_emu_row_tasks(sfb_sim* s, int32_t* out, long long cap) 
     }
     return n;
 }
+
+// host-side microbenchmark hook (tests/emu/bench_patch.py): patch a synthetic change log into a
+// mirror with the library's own apply_log on `threads` pool threads; returns milliseconds per call
+extern "C" double sfb_emu_bench_apply_log(int H, int W, int E, const unsigned long long* log, long long n, int8_t* mirror,
+                                          int threads, int reps, int single_step) {
+    sfb_sim s{};
+    s.d.H = H;
+    s.d.W = W;
+    s.d.E = E;
+    s.d.pitch = (W + 15) / 16 * 16;
+    s.d.plane = (int64_t)H * s.d.pitch;
+    s.pool = new HostPool((unsigned)threads);
+    s.patch_parallel_min = 16384;
+    double best = 1e30;
+    for (int r = 0; r < reps; ++r) {
+        const double t0 = now_ms();
+        apply_log(&s, log, n, mirror, 0, (unsigned long long)E * s.d.plane, single_step != 0);
+        best = std::min(best, now_ms() - t0);
+    }
+    delete s.pool;
+    s.pool = nullptr;
+    return best;
+}

@@ -471,6 +471,49 @@ def test_incremental_host_mirror_matches_full_download(shape):
         assert np.array_equal(other, mirror)
 
 
+@pytest.mark.parametrize("groups", [1, 3])
+def test_parallel_mirror_patching_paths(groups, monkeypatch):
+    """The host side of sfb_sync_fire_maps on several threads, forced on for small logs: the
+    one-pass path taken when a single step follows the between-step calls (its entries name every
+    cell at most once) and the ordered two-pass path for everything else (several steps per sync, a
+    mitigation call after the step, resets).  The patched mirror must always equal a download."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    monkeypatch.setenv("SFB_PATCH_PARALLEL_MIN", "8")
+    monkeypatch.setenv("SFB_HOST_THREADS", "4")
+    H, W, E = 70, 90, 9
+    wl = synthetic_operational(H, W, seed=12, patch=8)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True, max_fire_duration=3)
+    rng = np.random.default_rng(4)
+    with FireEngine(H, W, E, shared_static=True, env_groups=groups, track_changes=True, **kw) as eng:
+        eng.set_static(wl.planes)
+        eng.reset(wl.burnable_starts(E, seed=2, margin=3))
+        mirror = np.zeros((E, H, W), np.int8)
+        eng.sync_fire_maps(mirror)  # first call: full download
+        patched = 0
+        for it in range(40):
+            pts = [(int(e), int(rng.integers(0, W)), int(rng.integers(0, H)), int(rng.integers(0, 6))) for e in range(E)]
+            # a cell drawn twice in one call, and a cell next to the fire that may ignite in the same step
+            pts += [(0, 5, 5, 3), (0, 5, 5, 5)]
+            mode = it % 5
+            if mode in (0, 1, 2):      # mitigation, one step, sync: the one-pass path
+                eng.apply_points(pts)
+                eng.step(1)
+            elif mode == 3:            # several steps per sync: ordered path
+                eng.apply_points(pts)
+                eng.step(3)
+            else:                      # a call after the step, and a reset of two envs: ordered path
+                eng.step(1)
+                eng.apply_points(pts)
+                if it % 10 == 4:
+                    eng.reset(wl.burnable_starts(2, seed=it, margin=3), envs=[1, 7])
+            n = eng.sync_fire_maps(mirror)
+            patched += max(0, n)
+            assert np.array_equal(mirror, eng.fire_map()), f"iteration {it} (mode {mode})"
+        assert patched > 2000  # the logs were really patched, not re-downloaded
+
+
 def test_observation_tensor_matches_host_map():
     import torch
 
