@@ -396,6 +396,12 @@ struct RowWorker {
     int* key_lut;    // [32] behind seg_lut
     int wcount = 0;  // warp-uniform
     int f_live = 0, f_cand = 0;
+#ifdef SFB_ROWS_V2  // experimental variant of k_rows, built and measured separately
+    uint32_t my_groups = 0;             // seg_lut[lane], kept in a register
+    const CellT* envbase = nullptr;     // first cell of the current env
+    const CellT* row_above = nullptr;   // what stands in for row -1 / row H of the current env
+    const CellT* row_below = nullptr;
+#endif
 
     __device__ __forceinline__ RowWorker(const DevParams& p_, int par_, int lane_, unsigned long long* wq_,
                                          const uint32_t* lut_)
@@ -419,6 +425,12 @@ struct RowWorker {
         spread = !m.time_quit;
         env_off = (long long)env * p.plane;
         build_key_lut();
+#ifdef SFB_ROWS_V2
+        const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;
+        envbase = reinterpret_cast<const CellT*>(p.state) + env_off;
+        row_above = p.halo_top ? reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane : filler;
+        row_below = p.halo_bottom ? reinterpret_cast<const CellT*>(p.halo_bottom) + (long long)env * p.halo_bottom_plane : filler;
+#endif
     }
 
     __device__ __forceinline__ void publish_flags() {
@@ -486,8 +498,12 @@ struct RowWorker {
         CellT* const state = reinterpret_cast<CellT*>(p.state);
         const long long row_idx = env_off + (long long)y * p.pitch;  // cell index of (y, x = 0)
         const int cells = min(W - x0, WR);  // columns of this strip that exist in the grid
+#ifdef SFB_ROWS_V2
+        uint32_t groups = __reduce_or_sync(0xffffffffu, ((act >> lane) & 1u) ? my_groups : 0u);  // one REDUX
+#else
         uint32_t groups = 0;
         for (uint32_t a = act; a; a &= a - 1) groups |= seg_lut[__ffs(a) - 1];  // warp-uniform
+#endif
         while (groups) {  // warp-uniform
             const int g = __ffs(groups) - 1;
             groups &= groups - 1;
@@ -901,6 +917,9 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
 
     RW::build_seg_lut(lut_all[warp], lane);
     RW rw(p, par, lane, wq_all[warp], lut_all[warp]);
+#ifdef SFB_ROWS_V2
+    rw.my_groups = lut_all[warp][lane];
+#endif
     CellT(*sm)[RS] = sm_all[warp];
     const int H = p.H, pitch = p.pitch;
     const long long plane = p.plane;
@@ -922,6 +941,43 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
             const unsigned long long task = p.rows[t];
             const int y = (int)(task & 0xFFFFFu), strip = (int)((task >> 20) & 0xFFu), env = (int)(task >> 28);
             if (env != rw.env) rw.set_env(env, p.meta[(long long)par * p.meta_stride + env]);
+#ifdef SFB_ROWS_V2
+            // variant: the env's base and edge rows come from set_env; lanes 0 / 31 fetch the 16 bytes left /
+            // right of the strip as one vector each and store it into the staged row's pad
+            const int x0 = strip * WR;
+            rw.x0 = x0;
+            const int xl = x0 + lane * CPL;
+            const bool in_x = xl < pitch;
+            const bool edge_lane = lane == 0 || lane == 31;
+            const bool hpred = (lane == 0 && strip > 0) || (lane == 31 && x0 + WR < pitch);
+            const int poff = lane == 0 ? x0 - CPL : x0 + WR;  // first cell of the pad vector in the row
+            const int pslot = lane == 0 ? 0 : CPL + WR;       // ... and in the staged row
+            const CellT* rowp[3];
+            rowp[1] = rw.envbase + (long long)y * pitch;
+            rowp[0] = y > 0 ? rowp[1] - pitch : rw.row_above;
+            rowp[2] = y + 1 < H ? rowp[1] + pitch : rw.row_below;
+            uint4 v[3], vp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                v[r] = make_uint4(C::FILL, C::FILL, C::FILL, C::FILL);
+                vp[r] = v[r];
+                if (in_x) v[r] = *reinterpret_cast<const uint4*>(rowp[r] + xl);
+                if (hpred) vp[r] = *reinterpret_cast<const uint4*>(rowp[r] + poff);
+            }
+            __syncwarp();  // the previous task's readers are done with the staging rows
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                *reinterpret_cast<uint4*>(&sm[r][CPL + lane * CPL]) = v[r];
+                if (edge_lane) *reinterpret_cast<uint4*>(&sm[r][pslot]) = vp[r];
+            }
+            __syncwarp();
+            const uint4 vo = make_uint4(v[0].x | v[1].x | v[2].x, v[0].y | v[1].y | v[2].y, v[0].z | v[1].z | v[2].z,
+                                        v[0].w | v[1].w | v[2].w);
+            // the one cell that touches the strip: the last of the left pad, the first of the right pad
+            const uint32_t hv = lane == 0 ? ((vp[0].w | vp[1].w | vp[2].w) >> (32 - 8 * (int)sizeof(CellT)))
+                                          : ((vp[0].x | vp[1].x | vp[2].x) & RW::CELL_ALL);
+            const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, edge_lane ? hv : 0u));
+#else
             const int x0 = strip * WR;
             rw.x0 = x0;
             const int xl = x0 + lane * CPL;
@@ -954,6 +1010,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
             const uint4 vo = make_uint4(v[0].x | v[1].x | v[2].x, v[0].y | v[1].y | v[2].y, v[0].z | v[1].z | v[2].z,
                                         v[0].w | v[1].w | v[2].w);
             const uint32_t act = __ballot_sync(0xffffffffu, rw.seg_needs_look(vo, h[0] | h[1] | h[2]));
+#endif
             // row units: nothing to look at in the 3-row window -> the row leaves the list until an
             // ignition, a control line or a map upload next to it flags it again
             if (p.unit_rows && act == 0 && lane == 0) p.unit_act[(long long)env * p.unit_stride + (long long)y * p.strips + strip] = 0;

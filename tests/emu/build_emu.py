@@ -14,17 +14,22 @@ DEPS = [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "emu_lib.cpp")] + [
 ] + [os.path.join(ROOT, "include", "simfire_b200.h")]
 
 
-def build(force: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(force: bool = False, extra=(), out=OUT) -> str:
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in DEPS):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     # -ffp-contract=off mirrors nvcc --fmad=false (the Rothermel arithmetic rounds after every operation)
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, "-o", OUT,
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, *extra, "-o", out,
            os.path.join(HERE, "emu_lib.cpp"), "-lpthread"]  # fmt: skip
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stderr)
-    return OUT
+    return out
+
+
+def build_variant(macro: str) -> str:
+    """The same library with -D<macro> (experimental kernel variants, e.g. SFB_ROWS_V2)."""
+    return build(extra=("-D" + macro,), out=os.path.join(HERE, "_build", f"libsfb_emu_{macro.lower()}.so"))
 
 
 if __name__ == "__main__":

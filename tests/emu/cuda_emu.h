@@ -190,6 +190,11 @@ static inline void __syncthreads() { emu::block_sync(); }
 static inline uint32_t __ballot_sync(uint32_t, bool pred) { return emu::ballot(pred, 2); }
 static inline int __any_sync(uint32_t, bool pred) { return emu::ballot(pred, 3) != 0; }
 static inline int __all_sync(uint32_t, bool pred) { return emu::ballot(!pred, 4) == 0; }
+static inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) {
+    uint32_t r = 0;
+    for (int b = 0; b < 32; ++b) r |= (emu::ballot((v >> b) & 1u, 9 + b) != 0 ? 1u : 0u) << b;  // 32 votes: slow, simple
+    return r;
+}
 template <class T>
 static inline T __shfl_sync(uint32_t, T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");

@@ -69,6 +69,20 @@ def test_small_scale_cases_under_emulation():
     assert " passed" in out
 
 
+def test_experimental_k_rows_variant_under_emulation():
+    """-DSFB_ROWS_V2 (one REDUX for the group mask, 16-byte pad vectors instead of single halo cells,
+    per-env base pointers cached): not the default -- it needs 12-16 more registers and has not been
+    measured on a B200 yet -- but it has to stay correct so that it can be A/B'd."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    from build_emu import build_variant
+
+    env = dict(os.environ, SFB_LIB=build_variant("SFB_ROWS_V2"), SFB_EMULATED="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gpu_parity.py",
+           "-k", "golden_trajectory or random_scenarios or unit_skipping"]  # fmt: skip
+    res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, "\n".join((res.stdout + res.stderr).splitlines()[-25:])
+
+
 def _emu_env():
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     from build_emu import build
