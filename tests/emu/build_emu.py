@@ -32,5 +32,15 @@ def build_variant(macro: str) -> str:
     return build(extra=("-D" + macro,), out=os.path.join(HERE, "_build", f"libsfb_emu_{macro.lower()}.so"))
 
 
+def build_asan() -> str:
+    """AddressSanitizer build: device allocations get their exact size, so a kernel (or host) access
+    one byte past a plane, list or flag array aborts the test.  Load with LD_PRELOAD=libasan."""
+    return build(extra=("-fsanitize=address", "-fno-omit-frame-pointer"), out=os.path.join(HERE, "_build", "libsfb_emu_asan.so"))
+
+
+def asan_runtime() -> str:
+    return subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+
+
 if __name__ == "__main__":
     print(build(force=True))

@@ -257,7 +257,12 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     return cudaSuccess;
 }
 static inline cudaError_t cudaMalloc(void** p, size_t bytes) {
+#if defined(__SANITIZE_ADDRESS__)
+    // exact size, so that AddressSanitizer's red zone starts at the first byte past the allocation
+    if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) *p = nullptr;
+#else
     *p = aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+#endif
     if (*p) memset(*p, 0xA5, bytes);  // device memory is not zero-initialised
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }

@@ -83,6 +83,25 @@ def test_experimental_k_rows_variant_under_emulation():
     assert res.returncode == 0, "\n".join((res.stdout + res.stderr).splitlines()[-25:])
 
 
+def test_parity_under_address_sanitizer():
+    """The emulator build with -fsanitize=address and exact-size "device" allocations: any kernel or
+    host access past the end of a plane, work list, row-task list, flag array or change log aborts.
+    (A subset here to keep the CPU suite short; the whole emulated GPU suite, also with unit
+    skipping forced on for every handle, is clean: profiles/r01b_emu_asan.txt.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    from build_emu import asan_runtime, build_asan
+
+    rt = asan_runtime()
+    if not os.path.exists(rt):
+        pytest.skip("libasan is not installed")
+    env = dict(os.environ, SFB_LIB=build_asan(), SFB_EMULATED="1", LD_PRELOAD=rt,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1")  # fmt: skip
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gpu_parity.py",
+           "-k", "golden_trajectory or parallel_mirror or grouped_multi_step"]  # fmt: skip
+    res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, "\n".join((res.stdout + res.stderr).splitlines()[-25:])
+
+
 def _emu_env():
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     from build_emu import build
