@@ -152,9 +152,12 @@ def _crop_start(wl, crop: int, seed: int):
             return (x, y)
 
 
-def cpu_baseline_leg(wl, budget_s: float = 12.0):
-    """One host core, one env of the full grid, as many steps as fit the budget."""
-    sim = _oracle_sim(wl, min(wl.H, wl.W), _crop_start(wl, min(wl.H, wl.W), 1))
+def cpu_baseline_leg(wl, budget_s: float = 12.0, gpu_check=None):
+    """One host core, one env of the full grid, as many steps as fit the budget.  `gpu_check(start,
+    steps)` returns the device's fire_map for the same env after the same number of updates: the
+    oracle is the checker here (parity in the same run)."""
+    start = _crop_start(wl, min(wl.H, wl.W), 1)
+    sim = _oracle_sim(wl, min(wl.H, wl.W), start)
     sim.step()  # warm-up (first call pays NumPy dispatch caches)
     n, t0 = 0, time.perf_counter()
     while True:
@@ -164,8 +167,13 @@ def cpu_baseline_leg(wl, budget_s: float = 12.0):
         if dt > budget_s or n >= 400:
             break
     side = min(wl.H, wl.W)
-    return {"value": side * side * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle/dense_numpy.py, 1 env of {side}x{side} of the bench terrain, {n} steps in {dt:.1f} s"}  # fmt: skip
+    out = {"value": side * side * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"oracle/dense_numpy.py, 1 env of {side}x{side} of the bench terrain, {n} steps in {dt:.1f} s"}  # fmt: skip
+    if gpu_check is not None and side == wl.H == wl.W:
+        got = gpu_check(start, n + 1)
+        out["parity"] = {"updates": n + 1, "start": list(start), "fire_map_equal": bool(np.array_equal(got, sim.status)),
+                         "cells_burning_or_burned": int((sim.status == 1).sum() + (sim.status == 2).sum())}  # fmt: skip
+    return out
 
 
 def _ref_worker(args):
@@ -556,7 +564,15 @@ def gpu_arm(args):
         "sanity": {"envs_running": running, "burned_cells_first_envs": burned, "steps_done_env0": int(nsteps[0])},
     }  # fmt: skip
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_budget)
+        def gpu_check(start, updates):  # the same env, from the same ignition cell, on the device
+            with FireEngine(H, W, 1, shared_static=True, device=local, **wl.engine_kwargs()) as one:
+                one.set_static(wl.planes)
+                one.reset([start])
+                one.step(updates)
+                return one.fire_map(0, 1)[0]
+
+        eng.close()  # the batch's 43 GB are not needed any more
+        line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_budget, gpu_check)
     print(json.dumps(line), flush=True)
     ctx.close()
 

@@ -118,7 +118,7 @@ def test_bench_gpu_arm_dry_run_under_emulation():
     for skip in ("on", "off"):
         res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dry_run.py"), "--workload", "small",
                               "--steps", "3", "--warmup", "3", "--burn-in", "5", "--roofline-steps", "2", "--e2e-steps", "3",
-                              "--no-cpu-baseline", "--unit-skip", skip],
+                              *(["--no-cpu-baseline"] if skip == "off" else ["--cpu-budget", "1"]), "--unit-skip", skip],
                              cwd=ROOT, env=_emu_env(), capture_output=True, text=True, timeout=600)  # fmt: skip
         assert res.returncode == 0, res.stderr[-2000:]
         line = json.loads(res.stdout.strip().splitlines()[-1])
@@ -133,6 +133,8 @@ def test_bench_gpu_arm_dry_run_under_emulation():
         assert rf["unit_skipping"]["on"] == (skip == "on")
         if skip == "off":
             assert rf["unit_skipping"]["units_listed"] == rf["unit_skipping"]["units_total"]
+        else:  # the CPU leg also checks the device against the oracle on the env it timed
+            assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["parity"]["fire_map_equal"] is True
 
 
 def test_smoke_under_emulation():
