@@ -330,6 +330,58 @@ def gpu_arm_slab(args):
     ctx.close()
 
 
+def full_burn_arm(args):
+    """`--full-burn` ("also report a full-burn run for cfg1-2"): one env from its
+    configured ignition cell until the reference's loop would stop (GameStatus.QUIT), launched in
+    blocks of 64 updates; device-timed.  cfg1 is also replayed on the NumPy oracle and compared."""
+    import torch
+
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import cfg1_functional_flat, synthetic_operational
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the stepper has no CPU path")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    wl = cfg1_functional_flat(128) if args.workload == "cfg1" else synthetic_operational(1024, 1024, seed=0)
+    with FireEngine(wl.H, wl.W, 1, device=local, **wl.engine_kwargs()) as eng:
+        eng.set_static(wl.planes)
+        eng.reset([wl.init_pos])
+        eng.step(3)  # warm-up launches (the fire is three updates old when the clock starts)
+        ms, updates = 0.0, 3
+        with ClockSampler(local) as clocks:
+            while True:
+                ms += eng.step_timed(64)
+                st, el, n = eng.status()
+                updates = int(n[0])
+                if not st[0] or updates > 200000:
+                    break
+        final = eng.fire_map(0, 1)[0]
+        line = {"metric": METRIC, "value": wl.H * wl.W * (updates - 3) / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                "steps": updates - 3, "warmup": 3, "ms_per_step": ms / max(1, updates - 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32/f64", "data": "synthetic",
+                "config": {"workload": args.workload + " full burn", "grid": [wl.H, wl.W], "envs_total": 1,
+                           "terrain": wl.description, "start": list(wl.init_pos),
+                           "note": "updates until GameStatus.QUIT, enqueued 64 at a time; an env that has quit is "
+                                   "skipped by the kernels, so the last block is partly idle"},
+                "clocks": clocks.summary(), "gpu_launches": int(eng.launch_counts()[1]),
+                "result": {"updates_until_quit": updates, "elapsed_time_min": float(el[0]),
+                           "burned_cells": int((final == 2).sum()), "unburned_cells": int((final == 0).sum())}}  # fmt: skip
+    if args.workload == "cfg1":
+        sim = _oracle_sim(wl, wl.H, wl.init_pos)
+        t0 = time.perf_counter()
+        while sim.step() == 1:
+            pass
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": wl.H * wl.W * sim.step_count / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"oracle/dense_numpy.py, the same full burn: {sim.step_count} updates in {dt:.1f} s",
+                                "parity": {"fire_map_equal": bool(np.array_equal(final, sim.status)),
+                                           "updates_equal": sim.step_count == updates}}  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
 def gpu_arm(args):
     import torch
 
@@ -583,7 +635,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="target", choices=["target", "cfg3", "cfg3_perenv", "cfg2", "small", "cfg5"])
+    ap.add_argument("--workload", default="target", choices=["target", "cfg3", "cfg3_perenv", "cfg2", "small", "cfg5", "cfg1"])
+    ap.add_argument("--full-burn", action="store_true", help="cfg1 / cfg2: one env from ignition until GameStatus.QUIT")
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--burn-in", type=int, default=60)
     ap.add_argument("--rows-per-chunk", type=int, default=0)
@@ -604,7 +657,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.full_burn or args.workload == "cfg1":
+        if args.workload not in ("cfg1", "cfg2"):
+            raise SystemExit("--full-burn is defined for --workload cfg1 and cfg2")
+        full_burn_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     elif args.workload == "cfg5":
         gpu_arm_slab(args)

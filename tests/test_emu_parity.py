@@ -137,6 +137,19 @@ def test_bench_gpu_arm_dry_run_under_emulation():
             assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["parity"]["fire_map_equal"] is True
 
 
+def test_bench_full_burn_dry_run_under_emulation():
+    """`bench.py --workload cfg1 --full-burn` (BASELINE config 1 until GameStatus.QUIT), checked
+    against the oracle inside the bench itself."""
+    import json
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dry_run.py"), "--workload", "cfg1",
+                          "--full-burn"], cwd=ROOT, env=_emu_env(), capture_output=True, text=True, timeout=600)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["result"]["unburned_cells"] == 0 and line["result"]["burned_cells"] == 128 * 128
+    assert line["cpu_baseline"]["parity"] == {"fire_map_equal": True, "updates_equal": True}
+
+
 def test_smoke_under_emulation():
     res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_emu_env(),
                          capture_output=True, text=True, timeout=600)  # fmt: skip
