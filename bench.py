@@ -574,7 +574,14 @@ def gpu_arm(args):
         "config": {
             "workload": args.workload, "grid": [H, W], "envs_per_gpu": E, "envs_total": E * world,
             "static_planes": "shared" if shared else "per-env", "terrain": wl.description,
-            "burn_in_steps": args.burn_in, "l2": "state plane per GPU (%.0f MB) exceeds the 126 MB L2" % (cells_rank / 1e6),
+            "burn_in_steps": args.burn_in,
+            "l2": ("state plane per GPU (%.0f MB) exceeds the 126 MB L2" % (cells_rank / 1e6)) if unit_mode == "dense" else
+                  ("no flush: a step touches %.0f MB of rows, records and burn values that change from step to step "
+                   "(row tasks x 1.5 KB + work items x 72 B) %s the 126 MB L2; the %.1f MB of activity flags are re-read "
+                   "every step and stay in L2, as they would in production"
+                   % ((rows_bytes + eval_bytes + sweep_cells) / 1e6,
+                      "- more than" if rows_bytes + eval_bytes + sweep_cells > 126e6 else "- LESS than",
+                      units_total / 1e6)),
             "parallelism": f"env-sharded x{world}, no collective",
         },
         "clocks": clocks.summary(),
