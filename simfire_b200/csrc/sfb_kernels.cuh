@@ -396,8 +396,19 @@ struct RowWorker {
     int* key_lut;    // [32] behind seg_lut
     int wcount = 0;  // warp-uniform
     int f_live = 0, f_cand = 0;
-#ifdef SFB_ROWS_V2  // experimental variant of k_rows, built and measured separately
+    // experimental variants of k_rows, built and measured separately:
+    // -DSFB_ROWS_REDUX (group mask with one REDUX), -DSFB_ROWS_PADVEC (16-byte pad vectors and per-env
+    // cached row pointers), -DSFB_ROWS_V2 = both
+#if defined(SFB_ROWS_V2) && !defined(SFB_ROWS_REDUX)
+#define SFB_ROWS_REDUX
+#endif
+#if defined(SFB_ROWS_V2) && !defined(SFB_ROWS_PADVEC)
+#define SFB_ROWS_PADVEC
+#endif
+#ifdef SFB_ROWS_REDUX
     uint32_t my_groups = 0;             // seg_lut[lane], kept in a register
+#endif
+#ifdef SFB_ROWS_PADVEC
     const CellT* envbase = nullptr;     // first cell of the current env
     const CellT* row_above = nullptr;   // what stands in for row -1 / row H of the current env
     const CellT* row_below = nullptr;
@@ -425,7 +436,7 @@ struct RowWorker {
         spread = !m.time_quit;
         env_off = (long long)env * p.plane;
         build_key_lut();
-#ifdef SFB_ROWS_V2
+#ifdef SFB_ROWS_PADVEC
         const CellT* const filler = reinterpret_cast<const CellT*>(p.filler) + CPL;
         envbase = reinterpret_cast<const CellT*>(p.state) + env_off;
         row_above = p.halo_top ? reinterpret_cast<const CellT*>(p.halo_top) + (long long)env * p.halo_top_plane : filler;
@@ -498,7 +509,7 @@ struct RowWorker {
         CellT* const state = reinterpret_cast<CellT*>(p.state);
         const long long row_idx = env_off + (long long)y * p.pitch;  // cell index of (y, x = 0)
         const int cells = min(W - x0, WR);  // columns of this strip that exist in the grid
-#ifdef SFB_ROWS_V2
+#ifdef SFB_ROWS_REDUX
         uint32_t groups = __reduce_or_sync(0xffffffffu, ((act >> lane) & 1u) ? my_groups : 0u);  // one REDUX
 #else
         uint32_t groups = 0;
@@ -917,7 +928,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
 
     RW::build_seg_lut(lut_all[warp], lane);
     RW rw(p, par, lane, wq_all[warp], lut_all[warp]);
-#ifdef SFB_ROWS_V2
+#ifdef SFB_ROWS_REDUX
     rw.my_groups = lut_all[warp][lane];
 #endif
     CellT(*sm)[RS] = sm_all[warp];
@@ -941,7 +952,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
             const unsigned long long task = p.rows[t];
             const int y = (int)(task & 0xFFFFFu), strip = (int)((task >> 20) & 0xFFu), env = (int)(task >> 28);
             if (env != rw.env) rw.set_env(env, p.meta[(long long)par * p.meta_stride + env]);
-#ifdef SFB_ROWS_V2
+#ifdef SFB_ROWS_PADVEC
             // variant: the env's base and edge rows come from set_env; lanes 0 / 31 fetch the 16 bytes left /
             // right of the strip as one vector each and store it into the staged row's pad
             const int x0 = strip * WR;
