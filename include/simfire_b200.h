@@ -19,6 +19,12 @@
  * message of the last failure on the calling thread is sfb_last_error().  Nothing throws.
  * Threading: calls on one handle must be serialised by the caller (the reference is
  * single-threaded); different handles are independent.
+ *
+ * Environment variables read by sfb_create / sfb_sync_fire_maps (measurement and test knobs; none of
+ * them changes a result): SFB_UNIT_SKIP=0|1, SFB_UNIT_ROWS=0|1, SFB_GROUP_GRAPH=0|1 override the
+ * corresponding sfb_flags; SFB_SWEEP_BLOCKS_PER_SM=n; SFB_HOST_THREADS=n (threads that patch the host
+ * mirror, default: all cores); SFB_PATCH_PARALLEL_MIN=n (shortest log patched by several threads);
+ * SFB_DEBUG_TIMING=1 (sfb_sync_fire_maps prints where its time went).
  */
 #ifndef SIMFIRE_B200_H
 #define SIMFIRE_B200_H
