@@ -154,3 +154,51 @@ def test_smoke_under_emulation():
     res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_emu_env(),
                          capture_output=True, text=True, timeout=600)  # fmt: skip
     assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-1000:] + res.stderr[-2000:]
+
+
+def test_log_patching_orders_entries_of_one_cell():
+    """The host side of sfb_sync_fire_maps (apply_log in sfb.cu, called directly through the emulator
+    build's test hook) on adversarial logs: many entries per cell with alternating states and env
+    resets in between must end as if applied one by one in log order (the two-pass path on several
+    threads); a setup prefix followed by unique cells must as well (the one-pass path)."""
+    import ctypes as C
+
+    import numpy as np
+
+    lib = C.CDLL(_emu_env()["SFB_LIB"])
+    lib.sfb_emu_bench_apply_log.restype = C.c_double
+    H, W, E = 37, 48, 6  # pitch == W (linear plane)
+    rng = np.random.default_rng(3)
+    n = 60000
+    cells = rng.integers(0, E * H * W, n).astype(np.uint64)
+    hot = rng.integers(0, E * H * W, 40).astype(np.uint64)  # a few cells that change again and again
+    pick = rng.random(n) < 0.4
+    cells[pick] = hot[rng.integers(0, len(hot), int(pick.sum()))]
+    states = rng.integers(0, 6, n).astype(np.uint64)
+    log = cells | (states << np.uint64(48))
+    resets = np.sort(rng.choice(n, 25, replace=False))
+    log[resets] = rng.integers(0, E, len(resets)).astype(np.uint64) | (np.uint64(7) << np.uint64(48))  # LOG_ENV_RESET
+    want = np.full(E * H * W, 9, np.int8)
+    for e in log:
+        idx, st = int(e) & 0xFFFFFFFFFFFF, (int(e) >> 48) & 7
+        if st == 7:
+            want[idx * H * W : (idx + 1) * H * W] = 0
+        else:
+            want[idx] = st
+    for threads in (1, 3, 4):
+        got = np.full(E * H * W, 9, np.int8)
+        lib.sfb_emu_bench_apply_log(H, W, E, C.c_void_p(log.ctypes.data), C.c_longlong(n), C.c_void_p(got.ctypes.data), threads, 1, 0)
+        assert np.array_equal(got, want), f"ordered path, {threads} threads"
+    # one-pass path: setup entries (bit 56) first, duplicates allowed among them; then every cell at most once
+    uniq = rng.permutation(E * H * W)[:30000].astype(np.uint64)
+    step = uniq | (rng.integers(1, 3, len(uniq)).astype(np.uint64) << np.uint64(48))
+    setup_cells = np.concatenate([uniq[:200], uniq[:200]])  # also cells the step changes afterwards
+    setup = setup_cells | (rng.integers(0, 6, len(setup_cells)).astype(np.uint64) << np.uint64(48)) | (np.uint64(1) << np.uint64(56))
+    log2 = np.concatenate([setup, step])
+    want2 = np.full(E * H * W, 9, np.int8)
+    for e in log2:
+        want2[int(e) & 0xFFFFFFFFFFFF] = (int(e) >> 48) & 7
+    for threads in (2, 4):
+        got = np.full(E * H * W, 9, np.int8)
+        lib.sfb_emu_bench_apply_log(H, W, E, C.c_void_p(log2.ctypes.data), C.c_longlong(len(log2)), C.c_void_p(got.ctypes.data), threads, 1, 1)
+        assert np.array_equal(got, want2), f"one-pass path, {threads} threads"
