@@ -202,3 +202,16 @@ def test_log_patching_orders_entries_of_one_cell():
         got = np.full(E * H * W, 9, np.int8)
         lib.sfb_emu_bench_apply_log(H, W, E, C.c_void_p(log2.ctypes.data), C.c_longlong(len(log2)), C.c_void_p(got.ctypes.data), threads, 1, 1)
         assert np.array_equal(got, want2), f"one-pass path, {threads} threads"
+    # padded rows (pitch 64 > W 50): log indices address the padded plane, the mirror is dense
+    H, W, E, pitch = 21, 50, 5, 64
+    n = 40000
+    env, y, x = rng.integers(0, E, n), rng.integers(0, H, n), rng.integers(0, W, n)
+    st = rng.integers(0, 6, n)
+    log3 = ((env * H + y) * pitch + x).astype(np.uint64) | (st.astype(np.uint64) << np.uint64(48))
+    want3 = np.full((E, H, W), 9, np.int8)
+    for e_, y_, x_, s_ in zip(env, y, x, st):
+        want3[e_, y_, x_] = s_
+    for threads in (1, 4):
+        got = np.full((E, H, W), 9, np.int8)
+        lib.sfb_emu_bench_apply_log(H, W, E, C.c_void_p(log3.ctypes.data), C.c_longlong(n), C.c_void_p(got.ctypes.data), threads, 1, 0)
+        assert np.array_equal(got, want3), f"padded rows, {threads} threads"
