@@ -612,7 +612,8 @@ def gpu_arm(args):
             "bytes_per_launch": kernel_bytes[dominant], "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank,
             "ms_per_launch": dom_s * 1e3, "share_of_step": dom_s / (sweep_s + rows_s + eval_s),
             "dense_sweep_reference": "without unit skipping the step is one 1 B/cell TMA sweep at 1.08 of the measured "
-                                     "HBM copy bandwidth (profiles/r01b_bench_target_dense.json, r01_kernels.json)",
+                                     "HBM copy bandwidth (profiles/r01b_bench_target_dense.json, r01_kernels.json); "
+                                     "`dense_sweep` below is that sweep timed in this run",
             "row_tasks_per_step": row_tasks, "work_items_per_step": q_entries, "queue_overflowed": q_ovf,
             "survey_model": {"bytes_per_cell_update": survey_b,
                              "achieved": cells_rank * survey_b / (sweep_s + rows_s + eval_s) / 1e9,
@@ -631,7 +632,31 @@ def gpu_arm(args):
                 return one.fire_map(0, 1)[0]
 
         eng.close()  # the batch's 43 GB are not needed any more
+        eng = None
         line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_budget, gpu_check)
+    if world == 1 and skipping and not args.no_dense_reference and args.workload != "cfg3_perenv":
+        # the HBM-bound kernel of the design, measured live beside the front-proportional ones: the same
+        # batch stepped with unit skipping off, i.e. the 1 B/cell TMA sweep over every cell
+        if eng is not None:
+            eng.close()
+        with FireEngine(H, W, E, shared_static=shared, device=local, unit_skip=False, sweep_ldg=(args.sweep == "ldg"),
+                        env_groups=args.env_groups, **wl.engine_kwargs()) as dense:  # fmt: skip
+            dense.set_static(wl.planes)
+            dense.reset(starts)
+            dense.step(args.burn_in)
+            dense.set_kernel_timing(True)
+            dense.step(max(2, min(10, args.roofline_steps)))
+            d_sweep, d_rows, d_eval, d_n = dense.kernel_ms()
+            d_tasks, _ = dense.row_tasks()
+        d_bytes = cells_rank * 1.0 + d_tasks * 8.0
+        d_s = d_sweep / d_n * 1e-3
+        line["roofline"]["dense_sweep"] = {
+            "kernel": "k_sweep_" + args.sweep, "bound": "hbm", "ms_per_launch": d_s * 1e3, "bytes_per_launch": d_bytes,
+            "achieved": d_bytes / d_s / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": d_bytes / d_s / 1e9 / peak_gbs,
+            "traffic": load_traffic_note(args.workload, "k_sweep_" + args.sweep)[0],
+            "note": "the same batch with unit skipping off (every cell's state byte streamed once per step), at update "
+                    f"{args.burn_in + 1}+: the front end small handles and slab mode use",
+        }
     print(json.dumps(line), flush=True)
     ctx.close()
 
@@ -657,6 +682,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense-reference", action="store_true",
+                    help="skip the extra pass that times the dense TMA sweep beside the default front end")
     ap.add_argument("--slab-sync", default="p2p", choices=["p2p", "nccl"], help="cfg5: how the slabs agree per step")
     ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
     ap.add_argument("--mirror", default="pinned", choices=["pinned", "thp"],

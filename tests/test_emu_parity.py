@@ -135,6 +135,8 @@ def test_bench_gpu_arm_dry_run_under_emulation():
             assert rf["unit_skipping"]["units_listed"] == rf["unit_skipping"]["units_total"]
         else:  # the CPU leg also checks the device against the oracle on the env it timed
             assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["parity"]["fire_map_equal"] is True
+            ds = rf["dense_sweep"]  # ... and the dense TMA sweep is timed beside the default front end
+            assert ds["bound"] == "hbm" and ds["kernel"].startswith("k_sweep") and ds["bytes_per_launch"] >= 256 * 256 * 64
 
 
 def test_bench_full_burn_dry_run_under_emulation():
