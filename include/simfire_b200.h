@@ -296,6 +296,10 @@ int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total, int32_t* m
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and
  * whether the step overflowed the queue and ran the dense fallback. */
 int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32_t* overflowed);
+/* Test knob: enqueue a kernel that keeps the handle's stream busy for `microseconds` (at most 1 s)
+ * before whatever is called next on it.  The GPU tests use it to widen the window of stream-ordering
+ * races (a between-step call that is still running when the next call reads what it wrote). */
+int sfb_debug_stall(sfb_sim* sim, int32_t microseconds);
 /* Bytes of device memory held by the handle. */
 int sfb_device_bytes(sfb_sim* sim, int64_t* bytes);
 

@@ -28,7 +28,7 @@ EXPORTS = (
     "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
     "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
     "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab", "sfb_set_tracking",
-    "sfb_set_elevation", "sfb_get_row_tasks", "sfb_get_unit_stats",
+    "sfb_set_elevation", "sfb_get_row_tasks", "sfb_get_unit_stats", "sfb_debug_stall",
 )  # fmt: skip
 
 
@@ -106,6 +106,7 @@ def load() -> C.CDLL:
         "sfb_get_unit_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_get_queue_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_device_bytes": (C.c_int, [vp, C.POINTER(i64)]),
+        "sfb_debug_stall": (C.c_int, [vp, i32]),
         "sfb_rate_of_spread": (C.c_int, [i32, vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in proto.items():

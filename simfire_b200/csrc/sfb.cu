@@ -497,6 +497,21 @@ __global__ void k_derive_static(DevParams p, long long n_cells) {
     }
 }
 
+// test / measurement knob (sfb_debug_stall): keeps the handle's stream busy for a while, so that a
+// missing ordering between it and another stream shows up as a wrong result instead of passing by luck
+__global__ void k_stall(long long ns) {
+#ifndef SFB_EMU
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while ((long long)(t - t0) < ns);
+#else
+    (void)ns;
+#endif
+}
+
 __global__ void k_rate_of_spread(const int8_t* dir, const float* rec, SfbParticle fp, long long n, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sfb_rate_of_spread_pair(dir[i], rec + 8 * i, fp);
@@ -1720,17 +1735,21 @@ extern "C" int sfb_sync_fire_maps(sfb_sim* s, int8_t* mirror, int64_t* n_changes
     long long total = 0;
     bool overflow = false;
     double wait_ms = 0, patch_ms = 0;
+    const bool per_group_heads = grouped && heads_ready;
+    if (!per_group_heads) {
+        // Something ran after the last grouped step (a mitigation / reset kernel on the handle's stream
+        // may still be appending to any log), or the steps ran on the handle's stream in the first place:
+        // fetch every head on the handle's stream, which is ordered after all of it (it joined every
+        // group's `done` event when the steps were enqueued).  A group stream is NOT ordered after the
+        // setup kernels, so a head read there could miss their entries -- which the reset of the
+        // counters below would then drop for good.
+        CU(cudaMemcpyAsync(s->log_head, s->log_counts, (size_t)nl * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     for (int g = 0; g < nl && !overflow; ++g) {
         const double ta = debug ? now_ms() : 0.0;
-        cudaStream_t st = s->stream;
-        if (grouped) {
-            CU(cudaEventSynchronize(s->groups[g].done));
-            st = s->groups[g].last_stream ? s->groups[g].last_stream : s->groups[g].stream;
-        }
-        if (!(grouped && heads_ready)) {
-            CU(cudaMemcpyAsync(s->log_head + 2 * g, d.logs[g].count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        }
+        // heads fetched by the step itself: each rides behind its group's last kernel
+        if (per_group_heads) CU(cudaEventSynchronize(s->groups[g].done));
         const unsigned long long cnt = s->log_head[2 * g];
         if ((s->log_head[2 * g + 1] & 0xFFFFFFFFull) != 0 || cnt > (unsigned long long)d.logs[g].cap) {
             overflow = true;
@@ -1922,6 +1941,17 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
     if (listed) *listed = act;
     if (total) *total = tot;
     if (mode) *mode = !s->unit_skip ? 0 : (s->unit_rows ? 2 : 1);
+    return 0;
+}
+
+extern "C" int sfb_debug_stall(sfb_sim* s, int32_t microseconds) {
+    if (!s) return fail(SFB_ERR_INVALID, "sfb_debug_stall: null handle");
+    if (microseconds < 0 || microseconds > 1000000) return fail(SFB_ERR_INVALID, "sfb_debug_stall: %d us", microseconds);
+    int rc;
+    if ((rc = use(s))) return rc;
+    SFB_LAUNCH(k_stall, 1, 1, 0, s->stream, (long long)microseconds * 1000);
+    s->launches_all++;
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -362,6 +362,10 @@ class FireEngine:
         _lib.check(self._lib.sfb_get_queue_stats(self._h, C.byref(a), C.byref(b), C.byref(o)))
         return int(a.value), int(b.value), bool(o.value)
 
+    def debug_stall(self, microseconds: int) -> None:
+        """Test knob: keep the engine's stream busy for a while before the next call's work."""
+        _lib.check(self._lib.sfb_debug_stall(self._h, int(microseconds)))
+
     def device_bytes(self) -> int:
         b = C.c_int64()
         _lib.check(self._lib.sfb_device_bytes(self._h, C.byref(b)))

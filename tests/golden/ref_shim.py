@@ -1,142 +1,13 @@
-"""
-Import shim for the UNMODIFIED reference (mitrefireline/simfire) in the dev container.
-
-Used ONLY by ``tests/golden/gen_golden.py`` to produce the committed golden vectors.
-It never runs on the GPU box (``/root/reference`` does not exist there) and nothing in
-the product (``simfire_b200/``), ``bench.py`` or the ``-m gpu`` tests imports it.
-
-The reference is pure Python but imports ~12 display / GIS modules that are absent here
-(pygame, matplotlib, reportlab, ...).  None of them is touched by the headless hot path
-(``simfire/game/managers/fire.py:616-719`` -> ``simfire/world/rothermel.py:4-136``), so we
-register inert stand-ins in ``sys.modules`` before importing.  The only stand-in with
-behaviour is ``pygame.Rect`` (the reference keeps a sprite's (x, y) in ``Fire.rect``,
-``simfire/game/sprites.py:223-227``, and unpacks it at ``fire.py:139``).
-"""
-from __future__ import annotations
-
-import collections
-import collections.abc
-import importlib.metadata
+"""Forwarder: the import shim for the unmodified reference lives in ``oracle/ref_shim.py`` (the CPU arm
+of bench.py uses it too).  The golden generators in this directory run in the dev container only and
+read the mounted checkout."""
+import os
 import sys
-import types
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+os.environ.setdefault("SFB_REFERENCE_ROOT", "/root/reference")
+
+from oracle.ref_shim import *  # noqa: E402,F401,F403
+from oracle.ref_shim import import_reference, install, reference_root  # noqa: E402,F401
 
 REFERENCE_ROOT = "/root/reference"
-
-
-class _Rect:
-    """Minimal pygame.Rect: x, y, w, h, iterable, move()."""
-
-    def __init__(self, x, y=None, w=0, h=0):
-        if y is None:  # Rect((x, y, w, h))
-            x, y, w, h = x
-        self.x, self.y, self.w, self.h = int(x), int(y), int(w), int(h)
-
-    def __iter__(self):
-        return iter((self.x, self.y, self.w, self.h))
-
-    def move(self, dx, dy):
-        return _Rect(self.x + dx, self.y + dy, self.w, self.h)
-
-    def update(self, *a, **k):  # pragma: no cover
-        pass
-
-
-class _Sprite:
-    def __init__(self, *a, **k):
-        pass
-
-
-class _Anything(types.ModuleType):
-    """Module whose every attribute is an inert callable/class."""
-
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-
-        def _inert(*a, **k):
-            return None
-
-        return _inert
-
-
-def _mod(name: str, **attrs) -> types.ModuleType:
-    m = _Anything(name)
-    for k, v in attrs.items():
-        setattr(m, k, v)
-    sys.modules[name] = m
-    return m
-
-
-_installed = False
-
-
-def install() -> None:
-    """Register the stand-ins and put the reference on sys.path (idempotent)."""
-    global _installed
-    if _installed:
-        return
-    _installed = True
-
-    # Python >= 3.10 removed collections.Sequence (used at fire.py:415)
-    if not hasattr(collections, "Sequence"):
-        collections.Sequence = collections.abc.Sequence  # type: ignore[attr-defined]
-
-    # simfire/__init__.py:27 asks importlib.metadata for its own version
-    _orig_version = importlib.metadata.version
-
-    def _version(name):
-        if name == "simfire":
-            return "2.0.1"
-        return _orig_version(name)
-
-    importlib.metadata.version = _version  # type: ignore[assignment]
-
-    pg = _mod("pygame", Rect=_Rect)
-    pg.rect = _mod("pygame.rect", Rect=_Rect)
-    pg.sprite = _mod("pygame.sprite", Sprite=_Sprite)
-    pg.surface = _mod("pygame.surface", Surface=object)
-    pg.surfarray = _mod("pygame.surfarray")
-    pg.display = _mod("pygame.display")
-    pg.image = _mod("pygame.image")
-    pg.transform = _mod("pygame.transform")
-    pg.time = _mod("pygame.time")
-    pg.event = _mod("pygame.event")
-    pg.draw = _mod("pygame.draw")
-    pg.font = _mod("pygame.font")
-
-    mpl = _mod("matplotlib")
-    mpl.pyplot = _mod("matplotlib.pyplot", Figure=object)
-    mpl.lines = _mod("matplotlib.lines")
-    mpl.contour = _mod("matplotlib.contour", QuadContourSet=object)
-
-    rl = _mod("reportlab")
-    rl.graphics = _mod("reportlab.graphics", renderPM=None)
-    sv = _mod("svglib")
-    sv.svglib = _mod("svglib.svglib")
-    _mod("wurlitzer")
-    _mod("geopandas")
-    lf = _mod("landfire")
-    lf.product = _mod("landfire.product")
-    lf.product.enums = _mod(
-        "landfire.product.enums", ProductRegion=object, ProductTheme=object, ProductVersion=object
-    )
-    lf.product.search = _mod("landfire.product.search", ProductSearch=object)
-    gp = _mod("geopy")
-    gp.distance = _mod("geopy.distance")
-    _mod("geotiff", GeoTiff=object)
-    _mod("h5py")
-    _mod("jsonlines")
-    _mod("noise")
-
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-
-
-def import_reference():
-    """Return (fire_module, rothermel_module, enums, parameters, presets)."""
-    install()
-    from simfire import enums  # noqa: E402
-    from simfire.game.managers import fire  # noqa: E402
-    from simfire.world import parameters, presets, rothermel  # noqa: E402
-
-    return fire, rothermel, enums, parameters, presets

@@ -9,6 +9,8 @@ for pairs where 1 + phi_w + phi_s cancels ("Mixed precision
 error of a float32 transcendental is relative to the un-cancelled magnitude, so the
 absolute term is 3e-6 of the rate the same pair would have on flat ground.
 """
+import os
+
 import numpy as np
 import pytest
 from scenario_io import GOLDEN, check_trajectory, dense_params, load_scenario, scenario_names
@@ -512,6 +514,44 @@ def test_parallel_mirror_patching_paths(groups, monkeypatch):
             patched += max(0, n)
             assert np.array_equal(mirror, eng.fire_map()), f"iteration {it} (mode {mode})"
         assert patched > 2000  # the logs were really patched, not re-downloaded
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3, 4])
+def test_mirror_sees_calls_made_after_the_step(groups):
+    """Stream-ordering stress (round-1 hardware failure): step -> apply_points / reset -> sync.  The
+    between-step kernels run on the handle's stream while the step ran on the group streams; the
+    sync must read the log heads ordered after BOTH.  The handle's stream is stalled before the
+    mitigation kernel so that a head read on the wrong stream would certainly miss its entries, the
+    point batches are as large as the staged (no host sync) path allows, and the mirror must equal
+    a download after every iteration."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    H, W, E = 96, 128, 12
+    wl = synthetic_operational(H, W, seed=21, patch=8)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True, max_fire_duration=3)
+    rng = np.random.default_rng(8)
+    iters = int(os.environ.get("SFB_STRESS_ITERS", "40" if os.environ.get("SFB_EMULATED") == "1" else "500"))
+    with FireEngine(H, W, E, shared_static=True, env_groups=groups, track_changes=True, **kw) as eng:
+        eng.set_static(wl.planes)
+        eng.reset(wl.burnable_starts(E, seed=2, margin=3))
+        mirror = np.zeros((E, H, W), np.int8)
+        eng.sync_fire_maps(mirror)
+        patched = 0
+        for it in range(iters):
+            n_pts = int(rng.integers(1, 4000))  # <= 64 KB of points: staged, returns without a sync
+            pts = np.stack([rng.integers(0, E, n_pts), rng.integers(0, W, n_pts), rng.integers(0, H, n_pts),
+                            rng.integers(0, 6, n_pts)], axis=1)  # fmt: skip
+            eng.step(1, sync=False)
+            if it % 3 == 0:
+                eng.debug_stall(300)
+            eng.apply_points(pts)
+            if it % 50 == 49:  # everything burnt out or was painted over: start again in a few envs
+                eng.reset(wl.burnable_starts(3, seed=it, margin=3), envs=[0, 5, 11])
+            n = eng.sync_fire_maps(mirror)
+            patched += max(0, n)
+            assert np.array_equal(mirror, eng.fire_map()), f"iteration {it}"
+        assert patched > iters * 100
 
 
 def test_observation_tensor_matches_host_map():
