@@ -86,6 +86,11 @@ enum sfb_flags {
                                   flagged units are swept (k_units + k_sweep).  Default: a unit is a
                                   single row of a strip, the flagged units are the row tasks
                                   themselves and nothing is swept (k_row_list)                     */
+    SFB_FRONT_LISTS = 8192,    /* the list-driven step (sfb_lists.cuh): one watch list of the cells that can
+                                  change (sprites, their ignitable neighbours, attenuated control lines), one
+                                  kernel per step (k_front), no env groups.  Fewer instructions and bytes per
+                                  step than the sweep front ends, but all of it scattered 32-byte reads: it pays
+                                  where the planes fit L2 (single envs, small batches).  Results are identical  */
     SFB_STEP_GRAPH = 4096      /* multi-group handles: replay pairs of steps of sfb_step(n) as one CUDA
                                   graph forked over the group streams instead of enqueueing every
                                   kernel (single-group handles always replay a graph).  Off by
@@ -202,6 +207,15 @@ int sfb_step_timed(sfb_sim* sim, int32_t n_steps, float* ms);
  * GameStatus per env to status[n] (may be NULL). */
 int sfb_update(sfb_sim* sim, int32_t env0, int32_t n, int8_t* maps_inout, int32_t* status);
 
+/* Drop-in for `fire_map = ConstantSpreadFireManager.update(fire_map)` (fire.py:754-787) with HOST buffers,
+ * exactly as the reference executes it: sprites past max_fire_duration turn BURNED (fire.py:116-161), then
+ * every sprite whose duration equals rate_of_spread sets its in-bounds ignitable neighbours (8, or 4 without
+ * SFB_DIAGONAL_SPREAD) to BURNING.  The reference appends Fire sprites for those cells without a duration
+ * entry, and its next prune slices them off again (fire.py:148-155): they stay BURNING and never spread;
+ * here they get the status and no sprite.  Uploads int8 maps [n][H][W] of envs [env0, env0+n), advances EVERY
+ * env of the handle by one call, downloads the maps in place.  No GameStatus (the reference returns none). */
+int sfb_constant_spread_update(sfb_sim* sim, int32_t env0, int32_t n, int8_t* maps_inout, int32_t rate_of_spread);
+
 int sfb_synchronize(sfb_sim* sim);
 
 /* ---- results --------------------------------------------------------------------- */
@@ -233,6 +247,13 @@ int sfb_get_status(sfb_sim* sim, int32_t* status, double* elapsed, int32_t* step
  * synchronises the stream before returning). */
 int sfb_fire_map_device(sfb_sim* sim, void** dev);
 
+/* Zero-copy view of the static inputs (FireSimulation.get_attribute_data, simulation.py:376-403): *records
+ * points at DEVICE memory holding float32 records {w_0, delta, M_x, sigma, U, U_dir, slope_mag, slope_dir}
+ * (sfb_static_plane order, 32 bytes per cell) laid out [n_sets][H][pitch_cells]; n_sets is 1 under
+ * SFB_SHARED_STATIC, else E.  Plane k of set e is a strided view: element (y, x) at float index
+ * ((e * plane_cells + y * pitch_cells + x) * 8 + k).  Read-only for the caller. */
+int sfb_static_device(sfb_sim* sim, void** records, int64_t* plane_cells, int32_t* pitch_cells, int32_t* n_sets);
+
 /* ---- slab mode: one large grid split in horizontal slabs across handles / GPUs ----------
  * Each handle is created with slab_y0 / slab_total_H and holds rows [slab_y0, slab_y0 + H).
  * The sweep kernel reads the row above / below its slab straight from the neighbour slab's
@@ -260,6 +281,9 @@ int sfb_step_eval(sfb_sim* sim);
  * sfb_step_eval): 8 int32 per env; an element-wise MAX across slabs ORs any_live / any_cand
  * and leaves the other fields (identical on every slab) unchanged. */
 int sfb_flags_device(sfb_sim* sim, void** flags, int64_t* n_int32);
+/* Which half (0 / 1) of the double-buffered per-env records the NEXT step reads (the pointer
+ * sfb_flags_device returns is that half; the other half starts n_int32 * 4 bytes before or after it). */
+int sfb_get_parity(sfb_sim* sim, int32_t* parity);
 /* Peer-memory coordination (no host or NCCL round trip per step).  The handle owns a small
  * mailbox (sfb_slab_mailbox: device pointer + byte offset from the state plane, so it can be
  * reached through the state plane's IPC mapping); sfb_slab_connect receives, for every slab q of
@@ -291,11 +315,17 @@ int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* e
 int sfb_get_row_tasks(sfb_sim* sim, int64_t* tasks, int64_t* capacity);
 /* Units = (env, chunk of rows or single row, strip of columns) the last completed step listed,
  * and the number of units of the handle; mode: 0 = no unit skipping (every unit is swept, the two
- * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks. */
+ * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks, 3 = list-driven step
+ * (listed = entries of the watch list, total = cells of the handle). */
 int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total, int32_t* mode);
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and
  * whether the step overflowed the queue and ran the dense fallback. */
 int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32_t* overflowed);
+/* List handles (sfb_get_unit_stats mode 3): counters accumulated by k_front since the previous call, then
+ * reset: stats[0] cells examined, [1] candidates evaluated (fire.py:163-234), [2] cells ignited, [3] sprites
+ * pruned (fire.py:116-161), [4] cells that joined the watch list, [5] list entries read, [6] cells whose eight neighbours were read;
+ * n <= 7 values. */
+int sfb_get_front_stats(sfb_sim* sim, int64_t* stats, int32_t n);
 /* Test knob: enqueue a kernel that keeps the handle's stream busy for `microseconds` (at most 1 s)
  * before whatever is called next on it.  The GPU tests use it to widen the window of stream-ordering
  * races (a between-step call that is still running when the next call reads what it wrote). */

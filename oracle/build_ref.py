@@ -41,7 +41,7 @@ def stage(force: bool = False) -> str | None:
         shutil.rmtree(DST)
     manifest = {}
     for root, dirs, files in os.walk(SRC):
-        dirs[:] = [d for d in dirs if d not in ("_tests", "__pycache__", "assets", "textures", "pregenerated_wind_files")]
+        dirs[:] = [d for d in dirs if d not in ("_tests", "__pycache__")]  # .py files only: images and data files stay behind
         for f in files:
             if not f.endswith(".py"):
                 continue

@@ -70,6 +70,17 @@ class _Sprite:
         pass
 
 
+class _Surface:
+    """What `pygame.surfarray.make_surface(array)` returns, as far as `Fire.__init__` (sprites.py:229-236)
+    uses it when a manager is not headless (ConstantSpreadFireManager cannot be, fire.py:752)."""
+
+    def __init__(self, array):
+        self.w, self.h = int(array.shape[0]), int(array.shape[1])
+
+    def get_rect(self):
+        return _Rect(0, 0, self.w, self.h)
+
+
 class _Anything(types.ModuleType):
     """Module whose every attribute is an inert callable/class."""
 
@@ -119,7 +130,7 @@ def install() -> None:
     pg.rect = _mod("pygame.rect", Rect=_Rect)
     pg.sprite = _mod("pygame.sprite", Sprite=_Sprite)
     pg.surface = _mod("pygame.surface", Surface=object)
-    pg.surfarray = _mod("pygame.surfarray")
+    pg.surfarray = _mod("pygame.surfarray", make_surface=_Surface)
     pg.display = _mod("pygame.display")
     pg.image = _mod("pygame.image")
     pg.transform = _mod("pygame.transform")

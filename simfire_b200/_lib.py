@@ -13,7 +13,7 @@ ABI_VERSION = 1
 DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE_CELLS, SWEEP_LDG = 1, 2, 4, 8, 16, 32, 64
 TRACK_CHANGES = 128
 KEEP_IGNITION = 256
-UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS, STEP_GRAPH = 512, 1024, 2048, 4096
+UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS, STEP_GRAPH, FRONT_LISTS = 512, 1024, 2048, 4096, 8192
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS, PLANE_IGNITION = 0, 1, 2, 3, 4
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")
@@ -28,7 +28,7 @@ EXPORTS = (
     "sfb_rate_of_spread", "sfb_sync_fire_maps", "sfb_state_device", "sfb_ipc_export", "sfb_ipc_open",
     "sfb_ipc_close", "sfb_set_halo", "sfb_step_sweep", "sfb_step_eval", "sfb_flags_device", "sfb_set_stream",
     "sfb_slab_mailbox", "sfb_slab_connect", "sfb_step_slab", "sfb_set_tracking",
-    "sfb_set_elevation", "sfb_get_row_tasks", "sfb_get_unit_stats", "sfb_debug_stall",
+    "sfb_set_elevation", "sfb_get_row_tasks", "sfb_get_unit_stats", "sfb_debug_stall", "sfb_get_front_stats", "sfb_get_parity", "sfb_constant_spread_update", "sfb_static_device",
 )  # fmt: skip
 
 
@@ -107,6 +107,10 @@ def load() -> C.CDLL:
         "sfb_get_queue_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "sfb_device_bytes": (C.c_int, [vp, C.POINTER(i64)]),
         "sfb_debug_stall": (C.c_int, [vp, i32]),
+        "sfb_static_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+        "sfb_constant_spread_update": (C.c_int, [vp, i32, i32, vp, i32]),
+        "sfb_get_parity": (C.c_int, [vp, C.POINTER(i32)]),
+        "sfb_get_front_stats": (C.c_int, [vp, C.POINTER(i64), i32]),
         "sfb_rate_of_spread": (C.c_int, [i32, vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in proto.items():

@@ -26,6 +26,10 @@
 
 #include "../../include/simfire_b200.h"
 #include "sfb_kernels.cuh"
+#include "sfb_lists.cuh"
+#if !defined(SFB_EMU) && defined(SFB_EXPERIMENT_SORT)
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 using namespace sfb;
 
@@ -176,6 +180,12 @@ struct sfb_sim {
     int rows_blocks;  // persistent grid of k_rows
     int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
     int unit_rows;    // ... and a unit is a single row of a strip: no sweep at all (k_row_list)
+    int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
+    int lpar;         // which watch-list buffer the NEXT step reads
+    int front_blocks; // persistent grid of k_front
+    uint8_t* env_mark;            // device [E]: envs a purge / rebuild of the watch list applies to
+    unsigned long long* list_ctr; // device: wl_count[2] | ros_count | broken (int32) + ticket (uint32)
+    int64_t list_entries_last;    // entries the last completed step left on the list (sfb_get_queue_stats)
     CUtensorMap tmap; // state plane as uint32 [E][H][pitch_bytes / 4]
     int parity;       // which half of meta / qcount the NEXT step reads
     int in_step;      // sfb_step_sweep done, sfb_step_eval pending
@@ -291,7 +301,7 @@ __global__ void k_clear_envs(DevParams p, const int32_t* envs, int n, int clear_
 
 // FireSimulation._create_fire_map + FireManager.__init__ (simulation.py:561-566, fire.py:101-103)
 template <typename CellT>
-__global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const int32_t* xy, int n, int y_off) {
+__global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const int32_t* xy, int n, int y_off, int lpar) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int env = envs ? envs[k] : k;
@@ -301,6 +311,8 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
             (CellT)(ST_BURNING | (1 << 3));  // sprite created before update() call 1: ign = 0
         if (p.ign) p.ign[(long long)env * p.plane + (long long)y * p.pitch + x] = 0;
         if (p.unit_act) mark_units_around<CellT>(p, env, y, x);
+        // list handles: the sprite joins the watch list; at duration 0 its thread brings the neighbours in
+        if (p.listed && listed_test_and_set(p, (long long)env * p.plane + (long long)y * p.pitch + x)) list_append(p, lpar, env, y, x);
     }
     EnvMeta m;
     m.t = 1;
@@ -323,15 +335,18 @@ __global__ void k_reset_meta(DevParams p, int par, const int32_t* envs, const in
 
 // ControlLineManager.update (mitigation.py:77): fire_map[y, x] = kind, sprite untouched
 template <typename CellT>
-__global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int kind, int y_off) {
+__global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int kind, int y_off, int lpar) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int env = pts[4 * i], x = pts[4 * i + 1], y = pts[4 * i + 2] - y_off, k = pts[4 * i + 3];
     if (k != kind || y < 0 || y >= p.H) return;
     const long long idx = (long long)env * p.plane + (long long)y * p.pitch + x;
     CellT* c = reinterpret_cast<CellT*>(p.state) + idx;
-    *c = (CellT)((*c & ~7) | to_internal(k));
+    const int nc = (*c & ~7) | to_internal(k);
+    *c = (CellT)nc;
     if (p.unit_act) mark_units_around<CellT>(p, env, y, x);  // a control line is work under attenuation
+    // list handles: a cell that became ignitable next to a sprite, or an attenuated control line, is watched
+    if (p.listed && belongs_on_list<CellT>(p, env, y, x, nc) && listed_test_and_set(p, idx)) list_append(p, lpar, env, y, x);
     if (p.track) {
         const LogRef& L = log_of_env(p, env);
         log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48) | LOG_SETUP_BIT);
@@ -493,7 +508,12 @@ __global__ void k_derive_static(DevParams p, long long n_cells) {
         DerivedRec d;
         d.fuel = sfb_fuel_terms(r.fuel.x, r.fuel.y, r.fuel.z, r.fuel.w, p.part);
         d.env = r.env;
-        const_cast<DerivedRec*>(p.drv)[i] = d;
+        if (p.drv) const_cast<DerivedRec*>(p.drv)[i] = d;
+        if (p.rtab) {  // every input of rothermel.py:4-136 is static per (cell, direction): evaluate once
+            double* out = const_cast<double*>(p.rtab) + i * 8;
+#pragma unroll
+            for (int dir = 0; dir < 8; ++dir) out[dir] = sfb_spread_from_terms(dir, d.fuel, d.env.x, d.env.y, d.env.z, d.env.w);
+        }
     }
 }
 
@@ -515,6 +535,62 @@ __global__ void k_stall(long long ns) {
 __global__ void k_rate_of_spread(const int8_t* dir, const float* rec, SfbParticle fp, long long n, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sfb_rate_of_spread_pair(dir[i], rec + 8 * i, fp);
+}
+
+// ---------------------------------------------------------------------------------------
+// ConstantSpreadFireManager.update (fire.py:754-787), literally: prune (fire.py:116-161), then every sprite
+// whose duration equals rate_of_spread sets its in-bounds ignitable neighbours (fire.py:163-234) to BURNING.
+// The sprites it appends for them carry no duration entry and are sliced off by the next call's prune
+// (fire.py:148-155), so those cells stay BURNING and never spread: on the device they get the status
+// without a sprite code.  Two kernels, because the reference prunes every sprite before any spreads.
+// ---------------------------------------------------------------------------------------
+template <typename CellT>
+__global__ void k_cs_prune(DevParams p, int par) {
+    const long long total = (long long)p.E * p.plane;
+    CellT* state = reinterpret_cast<CellT*>(p.state);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = state[i];
+        if ((c >> 3) == 0) continue;
+        const EnvMeta& m = p.meta[(long long)par * p.meta_stride + (int)(i / p.plane)];
+        if (!m.running) continue;
+        if (sprite_age<CellT>(c >> 3, (m.t - 1) % Cell<CellT>::M) >= p.max_dur) state[i] = (CellT)ST_BURNED;
+    }
+}
+template <typename CellT>
+__global__ void k_cs_spread(DevParams p, int par, int rate_of_spread) {
+    const long long total = (long long)p.E * p.plane;
+    CellT* state = reinterpret_cast<CellT*>(p.state);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = state[i];
+        if ((c >> 3) == 0) continue;
+        const int env = (int)(i / p.plane);
+        const EnvMeta& m = p.meta[(long long)par * p.meta_stride + env];
+        if (!m.running || sprite_age<CellT>(c >> 3, (m.t - 1) % Cell<CellT>::M) != rate_of_spread) continue;
+        const long long cell = i - (long long)env * p.plane;
+        const int y = (int)(cell / p.pitch), x = (int)(cell - (long long)y * p.pitch);
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if ((dy == 0 && dx == 0) || (!p.diagonal && dy != 0 && dx != 0)) continue;
+                const int yy = y + dy, xx = x + dx;
+                if ((unsigned)yy >= (unsigned)p.H || (unsigned)xx >= (unsigned)p.W) continue;
+                CellT* q = state + i + (long long)dy * p.pitch + dx;
+                const int nc = *q;
+                if (ignitable(nc & 7)) *q = (CellT)((nc & ~7) | ST_BURNING);  // fire.py:779 (several sprites may write it: same value)
+            }
+    }
+}
+__global__ void k_cs_clock(DevParams p, int par) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    EnvMeta m = p.meta[(long long)par * p.meta_stride + env];
+    if (m.running) m.t += 1;  // durations += 1 (fire.py:785); this manager has no GameStatus
+    m.any_live = m.any_cand = 0;
+    p.meta[(long long)(par ^ 1) * p.meta_stride + env] = m;
+}
+
+__global__ void k_mark_envs(uint8_t* mark, const int32_t* envs, int env0, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) mark[envs ? envs[k] : env0 + k] = 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -555,6 +631,14 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.rows);
     cudaFree(s->d.unit_act);
     cudaFree(s->d.units);
+    cudaFree(s->d.wl[0]);
+    cudaFree(s->d.wl[1]);
+    cudaFree(s->d.listed);
+    cudaFree((void*)s->d.rtab);
+    cudaFree(s->d.ros_items);
+    cudaFree(s->d.late);
+    cudaFree(s->list_ctr);
+    cudaFree(s->env_mark);
     s->groups.push_back(s->all);
     for (auto& gr : s->groups) {
         cudaFree(gr.counters);
@@ -636,6 +720,19 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     d.n_units = (int64_t)d.E * d.chunks * d.strips;
 
     const int64_t total = (int64_t)d.E * d.plane;
+    // front end.  The sweep front ends (row units from 1024 units up, the dense TMA sweep below) are the
+    // default: their row tasks read the state in 512-byte runs, which HBM serves at full speed.  The
+    // list-driven step (sfb_lists.cuh, SFB_FRONT_LISTS) does less work per step -- one thread per cell
+    // that can change -- but every one of its reads is a scattered 32-byte sector, and B200 sustains only
+    // ~40 G such reads per second once they miss L2 (profiles/r02_gather_latency.txt): it wins where the
+    // planes fit L2 (single envs, small batches: SFB_FRONT=lists or the flag), not at the 2048^2 x 1024 target.
+    s->front_lists = prm->slab_total_H == 0 && (prm->flags & SFB_FRONT_LISTS) != 0;
+    if (const char* e = getenv("SFB_FRONT")) s->front_lists = prm->slab_total_H == 0 && strcmp(e, "lists") == 0;
+    if (d.H >= (1 << LE_BITS) || d.W >= (1 << LE_BITS) || d.E >= (1 << 22)) s->front_lists = 0;  // entry fields
+    // row tasks of the sweep front ends pack y into 20 bits and the strip into 8 (make_row_task)
+    if (!s->front_lists && (d.H >= (1 << 20) || d.strips > 256))
+        return fail(SFB_ERR_INVALID, "sfb_create: grid of %d rows x %d strips of %d columns exceeds the row-task fields (2^20 rows, 256 strips)",
+                    d.H, d.strips, wr);
     int64_t qcap = prm->queue_capacity;
     if (qcap <= 0) qcap = total <= (8 << 20) ? total : std::max<int64_t>(8 << 20, total / 8);
     d.qcap = qcap;
@@ -652,7 +749,17 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if ((prm->flags & SFB_KEEP_IGNITION) && (rc = dmalloc(s, &d.ign, (size_t)total * 4))) return rc;
     const int64_t stat_cells = d.shared_static ? d.plane : total;
     if ((rc = dmalloc(s, (StaticRec**)&d.stat, (size_t)stat_cells * sizeof(StaticRec)))) return rc;
-    if ((rc = dmalloc(s, (DerivedRec**)&d.drv, (size_t)stat_cells * sizeof(DerivedRec)))) return rc;
+    {
+        // every input of the Rothermel evaluation is static per (cell, direction): a table of the eight
+        // float64 rates per static cell (64 B) replaces the evaluation in the step -- if it fits easily
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)stat_cells * 8 * sizeof(double);
+        const size_t rest = (size_t)total * 12;  // burn + lists still to be allocated
+        if (!getenv("SFB_NO_RTAB") && free_b > rest && need <= (free_b - rest) / 2 && (rc = dmalloc(s, (double**)&d.rtab, need))) return rc;
+    }
+    if (!d.rtab && (rc = dmalloc(s, (DerivedRec**)&d.drv, (size_t)stat_cells * sizeof(DerivedRec)))) return rc;
+    // (the group views copy these pointers: make_view runs after this point)
     s->static_dirty = 1;
     if ((rc = dmalloc(s, &d.meta, (size_t)2 * d.E * sizeof(EnvMeta)))) return rc;
     d.track = (prm->flags & SFB_TRACK_CHANGES) != 0;
@@ -702,14 +809,57 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     d.meta_stride = d.E;
     d.idx_base = 0;
     d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
-    if ((rc = dmalloc(s, &d.queue, (size_t)d.qcap * 8))) return rc;
-    if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
+    if (s->front_lists) {
+        G = 1;
+        d.rows_cap = 1;
+        // every listed cell has one entry: a list as long as the grid cannot overflow; big batches get an
+        // eighth of that (an overflow turns the handle to the dense form of the step, results unchanged)
+        d.wl_cap = prm->queue_capacity > 0 ? prm->queue_capacity : (total <= (32 << 20) ? total : std::max<int64_t>(32 << 20, total / 8));
+        for (int k = 0; k < 2; ++k)
+            if ((rc = dmalloc(s, &d.wl[k], (size_t)d.wl_cap * 8))) return rc;
+        const size_t words = (size_t)(total + 31) / 32 + 1;
+        if ((rc = dmalloc(s, &d.listed, words * 4))) return rc;
+        CU(cudaMemsetAsync(d.listed, 0, words * 4, s->stream));
+        if ((rc = dmalloc(s, &s->list_ctr, 16 * sizeof(unsigned long long)))) return rc;
+        CU(cudaMemsetAsync(s->list_ctr, 0, 16 * sizeof(unsigned long long), s->stream));
+        d.front_stats = s->list_ctr + 8;
+        d.late_count = reinterpret_cast<unsigned int*>(s->list_ctr + 6);
+        d.late_cap = 1 << 16;
+        if ((rc = dmalloc(s, &d.late, (size_t)d.late_cap * 8))) return rc;
+        d.wl_count = s->list_ctr;
+        d.ros_count = s->list_ctr + 2;
+        d.broken = reinterpret_cast<int32_t*>(s->list_ctr + 3);
+        d.ticket = reinterpret_cast<unsigned int*>(s->list_ctr + 4);
+        d.dense_now = reinterpret_cast<int32_t*>(s->list_ctr + 5);
+        if ((rc = dmalloc(s, &s->env_mark, (size_t)d.E))) return rc;
+        CU(cudaMemsetAsync(s->env_mark, 0, (size_t)d.E, s->stream));
+        if (d.keep_ros) {
+            d.ros_cap = total;
+            if ((rc = dmalloc(s, &d.ros_items, (size_t)d.ros_cap * 16))) return rc;
+        }
+#define SFB_FRONT_SETUP(K)                                                                       \
+    do {                                                                                        \
+        CU(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_SMEM));   \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->front_blocks, K, FRONT_THREADS, FRONT_SMEM)); \
+    } while (0)
+        if (s->cell_bytes == 1 && d.rtab) SFB_FRONT_SETUP((k_front<uint8_t, true>));
+        else if (s->cell_bytes == 1) SFB_FRONT_SETUP((k_front<uint8_t, false>));
+        else if (d.rtab) SFB_FRONT_SETUP((k_front<uint16_t, true>));
+        else SFB_FRONT_SETUP((k_front<uint16_t, false>));
+#undef SFB_FRONT_SETUP
+        if (s->front_blocks < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_front does not fit on an SM");
+        s->front_blocks *= s->n_sm;
+        if (const char* e = getenv("SFB_FRONT_BLOCKS")) s->front_blocks = std::max(1, atoi(e));
+    } else {
+        if ((rc = dmalloc(s, &d.queue, (size_t)d.qcap * 8))) return rc;
+        if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
+    }
     // unit skipping: on for handles with enough units to make a list worth its launch, never in slab
     // mode (a neighbour slab's fire enters through the halo rows, which nobody here would flag)
-    s->unit_skip = prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31) &&
+    s->unit_skip = !s->front_lists && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31) &&
                    ((prm->flags & SFB_UNIT_SKIP_ON) || (!(prm->flags & SFB_UNIT_SKIP_OFF) && d.n_units >= 1024));
     if (const char* e = getenv("SFB_UNIT_SKIP"))
-        if (prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
+        if (!s->front_lists && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
     s->unit_rows = s->unit_skip && !(prm->flags & SFB_UNIT_CHUNKS);
     if (const char* e = getenv("SFB_UNIT_ROWS")) s->unit_rows = s->unit_skip && atoi(e) != 0;
     d.unit_stride = (int64_t)d.chunks * d.strips;
@@ -753,7 +903,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         if (d.ign) v.ign = d.ign + off;
         if (!d.shared_static) {
             v.stat = d.stat + off;
-            v.drv = d.drv + off;
+            if (d.drv) v.drv = d.drv + off;
+            if (d.rtab) v.rtab = d.rtab + off * 8;
         }
         v.meta = d.meta + e0;
         v.idx_base = off;
@@ -983,6 +1134,24 @@ extern "C" int sfb_set_elevation(sfb_sim* s, int32_t env, const double* elevatio
 }
 
 // ---------------------------------------------------------------------------------------
+// watch-list maintenance between steps (list handles)
+// ---------------------------------------------------------------------------------------
+// Marks envs (a device list, or [env0, env0 + n)) and removes their entries and `listed` bits; the
+// caller changes the cells, re-lists what belongs on the list and clears the marks again.
+static int list_drop_envs(sfb_sim* s, const int32_t* d_envs, int env0, int n) {
+    const DevParams& d = s->d;
+    SFB_LAUNCH(k_mark_envs, nblocks(n, 128), 128, 0, s->stream, s->env_mark, d_envs, env0, n);
+    SFB_LAUNCH(k_list_purge, cap_grid(s, std::max<int64_t>(1024, s->list_entries_last * 2 + 65536), 256), 256, 0, s->stream, d, s->lpar,
+               (const uint8_t*)s->env_mark);
+    CU(cudaMemsetAsync(d.wl_count + s->lpar, 0, sizeof(unsigned long long), s->stream));  // its survivors are in the other buffer now
+    s->lpar ^= 1;
+    SFB_LAUNCH(k_list_clear_bits, cap_grid(s, (long long)n * (d.plane / 16), 256), 256, 0, s->stream, d, d_envs, env0, n);
+    s->launches_all += 3;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // between-step mutations
 // ---------------------------------------------------------------------------------------
 extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32_t* xy) {
@@ -1005,6 +1174,7 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     int32_t* d_envs = envs ? s->small + 2 * (size_t)n : nullptr;
     CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (envs) CU(cudaMemcpyAsync(d_envs, envs, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    if (s->front_lists && (rc = list_drop_envs(s, d_envs, 0, n))) return rc;
     if (linear_bytes(s) && d.plane % 16 == 0) {
         SFB_LAUNCH(k_clear_envs_v16, cap_grid(s, (long long)n * (d.plane / 16), 256), 256, 0, s->stream, d, (const int32_t*)d_envs, n, d.plane / 16);
         s->launches_all++;
@@ -1012,7 +1182,8 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
         DISPATCH(s, k_clear_envs, cap_grid(s, (long long)n * d.plane, 256), 256, d, (const int32_t*)d_envs, n, 1);
     }
     DISPATCH(s, k_reset_meta, nblocks(n, 128), 128, d, s->parity, (const int32_t*)d_envs, (const int32_t*)d_xy, n,
-             s->prm.slab_y0);
+             s->prm.slab_y0, s->lpar);
+    if (s->front_lists) CU(cudaMemsetAsync(s->env_mark, 0, (size_t)d.E, s->stream));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));  // host buffers are borrowed for the call only
     return 0;
@@ -1054,7 +1225,7 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     for (int kind = 0; kind <= 5; ++kind) {
         if (!present[kind]) continue;
         DISPATCH(s, k_apply_points, nblocks(n, 256), 256, d, (const int32_t*)s->small, (long long)n, kind,
-                 s->prm.slab_y0);
+                 s->prm.slab_y0, s->lpar);
     }
     CU(cudaGetLastError());
     if (staged) CU(cudaEventRecord(s->pts_ev[s->pts_slot], s->stream));
@@ -1084,6 +1255,13 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     // wholesale replacement: any cell may have become a control line or ignitable next to a sprite
     if (d.unit_act)
         CU(cudaMemsetAsync(d.unit_act + (size_t)env0 * d.unit_stride, 1, (size_t)n * d.unit_stride, s->stream));
+    if (s->front_lists) {  // the same for the watch list: drop the envs' entries, re-list from the new state
+        if ((rc = list_drop_envs(s, nullptr, env0, n))) return rc;
+        if (s->cell_bytes == 1) SFB_LAUNCH(k_list_rebuild<uint8_t>, cap_grid(s, (long long)n * d.plane, 256), 256, 0, s->stream, d, s->lpar, env0, n);
+        else SFB_LAUNCH(k_list_rebuild<uint16_t>, cap_grid(s, (long long)n * d.plane, 256), 256, 0, s->stream, d, s->lpar, env0, n);
+        s->launches_all++;
+        CU(cudaMemsetAsync(s->env_mark, 0, (size_t)d.E, s->stream));
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1337,11 +1515,74 @@ static int run_group_graph(sfb_sim* s) {
     return 0;
 }
 
+// list handles: one k_front per step on the handle's stream (k_tail behind it with attenuation; the
+// rate_of_spread plane is rebuilt in between for SFB_KEEP_ROS handles)
+static int enqueue_list_steps(sfb_sim* s, int n) {
+    int rc;
+    if ((rc = derive_if_dirty(s))) return rc;
+    const DevParams& d = s->d;
+    for (int i = 0; i < n; ++i) {
+#if !defined(SFB_EMU) && defined(SFB_EXPERIMENT_SORT)
+        if (getenv("SFB_SORT_LIST")) {  // experiment: what an (env, y, x)-ordered list would buy
+            unsigned long long n_host = 0;
+            CU(cudaMemcpyAsync(&n_host, d.wl_count + s->lpar, 8, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            n_host = std::min<unsigned long long>(n_host, (unsigned long long)d.wl_cap);
+            static void* tmp = nullptr;
+            static size_t tmp_bytes = 0;
+            size_t need = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, need, d.wl[s->lpar], d.wl[s->lpar ^ 1], (int)n_host, 0, 62, s->stream);
+            if (need > tmp_bytes) { cudaFree(tmp); CU(cudaMalloc(&tmp, need)); tmp_bytes = need; }
+            cub::DeviceRadixSort::SortKeys(tmp, need, d.wl[s->lpar], d.wl[s->lpar ^ 1], (int)n_host, 0, 62, s->stream);
+            CU(cudaMemcpyAsync(d.wl[s->lpar], d.wl[s->lpar ^ 1], n_host * 8, cudaMemcpyDeviceToDevice, s->stream));
+        }
+#endif
+        if (s->timing) CU(cudaEventRecord(s->ev[0], s->stream));
+        if (d.keep_ros) CU(cudaMemsetAsync(d.ros_count, 0, sizeof(unsigned long long), s->stream));
+        if (s->cell_bytes == 1 && d.rtab) SFB_LAUNCH((k_front<uint8_t, true>), s->front_blocks, FRONT_THREADS, FRONT_SMEM, s->stream, d, s->parity, s->lpar);
+        else if (s->cell_bytes == 1) SFB_LAUNCH((k_front<uint8_t, false>), s->front_blocks, FRONT_THREADS, FRONT_SMEM, s->stream, d, s->parity, s->lpar);
+        else if (d.rtab) SFB_LAUNCH((k_front<uint16_t, true>), s->front_blocks, FRONT_THREADS, FRONT_SMEM, s->stream, d, s->parity, s->lpar);
+        else SFB_LAUNCH((k_front<uint16_t, false>), s->front_blocks, FRONT_THREADS, FRONT_SMEM, s->stream, d, s->parity, s->lpar);
+        s->launches_all++;
+        s->launches_step++;
+        if (s->timing) CU(cudaEventRecord(s->ev[1], s->stream));
+        if (d.keep_ros) {
+            SFB_LAUNCH(k_clear_ros, cap_grid(s, (long long)d.E * d.plane, 256), 256, 0, s->stream, d, s->parity);
+            SFB_LAUNCH(k_ros_apply, cap_grid(s, std::max<int64_t>(1024, s->list_entries_last + 65536), 256), 256, 0, s->stream, d);
+            s->launches_all += 2;
+        }
+        if (s->timing) CU(cudaEventRecord(s->ev[2], s->stream));
+        if (d.attenuate) {
+            const unsigned tail_blocks = (unsigned)std::min<int64_t>((int64_t)s->n_sm * 4, std::max<int64_t>(1, ((int64_t)d.E * d.plane + 255) / 256));
+            if (s->cell_bytes == 1) SFB_LAUNCH(k_tail<uint8_t>, tail_blocks, 256, 0, s->stream, d, s->parity, s->lpar ^ 1);
+            else SFB_LAUNCH(k_tail<uint16_t>, tail_blocks, 256, 0, s->stream, d, s->parity, s->lpar ^ 1);
+            s->launches_all++;
+            s->launches_step++;
+        }
+        s->parity ^= 1;
+        s->lpar ^= 1;
+        if (s->timing) {
+            CU(cudaEventRecord(s->ev[3], s->stream));
+            CU(cudaEventSynchronize(s->ev[3]));
+            float a = 0, b = 0, c = 0;
+            CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+            CU(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+            CU(cudaEventElapsedTime(&c, s->ev[2], s->ev[3]));
+            s->sweep_ms += a;  // k_front
+            s->rows_ms += b;   // (rate_of_spread plane, parity tests only)
+            s->eval_ms += c;   // k_tail
+            s->timed_steps++;
+        }
+    }
+    return 0;
+}
+
 static int enqueue_steps(sfb_sim* s, int n) {
     if (s->in_step) return fail(SFB_ERR_STATE, "a step is half done: call sfb_step_eval first");
     if (n <= 0) return 0;
     s->steps_since_sync = s->steps_since_sync > (1 << 20) ? s->steps_since_sync : s->steps_since_sync + n;
     int rc;
+    if (s->front_lists) return enqueue_list_steps(s, n);
     // one view of all envs on the handle's stream: single-group handles and per-kernel timing
     if (s->groups.empty() || s->timing) {
         if ((rc = enter_mode(s, 1))) return rc;
@@ -1388,6 +1629,7 @@ extern "C" int sfb_step_sweep(sfb_sim* s) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_step_sweep: null handle");
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_step_sweep: the previous sweep has not been evaluated");
     if (!s->groups.empty()) return fail(SFB_ERR_STATE, "sfb_step_sweep: create the handle with env_groups = 1");
+    if (s->front_lists) return fail(SFB_ERR_STATE, "sfb_step_sweep: not a sweep handle (create it in slab mode or with SFB_SWEEP_LDG)");
     { int rcm = enter_mode(s, 1); if (rcm) return rcm; }
     int rc;
     if ((rc = use(s))) return rc;
@@ -1454,6 +1696,12 @@ extern "C" int sfb_step_slab(sfb_sim* s, int32_t n_steps) {
     return 0;
 }
 
+extern "C" int sfb_get_parity(sfb_sim* s, int32_t* parity) {
+    if (!s || !parity) return fail(SFB_ERR_INVALID, "sfb_get_parity: null argument");
+    *parity = s->parity;
+    return 0;
+}
+
 extern "C" int sfb_flags_device(sfb_sim* s, void** flags, int64_t* n_int32) {
     if (!s || !flags || !n_int32) return fail(SFB_ERR_INVALID, "sfb_flags_device: null argument");
     *flags = (void*)(s->d.meta + (size_t)s->parity * s->d.E);
@@ -1476,6 +1724,18 @@ extern "C" int sfb_state_device(sfb_sim* s, void** state, int64_t* plane_cells, 
     if (plane_cells) *plane_cells = s->d.plane;
     if (pitch_cells) *pitch_cells = s->d.pitch;
     if (cell_bytes) *cell_bytes = s->cell_bytes;
+    return 0;
+}
+
+extern "C" int sfb_static_device(sfb_sim* s, void** records, int64_t* plane_cells, int32_t* pitch_cells, int32_t* n_sets) {
+    if (!s || !records) return fail(SFB_ERR_INVALID, "sfb_static_device: null argument");
+    int rc;
+    if ((rc = use(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));  // uploads in flight have landed
+    *records = (void*)s->d.stat;
+    if (plane_cells) *plane_cells = s->d.plane;
+    if (pitch_cells) *pitch_cells = s->d.pitch;
+    if (n_sets) *n_sets = s->d.shared_static ? 1 : s->d.E;
     return 0;
 }
 
@@ -1578,12 +1838,41 @@ extern "C" int sfb_update(sfb_sim* s, int32_t env0, int32_t n, int8_t* maps, int
     return 0;
 }
 
+extern "C" int sfb_constant_spread_update(sfb_sim* s, int32_t env0, int32_t n, int8_t* maps, int32_t rate_of_spread) {
+    if (!s || !maps) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: null argument");
+    if (rate_of_spread < 0) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: rate_of_spread %d", rate_of_spread);
+    if (s->in_step) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: a step is half done");
+    if (s->front_lists || s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: not for list or slab handles");
+    int rc;
+    if ((rc = check_env_range(s, "sfb_constant_spread_update", env0, n))) return rc;
+    if ((rc = use(s))) return rc;
+    if ((rc = upload_maps(s, env0, n, maps))) return rc;
+    const DevParams& d = s->d;
+    const unsigned grid = cap_grid(s, (long long)d.E * d.plane, 256);
+    DISPATCH(s, k_cs_prune, grid, 256, d, s->parity);
+    DISPATCH(s, k_cs_spread, grid, 256, d, s->parity, (int)rate_of_spread);
+    SFB_LAUNCH(k_cs_clock, nblocks(d.E, 128), 128, 0, s->stream, d, s->parity);
+    s->launches_all++;
+    s->parity ^= 1;
+    if (d.unit_act) CU(cudaMemsetAsync(d.unit_act, 1, (size_t)d.E * d.unit_stride, s->stream));  // cells changed behind the flags' back
+    s->full_resync = 1;
+    CU(cudaGetLastError());
+    if ((rc = download_maps(s, env0, n, maps))) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
 extern "C" int sfb_synchronize(sfb_sim* s) {
     if (!s) return fail(SFB_ERR_INVALID, "sfb_synchronize: null handle");
     int rc;
     if ((rc = use(s))) return rc;
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    if (s->front_lists) {
+        int32_t broken = 0;
+        CU(cudaMemcpy(&broken, s->d.broken, sizeof(broken), cudaMemcpyDeviceToHost));
+        if (broken == 2) return fail(SFB_ERR_STATE, "sfb_synchronize: more than %lld burning cells were overdrawn and re-ignited in one step", (long long)s->d.late_cap);
+    }
     if (s->d.slab_world > 0) {
         int32_t err = 0;
         CU(cudaMemcpy(&err, (const void*)&s->d.mailbox->error, sizeof(err), cudaMemcpyDeviceToHost));
@@ -1652,7 +1941,18 @@ static void apply_log(sfb_sim* s, const unsigned long long* log, long long n, in
             const long long m = n - n_setup;
             s->pool->run([&](unsigned k) {
                 const long long i0 = n_setup + m * k / T, i1 = n_setup + m * (k + 1) / T;
-                for (long long i = i0; i < i1; ++i) put(log[i] & 0xFFFFFFFFFFFFull, (int)(log[i] >> 48) & 7);
+                // the mirror is far larger than any cache and the entries land all over it: every store is a
+                // cache miss.  Asking for the lines a few dozen entries ahead keeps many misses in flight
+                // per thread instead of one (the loop is bound by memory latency, not bandwidth).
+                constexpr long long AHEAD = 24;
+                if (linear) {
+                    for (long long i = i0; i < i1; ++i) {
+                        if (i + AHEAD < i1) __builtin_prefetch(mirror + (log[i + AHEAD] & 0xFFFFFFFFFFFFull), 1, 0);
+                        mirror[log[i] & 0xFFFFFFFFFFFFull] = (int8_t)((log[i] >> 48) & 7);
+                    }
+                } else {
+                    for (long long i = i0; i < i1; ++i) put(log[i] & 0xFFFFFFFFFFFFull, (int)(log[i] >> 48) & 7);
+                }
             });
             return;
         }
@@ -1879,6 +2179,15 @@ extern "C" int sfb_get_queue_stats(sfb_sim* s, int64_t* entries, int64_t* capaci
     // step after next resets them
     const int par = s->parity ^ 1;
     CU(cudaStreamSynchronize(s->stream));
+    if (s->front_lists) {  // the watch list the next step reads; "overflowed" = the handle went dense
+        unsigned long long c[4];
+        CU(cudaMemcpy(c, s->list_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+        s->list_entries_last = (int64_t)c[s->lpar];
+        if (entries) *entries = (int64_t)c[s->lpar];
+        if (capacity) *capacity = s->d.wl_cap;
+        if (overflowed) *overflowed = (int32_t)(c[3] & 0xFFFFFFFFull) != 0;
+        return 0;
+    }
     int64_t tot = 0, cap = 0;
     int32_t any_ovf = 0;
     std::vector<EnvGroup*> views;
@@ -1904,6 +2213,11 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
     if ((rc = use(s))) return rc;
     const int par = s->parity ^ 1;
     CU(cudaStreamSynchronize(s->stream));
+    if (s->front_lists) {  // no row tasks: the step walks its watch list
+        if (tasks) *tasks = 0;
+        if (capacity) *capacity = 0;
+        return 0;
+    }
     int64_t tot = 0, cap = 0;
     std::vector<EnvGroup*> views;
     if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
@@ -1927,6 +2241,14 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
     const int par = s->parity ^ 1;
     CU(cudaStreamSynchronize(s->stream));
     int64_t tot = s->d.n_units, act = s->d.n_units;
+    if (s->front_lists) {
+        unsigned long long c[2];
+        CU(cudaMemcpy(c, s->list_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+        if (listed) *listed = (int64_t)c[s->lpar];
+        if (total) *total = (int64_t)s->d.E * s->d.H * s->d.W;
+        if (mode) *mode = 3;
+        return 0;
+    }
     if (s->unit_skip) {
         act = 0;
         std::vector<EnvGroup*> views;
@@ -1941,6 +2263,20 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
     if (listed) *listed = act;
     if (total) *total = tot;
     if (mode) *mode = !s->unit_skip ? 0 : (s->unit_rows ? 2 : 1);
+    return 0;
+}
+
+extern "C" int sfb_get_front_stats(sfb_sim* s, int64_t* stats, int32_t n) {
+    if (!s || !stats) return fail(SFB_ERR_INVALID, "sfb_get_front_stats: null argument");
+    if (n < 0 || n > FRONT_N_STATS) return fail(SFB_ERR_INVALID, "sfb_get_front_stats: n = %d of %d", n, FRONT_N_STATS);
+    if (!s->front_lists) return fail(SFB_ERR_STATE, "sfb_get_front_stats: not a list handle");
+    int rc;
+    if ((rc = use(s))) return rc;
+    unsigned long long c[FRONT_N_STATS];
+    CU(cudaMemcpyAsync(c, s->d.front_stats, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemsetAsync(s->d.front_stats, 0, sizeof(c), s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < n; ++k) stats[k] = (int64_t)c[k];
     return 0;
 }
 

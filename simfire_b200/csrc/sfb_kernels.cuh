@@ -157,6 +157,22 @@ struct DevParams {
     int32_t n_logs;
     int32_t log_e0[MAX_ENV_GROUPS + 1];  // log g holds envs [log_e0[g], log_e0[g + 1])
     LogRef logs[MAX_ENV_GROUPS];
+    // list-driven step (sfb_lists.cuh): one list of the cells that can change in a step
+    unsigned long long* wl[2];       // watch-list buffers; k_front reads wl[lpar] and writes wl[lpar ^ 1]
+    unsigned long long* wl_count;    // [2] entries of wl[k]
+    int64_t wl_cap;
+    uint32_t* listed;                // one bit per cell: the cell has an entry (nullptr: not a list handle)
+    int32_t* broken;                 // sticky: an append found the list full -> dense form of the same step
+    int32_t* dense_now;              // ... latched between launches: the form the next k_front takes
+    unsigned int* ticket;            // blocks of k_front that are done (the last one closes the step)
+    const double* rtab;              // [static cells][8] rate of spread per direction (ft/min), or nullptr
+    unsigned long long* ros_items;   // SFB_KEEP_ROS: (cell index, float64 bits) of this step's candidates
+    unsigned long long* ros_count;
+    int64_t ros_cap;
+    unsigned long long* late;        // cells that re-ignite while still a source for this step (rewritten by the last block)
+    unsigned int* late_count;
+    int64_t late_cap;
+    unsigned long long* front_stats; // [FRONT_N_STATS] accumulated by k_front, read and reset by sfb_get_front_stats
 };
 
 __device__ __forceinline__ const LogRef& log_of_env(const DevParams& p, int env) {
@@ -271,10 +287,17 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
     double ros;
     if (dir != DIR_NONE) {
         const long long cell = idx - (long long)env * p.plane;
-        const float4* rp = reinterpret_cast<const float4*>(p.drv + (p.shared_static ? cell : idx));
-        const float4 t0 = __ldg(rp), t1 = __ldg(rp + 1), e = __ldg(rp + 2);
-        const SfbFuelTerms t = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-        ros = sfb_spread_from_terms(dir, t, e.x, e.y, e.z, e.w) * p.dt;  // rothermel.py:4-136, fire.py:696
+        const long long sc = p.shared_static ? cell : idx;
+        if (p.rtab) {
+            // every input of rothermel.py:4-136 is static per (cell, direction): k_derive_static evaluated
+            // the eight float64 rates of the cell once, through the same device function as below
+            ros = __ldg(p.rtab + sc * 8 + dir) * p.dt;  // fire.py:696
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(p.drv + sc);
+            const float4 t0 = __ldg(rp), t1 = __ldg(rp + 1), e = __ldg(rp + 2);
+            const SfbFuelTerms t = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            ros = sfb_spread_from_terms(dir, t, e.x, e.y, e.z, e.w) * p.dt;  // rothermel.py:4-136, fire.py:696
+        }
         if (s & ST_LINE_BIT) ros = p.attenuate ? ros - line_attenuation(s) : 0.0;  // fire.py:271-282
     } else {
         // control line that no fire touches: attenuated only if the step got past the

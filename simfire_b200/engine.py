@@ -60,6 +60,7 @@ class FireEngine:
         unit_skip: Optional[bool] = None,
         unit_chunks: bool = False,
         step_graph: bool = False,
+        front_lists: bool = False,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -84,6 +85,7 @@ class FireEngine:
             flags |= _lib.UNIT_SKIP_ON if unit_skip else _lib.UNIT_SKIP_OFF
         flags |= _lib.UNIT_CHUNKS if unit_chunks else 0  # chunk-of-rows units + sweep instead of row units
         flags |= _lib.STEP_GRAPH if step_graph else 0    # multi-group handles: pairs of steps as one CUDA graph
+        flags |= _lib.FRONT_LISTS if front_lists else 0  # force the list-driven step (the default without sweep knobs)
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -186,6 +188,13 @@ class FireEngine:
         _lib.check(self._lib.sfb_update(self._h, int(env0), n, _ptr(maps), _ptr(status)))
         return status
 
+    def constant_spread_update(self, maps: np.ndarray, rate_of_spread: int, env0: int = 0) -> None:
+        """`fire_map = ConstantSpreadFireManager.update(fire_map)` (fire.py:754-787) with host maps, in place."""
+        if maps.dtype != np.int8 or not maps.flags.c_contiguous:
+            raise ValueError("constant_spread_update: maps must be a C-contiguous int8 array")
+        n = maps.size // (self.H * self.W)
+        _lib.check(self._lib.sfb_constant_spread_update(self._h, int(env0), n, _ptr(maps), int(rate_of_spread)))
+
     def synchronize(self) -> None:
         _lib.check(self._lib.sfb_synchronize(self._h))
 
@@ -194,6 +203,8 @@ class FireEngine:
         n = self.E - env0 if n is None else n
         if out is None:
             out = np.empty((n, self.H, self.W), dtype=np.int8)
+        elif out.dtype != np.int8 or not out.flags.c_contiguous or out.size != n * self.H * self.W:
+            raise ValueError("fire_map: out must be a C-contiguous int8 array of n*H*W cells")
         _lib.check(self._lib.sfb_get_fire_map(self._h, int(env0), int(n), _ptr(out)))
         return out
 
@@ -241,6 +252,23 @@ class FireEngine:
             __cuda_array_interface__ = {
                 "shape": (self.E, self.H, self.W), "typestr": "|i1", "data": (p.value, False),
                 "version": 3, "strides": None,
+            }  # fmt: skip
+
+        return torch.as_tensor(_Iface(), device=f"cuda:{self.device}")
+
+    def static_device(self):
+        """Zero-copy float32 CUDA tensor [n_sets, H, W, 8] over the static records (w_0, delta, M_x, sigma,
+        U, U_dir, slope_mag, slope_dir per cell; n_sets = 1 when the envs share one terrain).  A strided
+        view of the library's own memory: read-only for the caller."""
+        import torch
+
+        p, plane, pitch, sets = C.c_void_p(), C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.sfb_static_device(self._h, C.byref(p), C.byref(plane), C.byref(pitch), C.byref(sets)))
+
+        class _Iface:
+            __cuda_array_interface__ = {
+                "shape": (int(sets.value), self.H, self.W, 8), "typestr": "<f4", "data": (p.value, True), "version": 3,
+                "strides": (int(plane.value) * 32, int(pitch.value) * 32, 32, 4),
             }  # fmt: skip
 
         return torch.as_tensor(_Iface(), device=f"cuda:{self.device}")
@@ -309,9 +337,9 @@ class FireEngine:
         return out
 
     def _parity_probe(self) -> int:
-        # parity = number of completed steps mod 2 (every handle starts at 0)
-        _, step_kernels = self.launch_counts()
-        return (step_kernels // 3) % 2
+        par = C.c_int32()
+        _lib.check(self._lib.sfb_get_parity(self._h, C.byref(par)))
+        return int(par.value)
 
     def flags_parity(self) -> int:
         return self._parity_probe()
@@ -352,15 +380,23 @@ class FireEngine:
         return int(a.value), int(b.value)
 
     def unit_mode(self) -> str:
-        """'dense' (every unit swept), 'chunks' (flagged chunks swept) or 'rows' (flagged rows are the row tasks)."""
+        """'dense' (every unit swept), 'chunks' (flagged chunks swept), 'rows' (flagged rows are the row tasks)
+        or 'lists' (the list-driven step: no units, one watch list)."""
         a, b, m = C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
-        return ("dense", "chunks", "rows")[int(m.value)]
+        return ("dense", "chunks", "rows", "lists")[int(m.value)]
 
     def queue_stats(self):
         a, b, o = C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(self._lib.sfb_get_queue_stats(self._h, C.byref(a), C.byref(b), C.byref(o)))
         return int(a.value), int(b.value), bool(o.value)
+
+    def front_stats(self) -> dict:
+        """List handles: what k_front did since the previous call (the counters are reset)."""
+        a = (C.c_int64 * 7)()
+        _lib.check(self._lib.sfb_get_front_stats(self._h, a, 7))
+        names = ("examined", "candidates", "ignited", "pruned", "joined", "entries_read", "neighbourhoods_read")
+        return {k: int(v) for k, v in zip(names, a)}
 
     def debug_stall(self, microseconds: int) -> None:
         """Test knob: keep the engine's stream busy for a while before the next call's work."""

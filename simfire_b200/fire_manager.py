@@ -191,3 +191,67 @@ class RothermelFireManager:
 
 
 __all__ = ["RothermelFireManager", "BurnStatus", "GameStatus"]
+
+
+class ConstantSpreadFireManager:
+    """
+    Drop-in for `simfire.game.managers.fire.ConstantSpreadFireManager` (fire.py:722-787): same
+    constructor, same `update(fire_map) -> fire_map`, run on the device through
+    `sfb_constant_spread_update`.  The behaviour is the reference's as it executes, including its
+    quirk: the Fire sprites that `update` appends have no duration entry, so the next call's
+    `_prune_sprites` slices them off again (fire.py:148-155); the cells they marked stay BURNING
+    and never spread.  The grid size is taken from the first `fire_map` (the reference's
+    constructor has none either).  `sprites` lists the (x, y) of the sprites that still exist.
+    """
+
+    def __init__(self, init_pos: Tuple[int, int], fire_size: int, max_fire_duration: int, rate_of_spread: int,
+                 *, device: int = 0) -> None:  # fmt: skip
+        self.init_pos = tuple(int(v) for v in init_pos)
+        self.fire_size = fire_size
+        self.max_fire_duration = int(max_fire_duration)
+        self.rate_of_spread = int(rate_of_spread)
+        # FireManager.__init__ defaults (fire.py:49-103)
+        self.attenuate_line_ros, self.headless, self.diagonal_spread = True, False, True
+        self.device = device
+        self._engine: Optional[FireEngine] = None
+        self._calls = 0
+
+    def _ensure_engine(self, shape) -> FireEngine:
+        if self._engine is None:
+            H, W = shape
+            self._engine = FireEngine(H, W, 1, pixel_scale=1.0, update_rate=1.0, max_fire_duration=self.max_fire_duration,
+                                      attenuate_line_ros=True, diagonal_spread=True, device=self.device)  # fmt: skip
+            self._engine.reset([self.init_pos])  # the initial sprite (fire.py:101-103)
+        elif (self._engine.H, self._engine.W) != tuple(shape):
+            raise AssertionError(f"fire_map of shape {tuple(shape)}, the manager was started on {(self._engine.H, self._engine.W)}")
+        return self._engine
+
+    def update(self, fire_map: np.ndarray) -> np.ndarray:
+        fm = np.asarray(fire_map)
+        eng = self._ensure_engine(fm.shape)
+        buf = np.ascontiguousarray(fm.astype(np.int8)).reshape(1, *fm.shape)
+        eng.constant_spread_update(buf, self.rate_of_spread)
+        self._calls += 1
+        fire_map[...] = buf[0]  # the reference mutates the caller's array in place (fire.py:140, :779)
+        return fire_map
+
+    @property
+    def sprites(self):
+        # the initial sprite until it is pruned; the sprites appended by the spreading call live until the next call
+        if self._engine is None:
+            return [self.init_pos]
+        age = self._engine.plane("age", 0)
+        ys, xs = np.nonzero(age >= 0)
+        return [(int(x), int(y)) for y, x in zip(ys, xs)]
+
+    @property
+    def durations(self):
+        if self._engine is None:
+            return [0]
+        age = self._engine.plane("age", 0)
+        return [int(a) for a in age[age >= 0]]
+
+    def close(self) -> None:
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None

@@ -42,6 +42,16 @@ def _static_planes(config: Config):
                 slope_mag=0.0, slope_dir=0.0), elev  # fmt: skip
 
 
+def _engine_key(config: Config):
+    """Everything `_engine_from_config` bakes into an engine: the reference builds a new
+    RothermelFireManager from the CURRENT config on every reset() (simulation.py:273-290), and its config
+    objects are mutable, so a reset must notice a change of any of these."""
+    fp = FuelParticle()
+    return (tuple(config.area.screen_size), float(config.area.pixel_scale), float(config.simulation.update_rate),
+            int(config.fire.max_fire_duration), config.simulation.runtime, bool(config.mitigation.ros_attenuation),
+            bool(config.fire.diagonal_spread), (fp.h, fp.S_T, fp.S_e, fp.p_p), float(config.environment.moisture))  # fmt: skip
+
+
 def _engine_from_config(config: Config, E: int, device: int, shared_static: bool, **kw) -> FireEngine:
     fp = FuelParticle()
     H, W = config.area.screen_size
@@ -52,6 +62,15 @@ def _engine_from_config(config: Config, E: int, device: int, shared_static: bool
         fuel_particle=(fp.h, fp.S_T, fp.S_e, fp.p_p), M_f=config.environment.moisture,
         shared_static=shared_static, device=device, **kw,
     )  # fmt: skip
+
+
+def _attribute_tensors(engine: FireEngine, elevations: np.ndarray, static_set: int):
+    import torch
+
+    rec = engine.static_device()[static_set]  # (H, W, 8) strided view, no copy
+    return {"w_0": rec[..., 0], "sigma": rec[..., 3].to(torch.int32), "delta": rec[..., 1], "M_x": rec[..., 2],
+            "elevation": torch.as_tensor(np.asarray(elevations), device=rec.device),
+            "wind_speed": rec[..., 4], "wind_direction": rec[..., 5]}  # fmt: skip
 
 
 class FireSimulation:
@@ -68,10 +87,12 @@ class FireSimulation:
     # -- lifecycle (simulation.py:202-214) ----------------------------------------------------
     def reset(self) -> None:
         H, W = self.config.area.screen_size
-        if self._engine is None or (self._engine.H, self._engine.W) != (H, W):
+        key = _engine_key(self.config)
+        if self._engine is None or getattr(self, "_engine_key", None) != key:
             if self._engine is not None:
                 self._engine.close()
             self._engine = _engine_from_config(self.config, 1, self.device, shared_static=True)
+            self._engine_key = key
         self._planes, self._elevations = _static_planes(self.config)
         self._engine.set_static(self._planes)
         self._engine.set_elevation(self._elevations)  # slopes on the device (fire.py:436-449)
@@ -96,8 +117,13 @@ class FireSimulation:
     # -- fire_map: int64 (H, W) like the reference (simulation.py:561-564), fetched lazily -----
     @property
     def fire_map(self) -> np.ndarray:
+        """int64 (H, W) copy of the device map, refreshed after every run() / mitigation call.  In the
+        reference this is the live array and callers may write into it; here the state lives on the
+        device, so the copy is READ-ONLY (an in-place write raises instead of being silently lost):
+        assign a whole map (`sim.fire_map = m`, load_mitigation) or use update_mitigation()."""
         if self._fire_map is None:
             self._fire_map = self._engine.fire_map(0, 1)[0].astype(np.int64)
+            self._fire_map.setflags(write=False)
         return self._fire_map
 
     @fire_map.setter
@@ -147,6 +173,12 @@ class FireSimulation:
                 "elevation": np.asarray(self.config.terrain.topography_layer.data).reshape(self._elevations.shape),
                 "wind_speed": self.config.wind.speed,
                 "wind_direction": self.config.wind.direction}  # fmt: skip
+
+    def get_attribute_data_device(self):
+        """`get_attribute_data` (simulation.py:376-403) as CUDA tensors for an on-device policy: zero-copy
+        float32 (H, W) views of the stepper's own static records for the fuel and wind planes (sigma as int32:
+        torch has no uint32 arithmetic; the reference's host dtype is uint32), elevation uploaded once."""
+        return _attribute_tensors(self._engine, self._elevations, 0)
 
     # -- between-step mutations -------------------------------------------------------------------
     def load_mitigation(self, mitigation_map: np.ndarray) -> None:
@@ -372,6 +404,7 @@ class BatchedFireSimulation:
         self._engine.reset(pos)
         H, W = config.area.screen_size
         self.agent_positions = np.zeros((self.num_envs, H, W), dtype=np.int64)
+        self._agents_dev = None
 
     @property
     def engine(self) -> FireEngine:
@@ -383,6 +416,8 @@ class BatchedFireSimulation:
             positions = [self.config.fire.fire_initial_position] * len(envs)
         self._engine.reset(positions, envs=envs)
         self.agent_positions[envs] = 0
+        if self._agents_dev is not None:
+            self._agents_dev[envs] = 0
 
     def update_mitigation(self, points) -> None:
         pts = np.asarray(points, dtype=np.int32).reshape(-1, 4)
@@ -392,8 +427,13 @@ class BatchedFireSimulation:
     def update_agent_positions(self, points) -> None:
         for env, column, row, agent_id in points:
             a = self.agent_positions[env]
+            old = np.argwhere(a == agent_id)
             a[a == agent_id] = 0
             a[row, column] = agent_id
+            if self._agents_dev is not None:  # a few scalar writes per agent, no plane crosses PCIe
+                for oy, ox in old:
+                    self._agents_dev[env, int(oy), int(ox)] = 0
+                self._agents_dev[env, row, column] = agent_id
 
     def run(self, time: Union[str, int], out: Optional[np.ndarray] = None):
         if isinstance(time, str):
@@ -414,6 +454,20 @@ class BatchedFireSimulation:
 
     def fire_maps_device(self):
         return self._engine.fire_map_device()
+
+    def get_attribute_data_device(self):
+        """The shared terrain's attribute planes as CUDA tensors (see FireSimulation.get_attribute_data_device)."""
+        return _attribute_tensors(self._engine, self._elevations, 0)
+
+    @property
+    def agent_positions_device(self):
+        """`agent_positions` (simulation.py:480-499) as an int16 CUDA tensor [E, H, W], kept up to date by
+        update_agent_positions from the first access on (RL observation without a host round trip)."""
+        import torch
+
+        if self._agents_dev is None:
+            self._agents_dev = torch.as_tensor(self.agent_positions.astype(np.int16), device=f"cuda:{self._engine.device}")
+        return self._agents_dev
 
     @property
     def elapsed_time(self) -> np.ndarray:

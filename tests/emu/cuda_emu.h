@@ -53,6 +53,9 @@ struct __attribute__((aligned(16))) uint4 {
 struct __attribute__((aligned(16))) float4 {
     float x, y, z, w;
 };
+struct __attribute__((aligned(16))) int4 {
+    int x, y, z, w;
+};
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -78,6 +81,29 @@ static inline T atomicAdd(T* p, V v) {
     T old = *p;
     *p = (T)(old + (T)v);
     return old;
+}
+
+template <class T, class V>
+static inline T atomicOr(T* p, V v) {
+    T old = *p;
+    *p = (T)(old | (T)v);
+    return old;
+}
+template <class T, class V>
+static inline T atomicAnd(T* p, V v) {
+    T old = *p;
+    *p = (T)(old & (T)v);
+    return old;
+}
+static inline long long __double_as_longlong(double d) {
+    long long v;
+    memcpy(&v, &d, 8);
+    return v;
+}
+static inline double __longlong_as_double(long long v) {
+    double d;
+    memcpy(&d, &v, 8);
+    return d;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -265,6 +291,11 @@ static inline cudaError_t cudaMalloc(void** p, size_t bytes) {
 #endif
     if (*p) memset(*p, 0xA5, bytes);  // device memory is not zero-initialised
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) {
+    *free_b = (size_t)8 << 30;
+    *total_b = (size_t)16 << 30;
+    return cudaSuccess;
 }
 static inline cudaError_t cudaFree(void* p) {
     free(p);

@@ -25,7 +25,7 @@ def test_reference_arm_line():
     assert j["impl"] == "reference" and BASE_KEYS <= set(j)
     assert j["metric"] == "cell_updates_per_s" and j["unit"] == "cell-updates/s" and j["higher_is_better"] is True
     assert j["value"] > 0 and j["gpu_launches"] == 0 and j["vs_baseline"] is None
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["config"]["workload"] == "small"
 
@@ -38,13 +38,17 @@ def test_reference_arm_other_ranks_stay_silent():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    j = _run(["--workload", "small", "--steps", "20", "--warmup", "3", "--cpu-budget", "2"])
+    j = _run(["--workload", "small", "--steps", "20", "--warmup", "3", "--cpu-budget", "2", "--parity-updates", "40"])
     assert BASE_KEYS | {"roofline", "clocks", "cpu_baseline"} <= set(j)
     assert j["n_gpus"] == 1 and j["steps"] == 20 and j["value"] > 0 and j["scaling"] == "weak"
     r = j["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert j["gpu_launches"] > 0 and j["gpu_launches"] % 20 == 0
+    assert r["kernel"] == "k_front" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["dense_sweep"]["bound"] == "hbm"
+    assert j["gpu_launches"] == 20  # the list-driven step is one kernel (no attenuation in this workload)
     e = j["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["mirror_matches_download"]
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == 1
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1
+    assert cb["parity"]["full_grid"]["fire_map_equal"] is True and cb["parity"]["windows"]["all_equal"] is True
+    assert j["fire_age"]["updates"] == 2000
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

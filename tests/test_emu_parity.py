@@ -19,7 +19,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # need a CUDA context of torch's own (device tensors around raw pointers): not emulated
-NEEDS_TORCH_CUDA = "not observation_tensor and not row_slabs and not device_view"
+NEEDS_TORCH_CUDA = "not observation_tensor and not row_slabs and not device_view"  # (device_view: torch tensors over raw pointers)
 
 
 def _run(args, timeout=900):
@@ -115,10 +115,11 @@ def test_bench_gpu_arm_dry_run_under_emulation():
     bench before the GPU box does.  The numbers mean nothing; the line's shape is checked."""
     import json
 
-    for skip in ("on", "off"):
+    for front in ("lists", "rows", "dense"):
         res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dry_run.py"), "--workload", "small",
                               "--steps", "3", "--warmup", "3", "--burn-in", "5", "--roofline-steps", "2", "--e2e-steps", "3",
-                              *(["--no-cpu-baseline"] if skip == "off" else ["--cpu-budget", "1"]), "--unit-skip", skip],
+                              "--age-curve", "50" if front == "lists" else "0", "--parity-updates", "12",
+                              *(["--no-cpu-baseline"] if front == "dense" else ["--cpu-budget", "1"]), "--front", front],
                              cwd=ROOT, env=_emu_env(), capture_output=True, text=True, timeout=600)  # fmt: skip
         assert res.returncode == 0, res.stderr[-2000:]
         line = json.loads(res.stdout.strip().splitlines()[-1])
@@ -128,13 +129,19 @@ def test_bench_gpu_arm_dry_run_under_emulation():
         assert line["e2e"]["mirror_matches_download"] is True
         assert line["gpu_launches"] > 0
         rf = line["roofline"]
-        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "unit_skipping", "kernel_ms_per_launch"):
+        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel_ms_per_launch", "front"):
             assert key in rf, key
-        assert rf["unit_skipping"]["on"] == (skip == "on")
-        if skip == "off":
+        assert rf["front"] == front
+        if front == "lists":
+            assert rf["kernel"] == "k_front" and rf["per_launch"]["examined"] > 0 and not rf["went_dense"]
+            assert line["gpu_launches"] == 3  # one kernel per step (the small workload has no attenuation)
+            assert line["fire_age"]["updates"] == 50 and len(line["fire_age"]["blocks"]) == 1
+        if front == "dense":
             assert rf["unit_skipping"]["units_listed"] == rf["unit_skipping"]["units_total"]
-        else:  # the CPU leg also checks the device against the oracle on the env it timed
-            assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["parity"]["fire_map_equal"] is True
+        else:  # the CPU leg also checks the device against the reference (or the port) on the envs it names
+            cb = line["cpu_baseline"]
+            assert cb["kind"] in ("reference", "port") and cb["parity"]["full_grid"]["fire_map_equal"] is True
+            assert cb["parity"]["windows"]["all_equal"] is True and cb["parity"]["windows"]["updates"] == 12
             ds = rf["dense_sweep"]  # ... and the dense TMA sweep is timed beside the default front end
             assert ds["bound"] == "hbm" and ds["kernel"].startswith("k_sweep") and ds["bytes_per_launch"] >= 256 * 256 * 64
 
@@ -150,6 +157,7 @@ def test_bench_full_burn_dry_run_under_emulation():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["result"]["unburned_cells"] == 0 and line["result"]["burned_cells"] == 128 * 128
     assert line["cpu_baseline"]["parity"] == {"fire_map_equal": True, "updates_equal": True}
+    assert line["cpu_baseline"]["kind"] in ("reference", "port")
 
 
 def test_smoke_under_emulation():

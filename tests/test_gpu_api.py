@@ -438,3 +438,96 @@ def test_device_slopes_match_numpy_gradient():
         eng.set_elevation(sc["elevations"])
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
+
+
+def test_constant_spread_manager_replays_reference():
+    """`ConstantSpreadFireManager.update` (fire.py:754-787) against trajectories recorded from the unmodified
+    reference (tests/golden/gen_constant_golden.py): the reference's own test geometry (test_fire.py:399-470),
+    a corner ignition, control lines / burned cells around the fire, a sprite pruned before it can spread,
+    rate_of_spread 0 -- fire_map after every call, and how many sprites / durations are left."""
+    from simfire_b200.enums import BurnStatus
+    from simfire_b200.fire_manager import ConstantSpreadFireManager
+
+    z = np.load(f"{GOLDEN}/constant_spread.npz")
+    for name in z["names"]:
+        H, W, x0, y0, max_dur, ros, calls = (int(v) for v in z[f"{name}_cfg"])
+        mgr = ConstantSpreadFireManager((x0, y0), 2, max_dur, ros)
+        fire_map = np.zeros((H, W))  # float64, like the reference's test
+        for x, y, st in z[f"{name}_painted"]:
+            fire_map[y, x] = st
+        for k in range(calls):
+            out = mgr.update(fire_map)
+            assert out is fire_map and out.dtype == np.float64
+            assert np.array_equal(out.astype(np.int8), z[f"{name}_maps"][k]), f"{name}: call {k + 1}"
+            # sprites with a duration entry (the ones the reference's next prune keeps)
+            assert len(mgr.durations) == min(int(z[f"{name}_n_durations"][k]), int(z[f"{name}_n_sprites"][k])), f"{name}: call {k + 1}"
+        mgr.close()
+    # the reference's own assertions (test_fire.py:431-470): nothing spreads before rate_of_spread calls, then all 8 neighbours
+    mgr = ConstantSpreadFireManager((5, 2), 2, 4, 3)
+    fm = np.zeros((20, 28))
+    for _ in range(3):
+        fm = mgr.update(fm)
+        assert (fm == BurnStatus.BURNING).sum() == 0
+    fm = mgr.update(fm)
+    ys, xs = np.nonzero(fm == BurnStatus.BURNING)
+    assert sorted(zip(xs.tolist(), ys.tolist())) == sorted((5 + dx, 2 + dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0))
+    mgr.close()
+
+
+def test_device_view_of_attributes_and_agent_positions():
+    """`get_attribute_data` and `agent_positions` as device tensors (torch CUDA context
+    needed: not run under the emulator).  The fuel / wind planes are zero-copy strided views of the stepper's
+    own static records and must equal the host dictionaries of simulation.py:376-403."""
+    import torch
+
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import BatchedFireSimulation, FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_gauss48.npz")
+    cfg = Config(config_dict=yaml.safe_load(str(z["config_yaml"])))
+    sim = FireSimulation(cfg)
+    host, dev = sim.get_attribute_data(), sim.get_attribute_data_device()
+    assert set(dev) == set(host)
+    for k, v in dev.items():
+        assert v.is_cuda and tuple(v.shape) == tuple(cfg.area.screen_size)
+        np.testing.assert_allclose(v.cpu().numpy().astype(np.float64), np.broadcast_to(np.asarray(host[k], dtype=np.float64), v.shape),
+                                   rtol=1e-6 if k != "sigma" else 0)  # fmt: skip
+    assert dev["sigma"].dtype == torch.int32 and dev["w_0"].dtype == torch.float32
+    sim.close()
+    bat = BatchedFireSimulation(cfg, 3)
+    a = bat.agent_positions_device
+    assert a.is_cuda and tuple(a.shape) == (3, *cfg.area.screen_size) and int(a.abs().sum()) == 0
+    bat.update_agent_positions([(0, 5, 6, 1), (2, 7, 8, 2)])
+    bat.update_agent_positions([(0, 9, 6, 1)])  # agent 1 of env 0 moves
+    assert np.array_equal(bat.agent_positions_device.cpu().numpy(), bat.agent_positions.astype(np.int16))
+    assert bat.agent_positions[0, 6, 9] == 1 and bat.agent_positions[0, 6, 5] == 0
+    bat.reset(envs=[2])
+    assert int(bat.agent_positions_device[2].abs().sum()) == 0
+    for k, v in bat.get_attribute_data_device().items():
+        assert v.is_cuda
+    bat.close()
+
+
+def test_reset_rebuilds_the_engine_when_the_config_changed():
+    """The reference builds a new RothermelFireManager from the CURRENT config on every reset()
+    (simulation.py:273-290) and its config objects are mutable; so must reset() here.  Also: `fire_map` is
+    a read-only copy (in-place writes raise instead of being silently lost)."""
+    from simfire_b200.config import Config
+    from simfire_b200.simulation import FireSimulation
+
+    z = np.load(f"{GOLDEN}/api_sequence_flat64.npz")
+    sim = FireSimulation(Config(config_dict=yaml.safe_load(str(z["config_yaml"]))))
+    sim.run(6)
+    base = sim.fire_map.copy()
+    with pytest.raises(ValueError):
+        sim.fire_map[0, 0] = 3
+    sim.config.fire.max_fire_duration = 1  # sprites burn out after one update
+    sim.reset()
+    sim.run(6)
+    short = sim.fire_map.copy()
+    assert not np.array_equal(short, base)
+    ref = FireSimulation(sim.config)  # a fresh simulation of the edited config
+    ref.run(6)
+    assert np.array_equal(ref.fire_map, short)
+    ref.close()
+    sim.close()

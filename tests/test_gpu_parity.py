@@ -107,8 +107,9 @@ def test_golden_trajectory(name):
                                   "scenario_b_models_4nbr_noatt", "scenario_f_max_time"])  # fmt: skip
 @pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8",
                                      "skip", "skip_wide", "skip_ldg_rows8", "skip_overflow", "noskip",
-                                     "rowunits", "rowunits_wide", "rowunits_overflow"])
-def test_golden_trajectory_variants(name, variant):
+                                     "rowunits", "rowunits_wide", "rowunits_overflow",
+                                     "lists", "lists_wide", "lists_overflow", "lists_no_rate_table"])
+def test_golden_trajectory_variants(name, variant, monkeypatch):
     """The 16-bit cell layout, the dense fallback taken on queue overflow, other chunk
     heights and the non-TMA streaming front end must give the same trajectories."""
     sc = load_scenario(name)
@@ -122,12 +123,23 @@ def test_golden_trajectory_variants(name, variant):
           "skip_overflow": dict(unit_skip=True, unit_chunks=True, queue_capacity=3), "noskip": dict(unit_skip=False),
           # ... with one row per unit: the flagged rows are the row tasks, nothing is swept
           "rowunits": dict(unit_skip=True), "rowunits_wide": dict(unit_skip=True, wide_cells=True),
-          "rowunits_overflow": dict(unit_skip=True, queue_capacity=3)}[variant]  # fmt: skip
+          "rowunits_overflow": dict(unit_skip=True, queue_capacity=3),
+          # the list-driven step (k_front / k_tail): one watch list instead of a sweep; a list that is too short
+          # turns the handle to the dense form of the same per-cell routine
+          "lists": dict(front_lists=True), "lists_wide": dict(front_lists=True, wide_cells=True),
+          "lists_overflow": dict(front_lists=True, queue_capacity=3),
+          "lists_no_rate_table": dict(front_lists=True)}[variant]  # fmt: skip
+    if variant == "lists_no_rate_table":
+        monkeypatch.setenv("SFB_NO_RTAB", "1")  # rates evaluated in the step instead of looked up
     with engine_for(sc, **kw) as eng:
+        if variant.startswith("lists"):
+            assert eng.unit_mode() == "lists"
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
-        if variant == "queue_overflow":
+        if variant in ("queue_overflow", "lists_overflow"):
             assert eng.queue_stats()[1] == 3
+        if variant == "lists_overflow":
+            assert eng.queue_stats()[2]  # the handle went dense
 
 
 def test_batched_envs_are_independent():
@@ -198,7 +210,7 @@ def test_env_groups_on_streams_equal_one_group(groups):
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
 
 
-@pytest.mark.parametrize("front_end", ["tma", "ldg", "rows"])
+@pytest.mark.parametrize("front_end", ["tma", "ldg", "rows", "lists"])
 @pytest.mark.parametrize("attenuate", [True, False])
 def test_unit_skipping_changes_nothing(front_end, attenuate):
     """Looking only at the flagged units (chunks of rows that are then swept with either front end,
@@ -220,8 +232,12 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
     lines0 = [(e, x, 60, 3 + (x % 3)) for e in range(E) for x in range(400, 700)]
     engines = []
     for skip in (False, True):
-        eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, unit_chunks=(front_end != "rows"),
-                         sweep_ldg=(front_end == "ldg"), rows_per_chunk=8, track_changes=True, env_groups=2, **kw)  # fmt: skip
+        if front_end == "lists" and skip:  # the list-driven step against the dense sweep
+            eng = FireEngine(H, W, E, shared_static=True, front_lists=True, track_changes=True, **kw)
+            assert eng.unit_mode() == "lists"
+        else:
+            eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, unit_chunks=(front_end not in ("rows", "lists")),
+                             sweep_ldg=(front_end == "ldg"), rows_per_chunk=8, track_changes=True, env_groups=2, **kw)  # fmt: skip
         eng.set_static(wl.planes)
         eng.reset(starts)
         eng.apply_points(lines0)

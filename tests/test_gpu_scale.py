@@ -18,7 +18,7 @@ def _oracle(wl, start):
     return DenseFire(wl.planes, DenseParams(**wl.engine_kwargs()), tuple(int(v) for v in start))
 
 
-def _run_against_oracle(wl, start, n_steps, check_every=1, min_steps=15, **engine_kw):
+def _run_against_oracle(wl, start, n_steps, check_every=1, **engine_kw):
     """Steps engine and oracle together; fire_map must be identical at every checked step.
     The oracle also yields the smallest relative distance of any ignition test from the
     threshold: float32 libm differences (<= 1e-6) cannot flip a test further away than that."""
@@ -37,11 +37,11 @@ def _run_against_oracle(wl, start, n_steps, check_every=1, min_steps=15, **engin
                 margin = min(margin, float(np.min(np.abs(o.burn[changed] - wl.pixel_scale)) / max(wl.pixel_scale, 1e-9)))
             eng.step(1)
             if margin < 2e-5:
-                # an ignition test this close to the threshold could be flipped by a 1-ulp libm
-                # difference: everything up to the previous step has been verified, stop here
-                if step <= min_steps:
-                    pytest.skip(f"oracle ignition margin {margin:.1e} already at step {step}")
-                return o
+                # an ignition test this close to the threshold could be flipped by a 1-ulp libm difference.
+                # The inputs of these tests are seeded and were chosen (with the oracle, in the dev container)
+                # so that this never happens: if it does, the input changed -- a failure, not a shorter pass.
+                pytest.fail(f"test input: oracle ignition margin {margin:.1e} at step {step} of {n_steps} "
+                            f"({step - 1} steps verified); choose another seed")
             if step % check_every == 0 or st != 1:
                 gst, gel, gn = eng.status()
                 assert int(gst[0]) == st and float(gel[0]) == o.elapsed_time and int(gn[0]) == o.step_count, step
@@ -83,6 +83,64 @@ def test_cfg2_1024_against_oracle_short():
     _run_against_oracle(wl, wl.init_pos, 40, check_every=20)
 
 
+@pytest.mark.parametrize("front", ["lists", "rows"])
+def test_target_batch_2048x1024_against_oracle(front):
+    """The benchmarked configuration itself: 2048 x 2048 x 1024 envs on the bench terrain with the bench's
+    ignition cells (bench.bench_starts), 150 updates, eight envs compared with the NumPy oracle -- each on
+    the window its fire provably cannot leave in that many updates (oracle.reference_runner.window_around:
+    cells outside it are UNBURNED in the full-grid run, which the test also checks on the device map).
+    fire_map every 10 updates, status / elapsed_time / update count, and the float64 burn plane at the
+    end.  The envs are bench.PARITY_ENVS: screened with tools/screen_parity_envs.py so that no ignition
+    test comes within 2e-5 of the threshold (re-checked here: a smaller margin fails the test)."""
+    from bench import PARITY_ENVS, bench_starts
+    from oracle.dense_numpy import DenseFire, DenseParams
+    from oracle.reference_runner import window_around
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    H = W = 2048
+    E, n_updates = 1024, 150
+    wl = synthetic_operational(H, W, seed=0, flat=True)
+    starts = bench_starts(wl, E, 0)
+    envs = PARITY_ENVS["target"]
+    wins, oracles = [], []
+    for e in envs:
+        y0, x0, h, w = win = window_around(starts[e], n_updates, H, W)
+        planes = {k: np.ascontiguousarray(np.broadcast_to(v, (H, W))[y0 : y0 + h, x0 : x0 + w]) for k, v in wl.planes.items()}
+        oracles.append(DenseFire(planes, DenseParams(**wl.engine_kwargs()), (int(starts[e][0]) - x0, int(starts[e][1]) - y0)))
+        wins.append(win)
+    kw = dict(front_lists=True) if front == "lists" else dict(unit_skip=True)
+    margin = np.inf
+    with FireEngine(H, W, E, shared_static=True, **kw, **wl.engine_kwargs()) as eng:
+        assert eng.unit_mode() == front
+        eng.set_static(wl.planes)
+        eng.reset(starts)
+        for block in range(n_updates // 10):
+            eng.step(10)
+            st, el, cnt = eng.status()
+            for k, e in enumerate(envs):
+                o = oracles[k]
+                for _ in range(10):
+                    before = o.burn.copy()
+                    o.step()
+                    ch = o.burn != before
+                    if ch.any():
+                        margin = min(margin, float(np.min(np.abs(o.burn[ch] - wl.pixel_scale)) / wl.pixel_scale))
+                assert margin > 2e-5, f"test input: ignition margin {margin:.1e} in env {e}: re-screen bench.PARITY_ENVS"
+                y0, x0, h, w = wins[k]
+                got = eng.fire_map(e, 1)[0]
+                assert np.array_equal(got[y0 : y0 + h, x0 : x0 + w], o.status), f"env {e}, update {10 * (block + 1)}"
+                assert (got != 0).sum() == (o.status != 0).sum(), f"env {e}: cells outside the window changed"
+                assert (int(st[e]), float(el[e]), int(cnt[e])) == (o.game_status, o.elapsed_time, o.step_count), e
+        for k, e in enumerate(envs):
+            y0, x0, h, w = wins[k]
+            burn = eng.plane("burn", e)
+            scale = max(1.0, float(np.max(np.abs(oracles[k].burn))))
+            np.testing.assert_allclose(burn[y0 : y0 + h, x0 : x0 + w], oracles[k].burn, rtol=1e-5, atol=1e-5 * scale)
+            assert np.count_nonzero(burn) == np.count_nonzero(oracles[k].burn)
+        assert sum(int((o.status == 2).sum()) for o in oracles) > 50000  # the fires really grew
+
+
 def _checksums(eng):
     """Per-env position-weighted checksum of the fire_map, computed on the device."""
     import torch
@@ -95,8 +153,9 @@ def _checksums(eng):
 
 @pytest.mark.parametrize("shape", [(512, 512, 1024), (2048, 2048, 128)])
 def test_front_ends_agree_at_batch_size(shape):
-    """cfg3 batch (512^2 x 1024 envs) and the target grid (2048^2): TMA ring vs LDG window vs
-    16-bit cells vs the dense fallback -- identical fire maps for every env."""
+    """cfg3 batch (512^2 x 1024 envs) and the target grid (2048^2): the list-driven step vs the TMA ring
+    vs row units vs the LDG window vs 16-bit cells vs the dense form taken on a list overflow --
+    identical fire maps for every env."""
     from simfire_b200 import FireEngine
     from simfire_b200.workloads import synthetic_operational
 
@@ -107,9 +166,12 @@ def test_front_ends_agree_at_batch_size(shape):
     rng = np.random.default_rng(1)
     lines = np.stack([rng.integers(0, E, 4 * E), rng.integers(0, W, 4 * E), rng.integers(0, H, 4 * E),
                       rng.integers(3, 6, 4 * E)], axis=1)  # fmt: skip
-    variants = {"tma": {}, "ldg": dict(sweep_ldg=True), "wide": dict(wide_cells=True)}
+    # row units (the default at this size), the 16-bit layout, the dense TMA / LDG sweeps and the list-driven step
+    variants = {"rows": {}, "wide": dict(wide_cells=True), "tma": dict(unit_skip=False), "lists": dict(front_lists=True),
+                "lists_wide": dict(front_lists=True, wide_cells=True), "ldg": dict(sweep_ldg=True)}
     if H == 512:
         variants["overflow"] = dict(queue_capacity=1000)
+        variants["lists_overflow"] = dict(front_lists=True, queue_capacity=1000)
     results = {}
     for name, extra in variants.items():
         with FireEngine(H, W, E, shared_static=True, **kw, **extra) as eng:
@@ -118,12 +180,12 @@ def test_front_ends_agree_at_batch_size(shape):
             eng.apply_points(lines)
             seq = []
             for _ in range(3):
-                eng.step(20 if name != "overflow" else 6)
+                eng.step(20 if "overflow" not in name else 6)
                 seq.append(_checksums(eng))
             results[name] = (seq, eng.status())
-            if name == "overflow":
-                assert eng.queue_stats()[2]  # the last step really overflowed
-    if "overflow" in results:  # the fallback is slow: compare it over its shorter run
+            if "overflow" in name:
+                assert eng.queue_stats()[2]  # the last step really overflowed / the list handle went dense
+    if "overflow" in results:  # the fallbacks are slow: compare them over their shorter run
         with FireEngine(H, W, E, shared_static=True, **kw) as eng:
             eng.set_static(wl.planes)
             eng.reset(starts)
@@ -132,13 +194,14 @@ def test_front_ends_agree_at_batch_size(shape):
             for _ in range(3):
                 eng.step(6)
                 seq.append(_checksums(eng))
-            for a, b in zip(seq, results.pop("overflow")[0]):
-                assert all(np.array_equal(x, y) for x, y in zip(a, b))
-    base_seq, base_st = results["tma"]
+            for nm in ("overflow", "lists_overflow"):
+                for a, b in zip(seq, results.pop(nm)[0]):
+                    assert all(np.array_equal(x, y) for x, y in zip(a, b)), nm
+    base_seq, base_st = results["rows"]
     assert base_seq[-1][1].sum() > 50 * E  # fires really spread
     for name, (seq, st) in results.items():
         for k, (a, b) in enumerate(zip(seq, base_seq)):
-            assert all(np.array_equal(x, y) for x, y in zip(a, b)), f"{name} differs from tma after block {k}"
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), f"{name} differs from row units after block {k}"
         assert all(np.array_equal(x, y) for x, y in zip(st, base_st)), name
 
 
@@ -242,7 +305,7 @@ def test_fire_duration_limits_of_the_two_cell_layouts(max_dur):
     """max_fire_duration 30 is the last value the 8-bit cell can encode, 31 switches to 16-bit."""
     from simfire_b200.workloads import synthetic_operational
 
-    wl = synthetic_operational(64, 96, seed=11, patch=8)
+    wl = synthetic_operational(64, 96, seed=13, patch=8)  # (seed 13: ignition margin > 3e-4 over all 260 updates)
     wl.max_fire_duration = max_dur
     wl.pixel_scale = 400.0  # slow spread: sprites really live for many steps
     _run_against_oracle(wl, wl.init_pos, 90 if max_dur < 100 else 260, check_every=5)
