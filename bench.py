@@ -705,6 +705,18 @@ def gpu_arm(args):
     e2e_ok = bool(np.array_equal(maps_np[: min(E, 16)], eng.fire_map(0, min(E, 16))))
     e2e_value = cells_per_step * e2e_steps / ctx.max(e2e_s)
 
+    # ---- the same loop for a consumer that keeps the observation on the device (an RL policy on the GPU
+    # reads fire_map_device / the packed state): mitigation points in, per-env GameStatus and elapsed_time out
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pts_np[...] = actions[i]
+        eng.apply_points(pts_np)
+        eng.step(1, sync=False)
+        eng.status()  # device -> host: E x (status, elapsed, update count); synchronises
+    barrier()
+    status_only_value = cells_per_step * e2e_steps / ctx.max(time.perf_counter() - t0)
+
     # ---- sanity: the timed steps really advanced fires
     st, el, nsteps = eng.status()
     burned = int((maps_np[: min(E, 8)] == 2).sum())
@@ -754,6 +766,9 @@ def gpu_arm(args):
                 "steps": e2e_steps, "host_mirror_bytes": int(maps_np.nbytes) * world, "mirror_matches_download": e2e_ok,
                 "host_mirror_memory": "pinned" if args.mirror == "pinned" else "pageable, MADV_HUGEPAGE",
                 "ms_per_call": {"apply_points": e2e_calls[0], "step_enqueue": e2e_calls[1], "sync_fire_maps": e2e_calls[2]},
+                "status_only": {"value": status_only_value, "unit": UNIT, "d2h_bytes_per_step": 16 * E * world,
+                                "note": "the same loop when the observation stays in HBM (fire_map_device): points in, "
+                                        "GameStatus / elapsed_time / update count of every env out"},
                 "api": "FireEngine.apply_points (pinned H2D) + step + sync_fire_maps: every env's int8 fire_map is "
                        "brought up to date in host memory each step" + (" by patching the cells the device logged "
                        "as changed (%d B each)" % log_b if not args.no_track else " by a full download")},

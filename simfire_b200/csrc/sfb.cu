@@ -171,6 +171,7 @@ struct sfb_sim {
     cudaGraphExec_t group_graph;
     unsigned group_graph_epoch;
     int group_graph_on;
+    int group_graph_steps;   // steps per replay (even: the graph starts and ends at parity 0)
     int64_t group_launches_all, group_launches_step;
     int64_t pair_launches_all, pair_launches_step;
     cudaEvent_t fork_ev;
@@ -884,6 +885,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     if (const char* e = getenv("SFB_PATCH_PARALLEL_MIN")) s->patch_parallel_min = std::max(1, atoi(e));  // tests
     s->group_graph_on = (prm->flags & SFB_STEP_GRAPH) ? 1 : 0;
     if (const char* e = getenv("SFB_GROUP_GRAPH")) s->group_graph_on = atoi(e) != 0;
+    s->group_graph_steps = 2;
+    if (const char* e = getenv("SFB_GROUP_GRAPH_STEPS")) s->group_graph_steps = std::max(2, atoi(e) / 2 * 2);
 
     // second set of streams with descending priority: the kernels of earlier groups are scheduled
     // first, so the groups finish one after the other and the host can patch the change log of a
@@ -1489,11 +1492,11 @@ static int run_group_graph(sfb_sim* s) {
         CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         CU(cudaEventRecord(s->fork_ev, s->stream));
         for (auto& gr : s->groups) CU(cudaStreamWaitEvent(gr.stream, s->fork_ev, 0));
-        for (int par = 0; par < 2; ++par)
+        for (int k = 0; k < s->group_graph_steps; ++k)
             for (auto& gr : s->groups) {
-                launch_sweep(s, gr, gr.stream, par);
-                launch_rows(s, gr, gr.stream, par);
-                launch_eval(s, gr, gr.stream, par);
+                launch_sweep(s, gr, gr.stream, k & 1);
+                launch_rows(s, gr, gr.stream, k & 1);
+                launch_eval(s, gr, gr.stream, k & 1);
             }
         for (auto& gr : s->groups) {
             CU(cudaEventRecord(gr.done, gr.stream));
@@ -1609,14 +1612,14 @@ static int enqueue_steps(sfb_sim* s, int n) {
     if ((rc = derive_if_dirty(s))) return rc;
     sync_group_views(s);
     // device-resident stepping (no change log to drain group by group): pairs of steps as one graph
-    if (s->group_graph_on && !s->d.track && n >= 4 && s->stream == s->own_stream) {
+    if (s->group_graph_on && !s->d.track && n >= 2 * s->group_graph_steps && s->stream == s->own_stream) {
         if (s->parity == 1) {  // the graph starts at parity 0
             if ((rc = enqueue_group_steps(s, 1))) return rc;
             --n;
         }
         for (auto& gr : s->groups) gr.last_stream = gr.stream;
-        for (; n >= 2; n -= 2)
-            if ((rc = run_group_graph(s))) return rc;  // parity is 0 again after each pair
+        for (; n >= s->group_graph_steps; n -= s->group_graph_steps)
+            if ((rc = run_group_graph(s))) return rc;  // parity is 0 again after each replay
         s->head_valid = 0;
         if (n == 0) return 0;  // the graph joined every group back into the handle's stream
     }

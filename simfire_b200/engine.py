@@ -267,7 +267,7 @@ class FireEngine:
 
         class _Iface:
             __cuda_array_interface__ = {
-                "shape": (int(sets.value), self.H, self.W, 8), "typestr": "<f4", "data": (p.value, True), "version": 3,
+                "shape": (int(sets.value), self.H, self.W, 8), "typestr": "<f4", "data": (p.value, False), "version": 3,
                 "strides": (int(plane.value) * 32, int(pitch.value) * 32, 32, 4),
             }  # fmt: skip
 

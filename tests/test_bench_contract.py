@@ -42,9 +42,9 @@ def test_gpu_arm_line():
     assert BASE_KEYS | {"roofline", "clocks", "cpu_baseline"} <= set(j)
     assert j["n_gpus"] == 1 and j["steps"] == 20 and j["value"] > 0 and j["scaling"] == "weak"
     r = j["roofline"]
-    assert r["kernel"] == "k_front" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["bound"] in ("hbm", "issue", "latency") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["dense_sweep"]["bound"] == "hbm"
-    assert j["gpu_launches"] == 20  # the list-driven step is one kernel (no attenuation in this workload)
+    assert j["gpu_launches"] > 0 and j["gpu_launches"] % 20 == 0
     e = j["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["mirror_matches_download"]
     cb = j["cpu_baseline"]
