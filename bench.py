@@ -316,10 +316,11 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
-def load_traffic_note(workload: str, kernel: str):
+def load_traffic_note(workload: str, kernel: str, row_tasks=None, work_items=None):
     """Per-launch DRAM bytes of `kernel` from the committed ncu captures, if they match the workload:
-    (bytes, note).  profiles/ncu_sweep_summary.json: the dense sweep; profiles/ncu_kernel_traffic.json:
-    the front-proportional kernels, captured earlier in the run than the bench times them."""
+    (bytes, note).  profiles/ncu_sweep_summary.json: the dense sweep (same launch shape as any dense run);
+    profiles/ncu_kernel_traffic.json: the front-proportional kernels, captured at the task / item counts the
+    file names and scaled linearly to this run's counts.  A label, not a measurement of the timed run."""
     try:
         if kernel.startswith("k_sweep"):
             with open(os.path.join(ROOT, "profiles", "ncu_sweep_summary.json")) as f:
@@ -330,9 +331,15 @@ def load_traffic_note(workload: str, kernel: str):
             with open(os.path.join(ROOT, "profiles", "ncu_kernel_traffic.json")) as f:
                 j = json.load(f)
             if j.get("workload") == workload and kernel in j.get("kernels", {}):
-                return (j["kernels"][kernel]["dram_bytes_per_launch"],
-                        f"ncu --set full at ~{j.get('row_tasks_at_capture')} row tasks / {j.get('work_items_at_capture')} work "
-                        "items per launch (younger fires than in the timed pass: scale by the task counts)")
+                b = j["kernels"][kernel]["dram_bytes_per_launch"]
+                scale = 1.0
+                if kernel == "k_rows" and row_tasks:
+                    scale = row_tasks / max(1, j.get("row_tasks_at_capture", row_tasks))
+                if kernel == "k_eval" and work_items:
+                    scale = work_items / max(1, j.get("work_items_at_capture", work_items))
+                return (b * scale,
+                        f"ncu --set full at {j.get('row_tasks_at_capture')} row tasks / {j.get('work_items_at_capture')} work items "
+                        f"per launch ({b / 1e6:.1f} MB), scaled x{scale:.2f} to this run's counts")
     except Exception:
         pass
     return None, None
@@ -552,7 +559,7 @@ def roofline_sweeps(eng, args, cells_rank, peak_gbs, peak_src, workload):
     dominant = max(kernel_ms, key=kernel_ms.get)
     dom_s = kernel_ms[dominant] * 1e-3
     achieved = kernel_bytes[dominant] / dom_s / 1e9
-    traffic, traffic_note = load_traffic_note(workload, dominant)
+    traffic, traffic_note = load_traffic_note(workload, dominant, row_tasks, q_entries)
     if dominant.startswith("k_sweep") and skipping:
         traffic, traffic_note = None, None  # the committed capture is of the dense sweep
     bound = {"k_rows": "issue", "k_eval": "latency"}.get(dominant, "hbm")
@@ -845,6 +852,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-reference", action="store_true",
                     help="skip the extra pass that times the dense TMA sweep beside the default front end")
+    ap.add_argument("--as-batch", action="store_true",
+                    help="cfg5: step the 8192^2 grid as an ordinary one-env engine on one GPU (row units) instead of slab mode")
     ap.add_argument("--slab-sync", default="p2p", choices=["p2p", "nccl"], help="cfg5: how the slabs agree per step")
     ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
     ap.add_argument("--mirror", default="pinned", choices=["pinned", "thp"],
@@ -858,7 +867,7 @@ def main():
         full_burn_arm(args)
     elif args.impl == "reference":
         reference_arm(args)
-    elif args.workload == "cfg5":
+    elif args.workload == "cfg5" and not args.as_batch:
         gpu_arm_slab(args)
     else:
         gpu_arm(args)

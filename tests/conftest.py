@@ -14,7 +14,10 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """GPU tests are skipped (not failed) when no device is visible and -m gpu was not forced."""
+    """GPU tests are skipped (not failed) when no device is visible and -m gpu was not forced.  The parity
+    tests at the BASELINE sizes (tests/test_gpu_scale.py) run FIRST: the driver uses `-x`, and an unrelated
+    failure in an earlier file must not keep the benchmarked configuration from being checked."""
+    items.sort(key=lambda it: 0 if "test_gpu_scale" in it.nodeid else 1)  # stable: everything else keeps its order
     try:
         import torch
 
