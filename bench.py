@@ -469,7 +469,7 @@ def full_burn_arm(args):
     print(json.dumps(line), flush=True)
 
 
-FRONT_KW = {"auto": {}, "lists": dict(front_lists=True), "rows": dict(unit_skip=True),
+FRONT_KW = {"auto": {}, "lists": dict(front_lists=True), "bits": dict(front_bits=True), "rows": dict(unit_skip=True),
             "chunks": dict(unit_skip=True, unit_chunks=True), "dense": dict(unit_skip=False)}
 
 
@@ -547,6 +547,10 @@ def roofline_sweeps(eng, args, cells_rank, peak_gbs, peak_src, workload):
         sweep_cells = 0.0
         sweep_bytes = units_total * 1.0 + row_tasks * 8.0
         front_kernel = "k_row_list"
+    elif unit_mode == "bits":  # one flag byte per 32 x 32 tile
+        sweep_cells = 0.0
+        sweep_bytes = units_total * 1.0 + row_tasks * 8.0
+        front_kernel = "k_tile_list"
     else:  # 1 B per cell of every listed unit (+ an 8-byte row task per warp-row that needs a look)
         sweep_cells = cells_rank * (units_listed / max(1, units_total))
         sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
@@ -839,7 +843,7 @@ def main():
     ap.add_argument("--rows-per-chunk", type=int, default=0)
     ap.add_argument("--env-groups", type=int, default=0, help="env groups stepped on separate streams (0 = auto)")
     ap.add_argument("--sweep", default="tma", choices=["tma", "ldg"], help="streaming front end of k_sweep")
-    ap.add_argument("--front", default="auto", choices=["auto", "lists", "rows", "chunks", "dense"],
+    ap.add_argument("--front", default="auto", choices=["auto", "lists", "bits", "rows", "chunks", "dense"],
                     help="auto: the library's choice (row units for big batches, the dense sweep for small handles); "
                          "lists: the list-driven step; rows / chunks / dense: force a sweep front end")
     ap.add_argument("--age-curve", type=int, default=2000,

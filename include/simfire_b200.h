@@ -91,6 +91,10 @@ enum sfb_flags {
                                   kernel per step (k_front), no env groups.  Fewer instructions and bytes per
                                   step than the sweep front ends, but all of it scattered 32-byte reads: it pays
                                   where the planes fit L2 (single envs, small batches).  Results are identical  */
+    SFB_FRONT_BITS = 16384,    /* the bitboard front end (sfb_bits.cuh): bit planes next to the state bytes (ignitable,
+                                  control line, one plane per sprite duration), the candidate search as word-wide
+                                  bit operations on 32 x 32 tiles (k_tile_list + k_tiles instead of k_row_list +
+                                  k_rows).  Needs max_fire_duration <= 7; results are identical                  */
     SFB_STEP_GRAPH = 4096      /* multi-group handles: replay pairs of steps of sfb_step(n) as one CUDA
                                   graph forked over the group streams instead of enqueueing every
                                   kernel (single-group handles always replay a graph).  Off by
@@ -315,7 +319,7 @@ int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* e
 int sfb_get_row_tasks(sfb_sim* sim, int64_t* tasks, int64_t* capacity);
 /* Units = (env, chunk of rows or single row, strip of columns) the last completed step listed,
  * and the number of units of the handle; mode: 0 = no unit skipping (every unit is swept, the two
- * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks, 3 = list-driven step
+ * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks, 4 = flagged 32 x 32 tiles (bitboard front end), 3 = list-driven step
  * (listed = entries of the watch list, total = cells of the handle). */
 int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total, int32_t* mode);
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and

@@ -14,6 +14,7 @@ DIAGONAL_SPREAD, ATTENUATE_LINE_ROS, SHARED_STATIC, KEEP_ROS, HAS_MAX_TIME, WIDE
 TRACK_CHANGES = 128
 KEEP_IGNITION = 256
 UNIT_SKIP_OFF, UNIT_SKIP_ON, UNIT_CHUNKS, STEP_GRAPH, FRONT_LISTS = 512, 1024, 2048, 4096, 8192
+FRONT_BITS = 16384
 # sfb_state_plane
 PLANE_BURN, PLANE_ROS, PLANE_AGE, PLANE_STATUS, PLANE_IGNITION = 0, 1, 2, 3, 4
 STATIC_PLANES = ("w_0", "delta", "M_x", "sigma", "U", "U_dir", "slope_mag", "slope_dir")

@@ -8,9 +8,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "sfb.cu")
 DEPS = [
-    SRC,
-    os.path.join(PKG, "csrc", "sfb_kernels.cuh"),
-    os.path.join(PKG, "csrc", "sfb_rothermel.cuh"),
+    *(os.path.join(PKG, "csrc", f) for f in sorted(os.listdir(os.path.join(PKG, "csrc")))),
     os.path.join(os.path.dirname(PKG), "include", "simfire_b200.h"),
 ]
 LIB = os.environ.get("SFB_LIB") or os.path.join(PKG, "libsimfire_b200.so")

@@ -27,6 +27,7 @@
 #include "../../include/simfire_b200.h"
 #include "sfb_kernels.cuh"
 #include "sfb_lists.cuh"
+#include "sfb_bits.cuh"
 #if !defined(SFB_EMU) && defined(SFB_EXPERIMENT_SORT)
 #include <cub/device/device_radix_sort.cuh>
 #endif
@@ -181,6 +182,8 @@ struct sfb_sim {
     int rows_blocks;  // persistent grid of k_rows
     int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
     int unit_rows;    // ... and a unit is a single row of a strip: no sweep at all (k_row_list)
+    int front_bits;   // bitboard front end (sfb_bits.cuh): k_tile_list + k_tiles instead of k_row_list + k_rows
+    int tiles_blocks; // grid of k_tiles
     int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
     int lpar;         // which watch-list buffer the NEXT step reads
     int front_blocks; // persistent grid of k_front
@@ -348,6 +351,7 @@ __global__ void k_apply_points(DevParams p, const int32_t* pts, long long n, int
     if (p.unit_act) mark_units_around<CellT>(p, env, y, x);  // a control line is work under attenuation
     // list handles: a cell that became ignitable next to a sprite, or an attenuated control line, is watched
     if (p.listed && belongs_on_list<CellT>(p, env, y, x, nc) && listed_test_and_set(p, idx)) list_append(p, lpar, env, y, x);
+    if (p.bits) bits_on_status(p, env, y, x, nc & 7);
     if (p.track) {
         const LogRef& L = log_of_env(p, env);
         log_put(L, atomicAdd(L.count, 1ULL), (unsigned long long)idx | ((unsigned long long)k << 48) | LOG_SETUP_BIT);
@@ -632,6 +636,8 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     cudaFree(s->d.rows);
     cudaFree(s->d.unit_act);
     cudaFree(s->d.units);
+    cudaFree(s->d.bits);
+    cudaFree(s->d.tile_act);
     cudaFree(s->d.wl[0]);
     cudaFree(s->d.wl[1]);
     cudaFree(s->d.listed);
@@ -729,6 +735,10 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     // planes fit L2 (single envs, small batches: SFB_FRONT=lists or the flag), not at the 2048^2 x 1024 target.
     s->front_lists = prm->slab_total_H == 0 && (prm->flags & SFB_FRONT_LISTS) != 0;
     if (const char* e = getenv("SFB_FRONT")) s->front_lists = prm->slab_total_H == 0 && strcmp(e, "lists") == 0;
+    // bitboard front end: needs a short sprite life (one plane per duration) and tile indices that fit the task
+    s->front_bits = !s->front_lists && prm->slab_total_H == 0 && (prm->flags & SFB_FRONT_BITS) != 0;
+    if (const char* e = getenv("SFB_FRONT")) s->front_bits = !s->front_lists && prm->slab_total_H == 0 && strcmp(e, "bits") == 0;
+    if (prm->max_fire_duration > BITS_MAX_DUR || d.H > 32 * 65535 || d.W > 32 * 65535) s->front_bits = 0;
     if (d.H >= (1 << LE_BITS) || d.W >= (1 << LE_BITS) || d.E >= (1 << 22)) s->front_lists = 0;  // entry fields
     // row tasks of the sweep front ends pack y into 20 bits and the strip into 8 (make_row_task)
     if (!s->front_lists && (d.H >= (1 << 20) || d.strips > 256))
@@ -857,10 +867,10 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     }
     // unit skipping: on for handles with enough units to make a list worth its launch, never in slab
     // mode (a neighbour slab's fire enters through the halo rows, which nobody here would flag)
-    s->unit_skip = !s->front_lists && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31) &&
+    s->unit_skip = !s->front_lists && !s->front_bits && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31) &&
                    ((prm->flags & SFB_UNIT_SKIP_ON) || (!(prm->flags & SFB_UNIT_SKIP_OFF) && d.n_units >= 1024));
     if (const char* e = getenv("SFB_UNIT_SKIP"))
-        if (!s->front_lists && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
+        if (!s->front_lists && !s->front_bits && prm->slab_total_H == 0 && d.n_units < ((int64_t)1 << 31)) s->unit_skip = atoi(e) != 0;
     s->unit_rows = s->unit_skip && !(prm->flags & SFB_UNIT_CHUNKS);
     if (const char* e = getenv("SFB_UNIT_ROWS")) s->unit_rows = s->unit_skip && atoi(e) != 0;
     d.unit_stride = (int64_t)d.chunks * d.strips;
@@ -877,6 +887,24 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         if ((rc = dmalloc(s, &d.unit_act, flag_bytes))) return rc;
         if (!s->unit_rows && (rc = dmalloc(s, &d.units, (size_t)d.n_units * sizeof(uint32_t)))) return rc;
         CU(cudaMemsetAsync(d.unit_act, 0, flag_bytes, s->stream));
+    }
+    if (s->front_bits) {
+        d.ring = prm->max_fire_duration + 1;
+        d.tiles_x = (d.W + 31) / 32;
+        d.tiles_y = (d.H + 31) / 32;
+        d.bits_plane = (int64_t)d.tiles_x * d.H;
+        d.bits_env = (int64_t)(2 + d.ring) * d.bits_plane;
+        d.tile_stride = ((int64_t)d.tiles_y * d.tiles_x + 3) / 4 * 4;
+        if ((rc = dmalloc(s, &d.bits, (size_t)d.E * d.bits_env * 4))) return rc;
+        if ((rc = dmalloc(s, &d.tile_act, (size_t)d.E * d.tile_stride))) return rc;
+        CU(cudaMemsetAsync(d.bits, 0, (size_t)d.E * d.bits_env * 4, s->stream));
+        CU(cudaMemsetAsync(d.tile_act, 0, (size_t)d.E * d.tile_stride, s->stream));
+        // (the row-task list allocated above also holds the tile tasks: E * H * strips >= E * tiles)
+        int per_sm = 0;
+        if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint8_t>, TILES_WARPS * 32, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint16_t>, TILES_WARPS * 32, 0));
+        if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_tiles does not fit on an SM");
+        s->tiles_blocks = per_sm * s->n_sm;
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
     // measured (profiles/r01b_bench_target_groupgraph.json): the graph joins the groups after every pair of
@@ -916,6 +944,10 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.qcap = q_cap;
         v.rows = d.rows + (int64_t)e0 * d.H * d.strips;
         v.rows_cap = (int64_t)cnt * d.H * d.strips;
+        if (d.bits) {
+            v.bits = d.bits + (int64_t)e0 * d.bits_env;
+            v.tile_act = d.tile_act + (int64_t)e0 * d.tile_stride;
+        }
         if (d.unit_act) {
             v.unit_act = d.unit_act + (int64_t)e0 * d.unit_stride;
             if (d.units) v.units = d.units + (int64_t)e0 * d.chunks * d.strips;
@@ -959,8 +991,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
-        const long long unit_items = d.unit_rows ? (long long)cnt * d.unit_stride / 4 : v.n_units;  // words / flags
-        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((unit_items + 255) / 256, (long long)(d.unit_rows ? 8 : 4) * s->n_sm));
+        const long long unit_items = d.bits ? (long long)cnt * d.tile_stride / 4 : (d.unit_rows ? (long long)cnt * d.unit_stride / 4 : v.n_units);  // words / flags
+        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((unit_items + 255) / 256, (long long)((d.unit_rows || d.bits) ? 8 : 4) * s->n_sm));
         return 0;
     };
     if ((rc = make_view(s->all, 0, d.E, 0, d.qcap, false))) return rc;
@@ -1187,6 +1219,9 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     DISPATCH(s, k_reset_meta, nblocks(n, 128), 128, d, s->parity, (const int32_t*)d_envs, (const int32_t*)d_xy, n,
              s->prm.slab_y0, s->lpar);
     if (s->front_lists) CU(cudaMemsetAsync(s->env_mark, 0, (size_t)d.E, s->stream));
+    if (s->front_bits) {  // planes of the fresh maps (one ignitable plane, one sprite of duration 0)
+        DISPATCH(s, k_bits_rebuild, cap_grid(s, (long long)n * d.bits_plane, 256), 256, d, s->parity, (const int32_t*)d_envs, 0, n);
+    }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));  // host buffers are borrowed for the call only
     return 0;
@@ -1258,6 +1293,7 @@ static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     // wholesale replacement: any cell may have become a control line or ignitable next to a sprite
     if (d.unit_act)
         CU(cudaMemsetAsync(d.unit_act + (size_t)env0 * d.unit_stride, 1, (size_t)n * d.unit_stride, s->stream));
+    if (s->front_bits) DISPATCH(s, k_bits_rebuild, cap_grid(s, (long long)n * d.bits_plane, 256), 256, d, s->parity, (const int32_t*)nullptr, env0, n);
     if (s->front_lists) {  // the same for the watch list: drop the envs' entries, re-list from the new state
         if ((rc = list_drop_envs(s, nullptr, env0, n))) return rc;
         if (s->cell_bytes == 1) SFB_LAUNCH(k_list_rebuild<uint8_t>, cap_grid(s, (long long)n * d.plane, 256), 256, 0, s->stream, d, s->lpar, env0, n);
@@ -1310,6 +1346,12 @@ static int derive_if_dirty(sfb_sim* s) {
 }
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (gr.d.bits) {  // the flagged tiles are this step's tasks
+        SFB_LAUNCH(k_tile_list, gr.units_blocks, 256, 0, st, gr.d, par);
+        s->launches_all++;
+        s->launches_step++;
+        return;
+    }
     if (gr.d.unit_rows) {  // the flagged rows are this step's row tasks: nothing is swept
         SFB_LAUNCH(k_row_list, gr.units_blocks, 256, 0, st, gr.d, par);
         s->launches_all++;
@@ -1332,6 +1374,14 @@ static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     s->launches_step++;
 }
 static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (gr.d.bits) {
+        const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)gr.d.E * gr.d.tiles_y * gr.d.tiles_x + TILES_WARPS - 1) / TILES_WARPS, s->tiles_blocks));
+        if (s->cell_bytes == 1) SFB_LAUNCH(k_tiles<uint8_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        else SFB_LAUNCH(k_tiles<uint16_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        s->launches_all++;
+        s->launches_step++;
+        return;
+    }
     if (s->cell_bytes == 1) SFB_LAUNCH(k_rows<uint8_t>, gr.rows_blocks, ROWS_WARPS * 32, 0, st, gr.d, par);
     else SFB_LAUNCH(k_rows<uint16_t>, gr.rows_blocks, ROWS_WARPS * 32, 0, st, gr.d, par);
     s->launches_all++;
@@ -1845,7 +1895,7 @@ extern "C" int sfb_constant_spread_update(sfb_sim* s, int32_t env0, int32_t n, i
     if (!s || !maps) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: null argument");
     if (rate_of_spread < 0) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: rate_of_spread %d", rate_of_spread);
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: a step is half done");
-    if (s->front_lists || s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: not for list or slab handles");
+    if (s->front_lists || s->front_bits || s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: not for list, bitboard or slab handles");
     int rc;
     if ((rc = check_env_range(s, "sfb_constant_spread_update", env0, n))) return rc;
     if ((rc = use(s))) return rc;
@@ -2250,6 +2300,22 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
         if (listed) *listed = (int64_t)c[s->lpar];
         if (total) *total = (int64_t)s->d.E * s->d.H * s->d.W;
         if (mode) *mode = 3;
+        return 0;
+    }
+    if (s->front_bits) {  // the listed units are the tile tasks
+        act = 0;
+        tot = (int64_t)s->d.E * s->d.tiles_y * s->d.tiles_x;
+        std::vector<EnvGroup*> views;
+        if (s->last_mode == 2) for (auto& gr : s->groups) views.push_back(&gr);
+        else views.push_back(&s->all);
+        for (EnvGroup* grp : views) {
+            unsigned long long c[N_COUNTERS];
+            CU(cudaMemcpy(c, grp->counters, sizeof(c), cudaMemcpyDeviceToHost));
+            act += (int64_t)c[4 + par];
+        }
+        if (listed) *listed = act;
+        if (total) *total = tot;
+        if (mode) *mode = 4;
         return 0;
     }
     if (s->unit_skip) {

@@ -169,6 +169,12 @@ struct DevParams {
     unsigned long long* ros_items;   // SFB_KEEP_ROS: (cell index, float64 bits) of this step's candidates
     unsigned long long* ros_count;
     int64_t ros_cap;
+    // bitboard front end (sfb_bits.cuh): bit planes next to the state bytes, one word per (env, tile column, row)
+    uint32_t* bits;                  // [E][2 + ring][tiles_x][H] (nullptr: not a bitboard handle)
+    int32_t ring, tiles_x, tiles_y, bits_pad_;
+    int64_t bits_plane, bits_env;    // words per plane (tiles_x * H) and per env
+    uint8_t* tile_act;               // [E][tile_stride] activity flag per 32 x 32 tile
+    int64_t tile_stride;
     unsigned long long* late;        // cells that re-ignite while still a source for this step (rewritten by the last block)
     unsigned int* late_count;
     int64_t late_cap;
@@ -250,6 +256,30 @@ __device__ __forceinline__ void mark_units_of_cell(const DevParams& p, int env, 
     mark_units_around<CellT>(p, env, y, x);
 }
 
+// bitboard handles (sfb_bits.cuh): a cell ignited in update() call t joins ring plane t mod R (its sprite has
+// duration 0 in call t + 1), leaves the IGN / LINE planes, and the tiles within one cell of it are flagged
+__device__ __forceinline__ void bits_ignite_cell(const DevParams& p, int env, long long cell, int t) {
+    int y, x;
+    if (p.plane <= 0x7fffffffll) {
+        const uint32_t c = (uint32_t)cell;
+        y = (int)(c / (uint32_t)p.pitch);
+        x = (int)(c - (uint32_t)y * (uint32_t)p.pitch);
+    } else {
+        y = (int)(cell / p.pitch);
+        x = (int)(cell - (long long)y * p.pitch);
+    }
+    const uint32_t bit = 1u << (x & 31);
+    uint32_t* const w = p.bits + (long long)env * p.bits_env + (long long)(x >> 5) * p.H + y;  // word of plane 0 (IGN)
+    atomicAnd(w, ~bit);
+    atomicAnd(w + p.bits_plane, ~bit);                                  // LINE
+    atomicOr(w + (long long)(2 + t % p.ring) * p.bits_plane, bit);      // RING slot t mod R
+    const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
+    const int tx0 = (x > 0 ? x - 1 : 0) >> 5, tx1 = (x + 1 < p.W ? x + 1 : p.W - 1) >> 5;
+    uint8_t* f = p.tile_act + (long long)env * p.tile_stride;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) f[ty * p.tiles_x + tx] = 1;
+}
+
 __device__ __forceinline__ unsigned long long make_item(long long idx, int dir, int s) {
     return (unsigned long long)idx | ((unsigned long long)dir << 48) | ((unsigned long long)s << 52);
 }
@@ -316,6 +346,7 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
         reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(ST_BURNING | (code << 3));  // fire.py:571-587
         if (p.ign) p.ign[idx] = m.t;
         if (p.unit_act) mark_units_of_cell<CellT>(p, env, idx);
+        if (p.bits) bits_ignite_cell(p, env, idx - (long long)env * p.plane, m.t);
         return true;
     }
     return false;

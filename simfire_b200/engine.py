@@ -61,6 +61,7 @@ class FireEngine:
         unit_chunks: bool = False,
         step_graph: bool = False,
         front_lists: bool = False,
+        front_bits: bool = False,
         slab_y0: int = 0,
         slab_total_H: int = 0,
     ) -> None:
@@ -85,7 +86,8 @@ class FireEngine:
             flags |= _lib.UNIT_SKIP_ON if unit_skip else _lib.UNIT_SKIP_OFF
         flags |= _lib.UNIT_CHUNKS if unit_chunks else 0  # chunk-of-rows units + sweep instead of row units
         flags |= _lib.STEP_GRAPH if step_graph else 0    # multi-group handles: pairs of steps as one CUDA graph
-        flags |= _lib.FRONT_LISTS if front_lists else 0  # force the list-driven step (the default without sweep knobs)
+        flags |= _lib.FRONT_LISTS if front_lists else 0  # the list-driven step (k_front)
+        flags |= _lib.FRONT_BITS if front_bits else 0    # the bitboard front end (k_tiles); needs max_fire_duration <= 7
         h, S_T, S_e, p_p = (float(v) for v in fuel_particle)
         prm = _lib.SfbParams(
             abi_version=_lib.ABI_VERSION, device=self.device, H=self.H, W=self.W, E=self.E,
@@ -384,7 +386,7 @@ class FireEngine:
         or 'lists' (the list-driven step: no units, one watch list)."""
         a, b, m = C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
-        return ("dense", "chunks", "rows", "lists")[int(m.value)]
+        return ("dense", "chunks", "rows", "lists", "bits")[int(m.value)]
 
     def queue_stats(self):
         a, b, o = C.c_int64(), C.c_int64(), C.c_int32()

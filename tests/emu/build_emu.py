@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libsfb_emu.so")
 DEPS = [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "emu_lib.cpp")] + [
-    os.path.join(ROOT, "simfire_b200", "csrc", f) for f in ("sfb.cu", "sfb_kernels.cuh", "sfb_rothermel.cuh")
+    os.path.join(ROOT, "simfire_b200", "csrc", f) for f in sorted(os.listdir(os.path.join(ROOT, "simfire_b200", "csrc")))
 ] + [os.path.join(ROOT, "include", "simfire_b200.h")]
 
 

@@ -108,7 +108,8 @@ def test_golden_trajectory(name):
 @pytest.mark.parametrize("variant", ["wide_cells", "queue_overflow", "rows4", "rows64", "ldg", "ldg_wide", "ldg_rows8",
                                      "skip", "skip_wide", "skip_ldg_rows8", "skip_overflow", "noskip",
                                      "rowunits", "rowunits_wide", "rowunits_overflow",
-                                     "lists", "lists_wide", "lists_overflow", "lists_no_rate_table"])
+                                     "lists", "lists_wide", "lists_overflow", "lists_no_rate_table",
+                                     "bits", "bits_wide", "bits_overflow", "bits_groups3"])
 def test_golden_trajectory_variants(name, variant, monkeypatch):
     """The 16-bit cell layout, the dense fallback taken on queue overflow, other chunk
     heights and the non-TMA streaming front end must give the same trajectories."""
@@ -128,15 +129,21 @@ def test_golden_trajectory_variants(name, variant, monkeypatch):
           # turns the handle to the dense form of the same per-cell routine
           "lists": dict(front_lists=True), "lists_wide": dict(front_lists=True, wide_cells=True),
           "lists_overflow": dict(front_lists=True, queue_capacity=3),
-          "lists_no_rate_table": dict(front_lists=True)}[variant]  # fmt: skip
+          "lists_no_rate_table": dict(front_lists=True),
+          # the bitboard front end (k_tile_list + k_tiles): bit planes per sprite duration, 32 x 32 tiles
+          "bits": dict(front_bits=True), "bits_wide": dict(front_bits=True, wide_cells=True),
+          "bits_overflow": dict(front_bits=True, queue_capacity=3),
+          "bits_groups3": dict(front_bits=True, env_groups=3)}[variant]  # fmt: skip
     if variant == "lists_no_rate_table":
         monkeypatch.setenv("SFB_NO_RTAB", "1")  # rates evaluated in the step instead of looked up
     with engine_for(sc, **kw) as eng:
         if variant.startswith("lists"):
             assert eng.unit_mode() == "lists"
+        if variant.startswith("bits"):
+            assert eng.unit_mode() == "bits"
         eng.reset([sc["init"]])
         check_trajectory(sc, EngineAdapter(eng), **_burn_tol(sc))
-        if variant in ("queue_overflow", "lists_overflow"):
+        if variant in ("queue_overflow", "lists_overflow", "bits_overflow"):
             assert eng.queue_stats()[1] == 3
         if variant == "lists_overflow":
             assert eng.queue_stats()[2]  # the handle went dense
@@ -210,7 +217,7 @@ def test_env_groups_on_streams_equal_one_group(groups):
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
 
 
-@pytest.mark.parametrize("front_end", ["tma", "ldg", "rows", "lists"])
+@pytest.mark.parametrize("front_end", ["tma", "ldg", "rows", "lists", "bits"])
 @pytest.mark.parametrize("attenuate", [True, False])
 def test_unit_skipping_changes_nothing(front_end, attenuate):
     """Looking only at the flagged units (chunks of rows that are then swept with either front end,
@@ -235,8 +242,11 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
         if front_end == "lists" and skip:  # the list-driven step against the dense sweep
             eng = FireEngine(H, W, E, shared_static=True, front_lists=True, track_changes=True, **kw)
             assert eng.unit_mode() == "lists"
+        elif front_end == "bits" and skip:  # the bitboard front end against the dense sweep
+            eng = FireEngine(H, W, E, shared_static=True, front_bits=True, track_changes=True, env_groups=2, **kw)
+            assert eng.unit_mode() == "bits"
         else:
-            eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, unit_chunks=(front_end not in ("rows", "lists")),
+            eng = FireEngine(H, W, E, shared_static=True, unit_skip=skip, unit_chunks=(front_end not in ("rows", "lists", "bits")),
                              sweep_ldg=(front_end == "ldg"), rows_per_chunk=8, track_changes=True, env_groups=2, **kw)  # fmt: skip
         eng.set_static(wl.planes)
         eng.reset(starts)
