@@ -531,6 +531,55 @@ def roofline_lists(eng, args, cells_rank, peak_gbs, peak_src, workload):
     }
 
 
+def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
+    """The bitboard front end: k_tile_list + k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
+    per launch of k_tiles, from the kernel's own counters over the per-launch-timed
+    pass: per tile its 8-byte task, the 32 words of the ignitable and control-line planes and of the
+    expiring sprite plane, 34 words of each of the ring - 1 source planes (32 rows + the row above and
+    below); per candidate the 8-byte rate of its (cell, direction) pair and the float64 burn value read
+    and written; one state byte per ignition / burn-out; per tile up to three 128-byte plane rows written
+    back and one flag byte."""
+    eng.front_stats()  # reset the counters
+    eng.set_kernel_timing(True)
+    eng.step(args.roofline_steps)
+    list_ms, tiles_ms, eval_ms, n_t = eng.kernel_ms()
+    eng.set_kernel_timing(False)
+    fs = {k: v / n_t for k, v in eng.front_stats().items()}
+    tiles, cand = fs["entries_read"], fs["candidates"]
+    units_listed, units_total = eng.unit_stats()
+    q_entries, q_cap, q_ovf = eng.queue_stats()
+    list_s, tiles_s, eval_s = list_ms / n_t * 1e-3, tiles_ms / n_t * 1e-3, eval_ms / n_t * 1e-3
+    tiles_bytes = (tiles * (8.0 + 3 * 128.0 + (ring - 1) * 34 * 4.0 + 1.0) + cand * 24.0 + fs["ignited"] * (1.0 + 12.0) +
+                   fs["pruned"] * (1.0 + 4.0))
+    list_bytes = units_total * 1.0 + tiles * 8.0
+    eval_bytes = q_entries * (8.0 + 16.0) + 64.0 * eng.E
+    kernel_ms = {"k_tile_list": list_s * 1e3, "k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
+    kernel_bytes = {"k_tile_list": list_bytes, "k_tiles": tiles_bytes, "k_eval": eval_bytes}
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    dom_s = kernel_ms[dominant] * 1e-3
+    achieved = kernel_bytes[dominant] / dom_s / 1e9
+    return {
+        "bound": "latency", "kernel": dominant, "env_groups_timed_one_after_the_other": True, "achieved": achieved,
+        "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+        "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+        "traffic": None, "traffic_source": None,
+        "note": "front-proportional kernels: a step touches a few tens of MB (bit planes of the listed tiles, rate / burn "
+                "of the candidates), so HBM bandwidth is not what bounds it -- dependent-load latency and the launches "
+                "are; the HBM-bound kernel of this design is the dense TMA sweep (`dense_sweep`).",
+        "kernels": {k: {"ms_per_launch": kernel_ms[k], "bytes_per_launch": kernel_bytes[k],
+                        "achieved": kernel_bytes[k] / (kernel_ms[k] * 1e-3) / 1e9 if kernel_ms[k] > 0 else None}
+                    for k in kernel_ms},
+        "unit_skipping": {"on": True, "mode": "bits", "units_listed": units_listed, "units_total": units_total,
+                          "cells_swept_per_step": 0.0, "cells_per_step": cells_rank},
+        "kernel_ms_per_launch": kernel_ms, "bytes_per_launch": kernel_bytes[dominant],
+        "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank, "ms_per_launch": dom_s * 1e3,
+        "share_of_step": dom_s / (list_s + tiles_s + eval_s),
+        "per_launch": {k: round(v, 1) for k, v in fs.items()},
+        "row_tasks_per_step": tiles, "work_items_per_step": cand, "items_left_to_k_eval": q_entries,
+        "queue_overflowed": q_ovf, "front": "bits",
+    }  # fmt: skip
+
+
 def roofline_sweeps(eng, args, cells_rank, peak_gbs, peak_src, workload):
     """The sweep front ends (--front rows | chunks | dense): front end + k_rows + k_eval."""
     eng.set_kernel_timing(True)
@@ -547,10 +596,6 @@ def roofline_sweeps(eng, args, cells_rank, peak_gbs, peak_src, workload):
         sweep_cells = 0.0
         sweep_bytes = units_total * 1.0 + row_tasks * 8.0
         front_kernel = "k_row_list"
-    elif unit_mode == "bits":  # one flag byte per 32 x 32 tile
-        sweep_cells = 0.0
-        sweep_bytes = units_total * 1.0 + row_tasks * 8.0
-        front_kernel = "k_tile_list"
     else:  # 1 B per cell of every listed unit (+ an 8-byte row task per warp-row that needs a look)
         sweep_cells = cells_rank * (units_listed / max(1, units_total))
         sweep_bytes = sweep_cells * 1.0 + row_tasks * 8.0 + (units_total + 8.0 * units_listed if skipping else 0.0)
@@ -652,7 +697,10 @@ def gpu_arm(args):
     # ---- dominant-kernel timing for the roofline (separate pass, every launch bracketed by events)
     peak_gbs, peak_src = load_peak()
     unit_mode = eng.unit_mode()
-    roof = (roofline_lists if unit_mode == "lists" else roofline_sweeps)(eng, args, cells_rank, peak_gbs, peak_src, args.workload)
+    if unit_mode == "bits":
+        roof = roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, args.workload, wl.max_fire_duration + 1)
+    else:
+        roof = (roofline_lists if unit_mode == "lists" else roofline_sweeps)(eng, args, cells_rank, peak_gbs, peak_src, args.workload)
 
     if not args.no_track:
         eng.set_tracking(True)
@@ -718,6 +766,8 @@ def gpu_arm(args):
 
     # ---- the same loop for a consumer that keeps the observation on the device (an RL policy on the GPU
     # reads fire_map_device / the packed state): mitigation points in, per-env GameStatus and elapsed_time out
+    if not args.no_track:
+        eng.set_tracking(False)  # nobody drains the change log in this loop: such a consumer does not ask for it
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
@@ -727,6 +777,8 @@ def gpu_arm(args):
         eng.status()  # device -> host: E x (status, elapsed, update count); synchronises
     barrier()
     status_only_value = cells_per_step * e2e_steps / ctx.max(time.perf_counter() - t0)
+    if not args.no_track:
+        eng.set_tracking(True)
 
     # ---- sanity: the timed steps really advanced fires
     st, el, nsteps = eng.status()

@@ -328,7 +328,9 @@ int sfb_get_queue_stats(sfb_sim* sim, int64_t* entries, int64_t* capacity, int32
 /* List handles (sfb_get_unit_stats mode 3): counters accumulated by k_front since the previous call, then
  * reset: stats[0] cells examined, [1] candidates evaluated (fire.py:163-234), [2] cells ignited, [3] sprites
  * pruned (fire.py:116-161), [4] cells that joined the watch list, [5] list entries read, [6] cells whose eight neighbours were read;
- * n <= 7 values. */
+ * n <= 7 values.  Bitboard handles (mode 4) accumulate while kernel timing is on: [0] cells of the tiles
+ * looked at, [1] candidates evaluated, [2] cells ignited, [3] sprites pruned, [5] tiles, [6] control-line cells
+ * left to k_eval. */
 int sfb_get_front_stats(sfb_sim* sim, int64_t* stats, int32_t n);
 /* Test knob: enqueue a kernel that keeps the handle's stream busy for `microseconds` (at most 1 s)
  * before whatever is called next on it.  The GPU tests use it to widen the window of stream-ordering

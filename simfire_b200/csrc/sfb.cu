@@ -5,9 +5,27 @@
 // test-only build with g++ (tests/emu): the fiber emulator stands in for the CUDA runtime
 #include "cuda_emu.h"
 #define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(#kernel, (grid), (block), (smem), kernel, __VA_ARGS__)
+#define SFB_LAUNCH_DEP(dep, kernel, grid, block, smem, stream, ...) emu::launch(#kernel, (grid), (block), (smem), kernel, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>
 #define SFB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains; it
+// executes griddepcontrol.wait (grid_dep_wait) before it touches anything the predecessor wrote
+template <typename... KArgs, typename... Args>
+static inline void sfb_launch_dep(bool dep, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = dep ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#define SFB_LAUNCH_DEP(dep, kernel, grid, block, smem, stream, ...) sfb_launch_dep((dep), kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 #include <stdarg.h>
 #include <stdio.h>
@@ -182,6 +200,7 @@ struct sfb_sim {
     int rows_blocks;  // persistent grid of k_rows
     int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
     int unit_rows;    // ... and a unit is a single row of a strip: no sweep at all (k_row_list)
+    int pdl;          // bitboard handles: programmatic dependent launch of the step kernels (SFB_PDL=0 turns it off)
     int front_bits;   // bitboard front end (sfb_bits.cuh): k_tile_list + k_tiles instead of k_row_list + k_rows
     int tiles_blocks; // grid of k_tiles
     int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
@@ -235,6 +254,7 @@ struct sfb_sim {
 static int use(sfb_sim* s) {
     CU(cudaSetDevice(s->prm.device));
     s->head_valid = 0;  // any call may append to the change logs; only a grouped step re-validates
+    s->d.bits_par = s->parity;  // bitboard handles: setup kernels raise the tile flags the next step reads
     return 0;
 }
 
@@ -506,6 +526,22 @@ __global__ void k_clear_ros(DevParams p, int par) {
     }
 }
 
+// bitboard handles evaluate their candidates before the env-wide "any candidate" is known (k_tiles): the
+// step's rates are written to a second plane, zeroed before k_tiles and committed after k_eval
+__global__ void k_ros_zero(DevParams p) {
+    const long long total = (long long)p.E * p.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        p.ros_w[i] = 0.0;
+}
+__global__ void k_ros_commit(DevParams p, int par) {
+    const long long total = (long long)p.E * p.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const EnvMeta& m = p.meta[(long long)par * p.meta_stride + (int)(i / p.plane)];
+        if (m.running && !m.time_quit && m.any_cand) p.ros[i] = p.ros_w[i];
+    }
+}
+
 // fuel-only Rothermel terms of every static cell, through the same code as the one-shot path
 __global__ void k_derive_static(DevParams p, long long n_cells) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
@@ -627,6 +663,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     s->stream = s->own_stream;
     cudaFree(s->d.state);
     cudaFree(s->d.burn);
+    if (s->d.ros_w != s->d.ros) cudaFree(s->d.ros_w);
     cudaFree(s->d.ros);
     cudaFree(s->d.ign);
     cudaFree((void*)s->d.stat);
@@ -736,9 +773,19 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     s->front_lists = prm->slab_total_H == 0 && (prm->flags & SFB_FRONT_LISTS) != 0;
     if (const char* e = getenv("SFB_FRONT")) s->front_lists = prm->slab_total_H == 0 && strcmp(e, "lists") == 0;
     // bitboard front end: needs a short sprite life (one plane per duration) and tile indices that fit the task
-    s->front_bits = !s->front_lists && prm->slab_total_H == 0 && (prm->flags & SFB_FRONT_BITS) != 0;
-    if (const char* e = getenv("SFB_FRONT")) s->front_bits = !s->front_lists && prm->slab_total_H == 0 && strcmp(e, "bits") == 0;
-    if (prm->max_fire_duration > BITS_MAX_DUR || d.H > 32 * 65535 || d.W > 32 * 65535) s->front_bits = 0;
+    // It is the default for handles big enough to skip units at all (the same threshold as row units) when
+    // the caller asked for no particular front end; SFB_FRONT=rows|dense|... or any of the sweep flags keep the others.
+    {
+        const bool eligible = !s->front_lists && prm->slab_total_H == 0 && prm->max_fire_duration <= BITS_MAX_DUR &&
+                              d.H <= 32 * 65535 && d.W <= TW * 65535;
+        const bool asked_other = (prm->flags & (SFB_UNIT_SKIP_OFF | SFB_UNIT_SKIP_ON | SFB_UNIT_CHUNKS | SFB_SWEEP_LDG | SFB_STEP_GRAPH)) != 0 ||
+                                 prm->rows_per_chunk > 0 || getenv("SFB_UNIT_SKIP") || getenv("SFB_UNIT_ROWS");
+        const int64_t row_units = (int64_t)d.E * d.H * ((d.W + wr - 1) / wr);
+        s->front_bits = eligible && ((prm->flags & SFB_FRONT_BITS) != 0 || (!asked_other && row_units >= 1024));
+        if (const char* e = getenv("SFB_FRONT")) s->front_bits = eligible && strcmp(e, "bits") == 0;
+    }
+    s->pdl = 1;
+    if (const char* e = getenv("SFB_PDL")) s->pdl = atoi(e) != 0;
     if (d.H >= (1 << LE_BITS) || d.W >= (1 << LE_BITS) || d.E >= (1 << 22)) s->front_lists = 0;  // entry fields
     // row tasks of the sweep front ends pack y into 20 bits and the strip into 8 (make_row_task)
     if (!s->front_lists && (d.H >= (1 << 20) || d.strips > 256))
@@ -757,6 +804,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     CU(cudaMemsetAsync(d.mailbox, 0, sizeof(SlabMailbox), s->stream));
     if ((rc = dmalloc(s, &d.burn, (size_t)total * 8))) return rc;
     if (d.keep_ros && (rc = dmalloc(s, &d.ros, (size_t)total * 8))) return rc;
+    d.ros_w = d.ros;
     if ((prm->flags & SFB_KEEP_IGNITION) && (rc = dmalloc(s, &d.ign, (size_t)total * 4))) return rc;
     const int64_t stat_cells = d.shared_static ? d.plane : total;
     if ((rc = dmalloc(s, (StaticRec**)&d.stat, (size_t)stat_cells * sizeof(StaticRec)))) return rc;
@@ -816,10 +864,16 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     int G = prm->env_groups;
     if (G <= 0) G = prm->slab_total_H != 0 ? 1 : (d.E >= 512 ? 4 : (d.E >= 64 ? 2 : 1));
     if (prm->slab_total_H != 0) G = 1;
+    // bitboard handles: a step is three short kernels whose tails are not worth hiding behind another group's
+    // launches (measured on the target batch: 1 group 128 T, 2 groups 117 T, 4 groups 67 T cell-updates/s)
+    if (prm->env_groups <= 0 && s->front_bits) G = 1;
     G = std::min(G, std::min(d.E, 16));
     d.meta_stride = d.E;
     d.idx_base = 0;
-    d.rows_cap = (int64_t)d.E * d.H * d.strips;  // every warp-row of the grid: the list cannot overflow
+    // every warp-row of the grid (every tile of a bitboard handle): the list cannot overflow
+    const int64_t tasks_per_env = s->front_bits ? std::max<int64_t>((int64_t)d.H * d.strips, (int64_t)((d.H + 31) / 32) * ((d.W + TW - 1) / TW))
+                                                : (int64_t)d.H * d.strips;
+    d.rows_cap = (int64_t)d.E * tasks_per_env;
     if (s->front_lists) {
         G = 1;
         d.rows_cap = 1;
@@ -890,16 +944,21 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     }
     if (s->front_bits) {
         d.ring = prm->max_fire_duration + 1;
-        d.tiles_x = (d.W + 31) / 32;
+        d.tiles_x = (d.W + TW - 1) / TW;
         d.tiles_y = (d.H + 31) / 32;
         d.bits_plane = (int64_t)d.tiles_x * d.H;
         d.bits_env = (int64_t)(2 + d.ring) * d.bits_plane;
-        d.tile_stride = ((int64_t)d.tiles_y * d.tiles_x + 3) / 4 * 4;
+        if (d.bits_env >= ((int64_t)1 << 31)) return fail(SFB_ERR_INVALID, "sfb_create: bitboard planes of %lld words per env exceed 32-bit offsets", (long long)d.bits_env);
+        d.tile_stride = ((int64_t)d.tiles_y * d.tiles_x + 15) / 16 * 16;
+        d.tile_buf = (int64_t)d.E * d.tile_stride;
         if ((rc = dmalloc(s, &d.bits, (size_t)d.E * d.bits_env * 4))) return rc;
-        if ((rc = dmalloc(s, &d.tile_act, (size_t)d.E * d.tile_stride))) return rc;
+        if ((rc = dmalloc(s, &d.tile_act, (size_t)2 * d.tile_buf))) return rc;
         CU(cudaMemsetAsync(d.bits, 0, (size_t)d.E * d.bits_env * 4, s->stream));
-        CU(cudaMemsetAsync(d.tile_act, 0, (size_t)d.E * d.tile_stride, s->stream));
-        // (the row-task list allocated above also holds the tile tasks: E * H * strips >= E * tiles)
+        CU(cudaMemsetAsync(d.tile_act, 0, (size_t)2 * d.tile_buf, s->stream));
+        if (d.keep_ros && (rc = dmalloc(s, &d.ros_w, (size_t)total * 8))) return rc;
+        if ((rc = dmalloc(s, &s->list_ctr, 16 * sizeof(unsigned long long)))) return rc;  // statistics of timed passes
+        CU(cudaMemsetAsync(s->list_ctr, 0, 16 * sizeof(unsigned long long), s->stream));
+        // (the row-task list allocated above is sized for the tile tasks)
         int per_sm = 0;
         if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint8_t>, TILES_WARPS * 32, 0));
         else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint16_t>, TILES_WARPS * 32, 0));
@@ -931,6 +990,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.state = (char*)d.state + off * s->cell_bytes;
         v.burn = d.burn + off;
         if (d.ros) v.ros = d.ros + off;
+        if (d.ros_w) v.ros_w = d.ros_w + off;
         if (d.ign) v.ign = d.ign + off;
         if (!d.shared_static) {
             v.stat = d.stat + off;
@@ -942,8 +1002,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.n_units = (int64_t)cnt * d.chunks * d.strips;
         v.queue = d.queue + q_off;
         v.qcap = q_cap;
-        v.rows = d.rows + (int64_t)e0 * d.H * d.strips;
-        v.rows_cap = (int64_t)cnt * d.H * d.strips;
+        v.rows = d.rows + (int64_t)e0 * tasks_per_env;
+        v.rows_cap = (int64_t)cnt * tasks_per_env;
         if (d.bits) {
             v.bits = d.bits + (int64_t)e0 * d.bits_env;
             v.tile_act = d.tile_act + (int64_t)e0 * d.tile_stride;
@@ -1347,7 +1407,7 @@ static int derive_if_dirty(sfb_sim* s) {
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (gr.d.bits) {  // the flagged tiles are this step's tasks
-        SFB_LAUNCH(k_tile_list, gr.units_blocks, 256, 0, st, gr.d, par);
+        SFB_LAUNCH_DEP(s->pdl, k_tile_list, gr.units_blocks, 256, 0, st, gr.d, par);
         s->launches_all++;
         s->launches_step++;
         return;
@@ -1375,9 +1435,13 @@ static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
 }
 static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (gr.d.bits) {
+        if (gr.d.keep_ros) {
+            SFB_LAUNCH(k_ros_zero, cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st, gr.d);
+            s->launches_all++;
+        }
         const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)gr.d.E * gr.d.tiles_y * gr.d.tiles_x + TILES_WARPS - 1) / TILES_WARPS, s->tiles_blocks));
-        if (s->cell_bytes == 1) SFB_LAUNCH(k_tiles<uint8_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
-        else SFB_LAUNCH(k_tiles<uint16_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        if (s->cell_bytes == 1) SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, k_tiles<uint8_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        else SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, k_tiles<uint16_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
         s->launches_all++;
         s->launches_step++;
         return;
@@ -1388,14 +1452,19 @@ static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     s->launches_step++;
 }
 static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
-    if (gr.d.keep_ros) {
+    if (gr.d.keep_ros && !gr.d.bits) {
         SFB_LAUNCH(k_clear_ros, cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st, gr.d, par);
         s->launches_all++;
     }
-    if (s->cell_bytes == 1) SFB_LAUNCH(k_eval<uint8_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
-    else SFB_LAUNCH(k_eval<uint16_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
+    const bool dep = s->pdl && gr.d.bits && !gr.d.keep_ros;
+    if (s->cell_bytes == 1) SFB_LAUNCH_DEP(dep, k_eval<uint8_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
+    else SFB_LAUNCH_DEP(dep, k_eval<uint16_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
     s->launches_all++;
     s->launches_step++;
+    if (gr.d.keep_ros && gr.d.bits) {
+        SFB_LAUNCH(k_ros_commit, cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st, gr.d, par);
+        s->launches_all++;
+    }
 }
 
 // refresh the fields of the group views that setters may have changed on the handle-wide params
@@ -1409,6 +1478,7 @@ static void sync_one_view(sfb_sim* s, EnvGroup& gr) {
         const DevParams before = gr.d;
         // the whole-handle view of a multi-group handle does not log (its steps invalidate the logs)
         gr.d.track = (&gr == &s->all && !s->groups.empty()) ? 0 : s->d.track;
+        gr.d.tile_stats = (s->front_bits && s->timing) ? s->list_ctr + 8 : nullptr;
         gr.d.halo_top = s->d.halo_top;
         gr.d.halo_bottom = s->d.halo_bottom;
         gr.d.halo_top_plane = s->d.halo_top_plane;
@@ -1895,7 +1965,7 @@ extern "C" int sfb_constant_spread_update(sfb_sim* s, int32_t env0, int32_t n, i
     if (!s || !maps) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: null argument");
     if (rate_of_spread < 0) return fail(SFB_ERR_INVALID, "sfb_constant_spread_update: rate_of_spread %d", rate_of_spread);
     if (s->in_step) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: a step is half done");
-    if (s->front_lists || s->front_bits || s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: not for list, bitboard or slab handles");
+    if (s->front_lists || s->prm.slab_total_H) return fail(SFB_ERR_STATE, "sfb_constant_spread_update: not for list or slab handles");
     int rc;
     if ((rc = check_env_range(s, "sfb_constant_spread_update", env0, n))) return rc;
     if ((rc = use(s))) return rc;
@@ -1908,6 +1978,7 @@ extern "C" int sfb_constant_spread_update(sfb_sim* s, int32_t env0, int32_t n, i
     s->launches_all++;
     s->parity ^= 1;
     if (d.unit_act) CU(cudaMemsetAsync(d.unit_act, 1, (size_t)d.E * d.unit_stride, s->stream));  // cells changed behind the flags' back
+    if (s->front_bits) DISPATCH(s, k_bits_rebuild, cap_grid(s, (long long)n * d.bits_plane, 256), 256, d, s->parity, (const int32_t*)nullptr, env0, n);  // ... and the planes'
     s->full_resync = 1;
     CU(cudaGetLastError());
     if ((rc = download_maps(s, env0, n, maps))) return rc;
@@ -2338,12 +2409,13 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
 extern "C" int sfb_get_front_stats(sfb_sim* s, int64_t* stats, int32_t n) {
     if (!s || !stats) return fail(SFB_ERR_INVALID, "sfb_get_front_stats: null argument");
     if (n < 0 || n > FRONT_N_STATS) return fail(SFB_ERR_INVALID, "sfb_get_front_stats: n = %d of %d", n, FRONT_N_STATS);
-    if (!s->front_lists) return fail(SFB_ERR_STATE, "sfb_get_front_stats: not a list handle");
+    if (!s->front_lists && !s->front_bits) return fail(SFB_ERR_STATE, "sfb_get_front_stats: not a list or bitboard handle");
     int rc;
     if ((rc = use(s))) return rc;
     unsigned long long c[FRONT_N_STATS];
-    CU(cudaMemcpyAsync(c, s->d.front_stats, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemsetAsync(s->d.front_stats, 0, sizeof(c), s->stream));
+    unsigned long long* dev = s->front_lists ? s->d.front_stats : s->list_ctr + 8;
+    CU(cudaMemcpyAsync(c, dev, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemsetAsync(dev, 0, sizeof(c), s->stream));
     CU(cudaStreamSynchronize(s->stream));
     for (int k = 0; k < n; ++k) stats[k] = (int64_t)c[k];
     return 0;

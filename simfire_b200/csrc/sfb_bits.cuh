@@ -1,29 +1,44 @@
-// Bitboard front end (SFB_FRONT_BITS): the candidate search of one update() call as word-wide bit
-// operations on 32 x 32-cell tiles, instead of a cell-by-cell look at 512-cell rows (k_rows).
+// Bitboard front end (SFB_FRONT_BITS): one update() call as word-wide bit operations on tiles of
+// 32 rows x 30 columns, with the rate look-up, the burn accumulation and the ignition test of the
+// tile's candidates done by the same warp -- instead of a cell-by-cell look at 512-cell rows (k_rows)
+// followed by a pass over a global work queue (k_eval).
 //
 // Next to the canonical per-cell state bytes the handle keeps bit planes, one 32-bit word per
-// (env, tile column of 32 cells, row):
+// (env, tile column, row).  A word owns 30 cells -- bit 1 + (x mod 30) of word x / 30 -- and, in the
+// sprite planes, carries a copy of the cell left of them in bit 0 and of the cell right of them in bit 31, so
+// that the three rows y-1, y, y+1 of ONE word column hold the whole 3 x 3 neighbourhood of its 30 cells:
 //
-//   IGN    the cell is ignitable (UNBURNED or a control line, fire.py:192-205)
-//   LINE   the cell is a control line
+//   IGN    the cell is ignitable (UNBURNED or a control line, fire.py:192-205); owned bits only
+//   LINE   the cell is a control line; owned bits only
 //   RING   R = max_fire_duration + 1 planes: plane (s mod R) holds the Fire sprites created by update()
 //          call s.  In call t the sprites of duration a (fire.py:633) are plane (t - 1 - a) mod R: the
-//          sources of the step are R - 1 of the planes as they stand, the remaining plane
-//          (t mod R) holds the sprites that have reached max_fire_duration -- they are pruned
-//          (fire.py:116-161), the plane is cleared, and the cells ignited by this call are written into
-//          it.  No sprite code is ever decoded and no plane that is read as a source is written during
-//          the step, so tiles never race.
+//          sources of the step are R - 1 of the planes as they stand; the remaining plane (t mod R)
+//          holds the sprites that have reached max_fire_duration -- they are pruned (fire.py:116-161)
+//          and the cells ignited by this call are written into it.  No plane that is read as a source
+//          is written during the step, every bit of a word has exactly one writer (the owner of the cell;
+//          all updates are atomic bit operations), and nothing but the owner of a cell touches its state
+//          byte or burn value: tiles never race, whatever the order the warps take them in.
 //
-// k_tiles, one warp per flagged tile, lane = row: for every duration (youngest first) and every
-// neighbour in the reference's last-write-wins order (S-E, S, S-W, E, W, N-E, N, N-W: fire.py:704-705
-// + sprite-list order) the shifted source plane is ANDed with the still undecided ignitable cells; three
-// more planes collect the winning direction.  ~60 warp-instructions per duration decide all 1024 cells
-// of a tile.  Candidates and (with attenuation) untouched control-line cells are pushed to the work
-// queue exactly as k_rows pushes them, so k_eval is unchanged -- it only also sets the new sprite's ring
-// bit and clears its IGN / LINE bits when a cell ignites.
+// A step is k_tile_list (compacts the flagged tiles of running envs), k_tiles, k_eval.
 //
-// A tile is flagged (tile_act) while its 34 x 34 window holds a ring bit or (with attenuation) the tile
-// holds a control line: raised at ignitions / resets / mitigation / map uploads, lowered by k_tiles.
+// k_tiles, one warp per listed tile, lane = row:
+//   * prune: the owned bits of plane t mod R -> BURNED state bytes, bits cleared (also the copies);
+//   * candidate search: for every duration (youngest first) and every neighbour in the reference's
+//     last-write-wins order (S-E, S, S-W, E, W, N-E, N, N-W: fire.py:704-705 + sprite-list order) the shifted
+//     source word is ANDed with the still undecided ignitable cells; three more words collect the winning
+//     direction.  ~25 warp-instructions per duration decide the 960 cells of a tile;
+//   * the candidates are compacted into shared memory and evaluated one per lane (process_item: the
+//     tabulated rate of the (cell, direction) pair, attenuation, float64 burn +=, strict > pixel_scale);
+//     the cells that ignite are collected per row and written to plane t mod R with one atomic per word;
+//   * control-line cells no fire touches are attenuated only if the env has any candidate in this call
+//     (fire.py:271-278, :651-652): a whole-env fact, so they go to the work queue and k_eval, which runs
+//     after every tile, applies them; k_eval also advances the per-env clocks, as in every front end.
+//
+// A tile is flagged (tile_act) while the 34 x 32 window of its words holds a sprite bit or (with
+// attenuation) the tile holds a control line.  The flags are double-buffered by step parity: a step
+// consumes the flags of its parity and raises those of the next step (the tile itself if it still has
+// something to look at, the neighbours of a cell that ignites on the tile's border), so lowering and
+// raising never meet on one byte.  Resets, mitigation and map uploads raise the flags the next step reads.
 #pragma once
 #include "sfb_kernels.cuh"
 
@@ -31,6 +46,8 @@ namespace sfb {
 
 constexpr int BP_IGN = 0, BP_LINE = 1, BP_RING = 2;
 constexpr int BITS_MAX_DUR = 7;  // ring of at most 8 planes; longer-lived sprites use the byte front ends
+constexpr int TW = 30;           // cells a word owns
+constexpr uint32_t OWN = 0x7FFFFFFEu;
 
 __device__ __forceinline__ uint32_t* bits_word(const DevParams& p, int env, int plane, int tx, int y) {
     return p.bits + (long long)env * p.bits_env + (long long)plane * p.bits_plane + (long long)tx * p.H + y;
@@ -40,30 +57,67 @@ __device__ __forceinline__ int ring_slot(int t, int a, int R) {
     int s = (t - 1 - a) % R;
     return s < 0 ? s + R : s;
 }
-__device__ __forceinline__ void mark_tiles_around(const DevParams& p, int env, int y, int x) {
+__device__ __forceinline__ void raise_tile(const DevParams& p, int buf, int env, int ty, int tx) {
+    p.tile_act[(long long)buf * p.tile_buf + (long long)env * p.tile_stride + (long long)ty * p.tiles_x + tx] = 1;
+}
+// every tile whose 34 x 32 window holds cell (y, x)
+__device__ __forceinline__ void raise_tiles_around(const DevParams& p, int buf, int env, int y, int x) {
     const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
-    const int tx0 = (x > 0 ? x - 1 : 0) >> 5, tx1 = (x + 1 < p.W ? x + 1 : p.W - 1) >> 5;
-    uint8_t* f = p.tile_act + (long long)env * p.tile_stride;
+    const int tx0 = (x > 0 ? x - 1 : 0) / TW, tx1 = (x + 1 < p.W ? x + 1 : p.W - 1) / TW;
     for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) f[ty * p.tiles_x + tx] = 1;
+        for (int tx = tx0; tx <= tx1; ++tx) raise_tile(p, buf, env, ty, tx);
+}
+// set / clear the bit of cell (y, x) in a sprite plane: the owned bit and its copies in the neighbour words
+__device__ __forceinline__ void ring_set_cell(const DevParams& p, int env, int slot, int y, int x, bool on) {
+    const int tx = x / TW, b = x - tx * TW;
+    uint32_t* w = bits_word(p, env, BP_RING + slot, tx, y);
+    if (on) {
+        atomicOr(w, 2u << b);
+        if (b == 0 && tx > 0) atomicOr(w - p.H, 1u << 31);
+        if (b == TW - 1 && tx + 1 < p.tiles_x) atomicOr(w + p.H, 1u);
+    } else {
+        atomicAnd(w, ~(2u << b));
+        if (b == 0 && tx > 0) atomicAnd(w - p.H, ~(1u << 31));
+        if (b == TW - 1 && tx + 1 < p.tiles_x) atomicAnd(w + p.H, ~1u);
+    }
 }
 // fire_map[y, x] was set to internal status `s` from outside (mitigation.py:77): sprite planes untouched
 __device__ __forceinline__ void bits_on_status(const DevParams& p, int env, int y, int x, int s) {
-    const uint32_t bit = 1u << (x & 31);
-    uint32_t* ign = bits_word(p, env, BP_IGN, x >> 5, y);
-    uint32_t* line = bits_word(p, env, BP_LINE, x >> 5, y);
+    const int tx = x / TW;
+    const uint32_t bit = 2u << (x - tx * TW);
+    uint32_t* ign = bits_word(p, env, BP_IGN, tx, y);
+    uint32_t* line = bits_word(p, env, BP_LINE, tx, y);
     if (ignitable(s)) atomicOr(ign, bit);
     else atomicAnd(ign, ~bit);
     if (s & ST_LINE_BIT) {
         atomicOr(line, bit);
-        if (p.attenuate) p.tile_act[(long long)env * p.tile_stride + (y >> 5) * p.tiles_x + (x >> 5)] = 1;
+        if (p.attenuate) raise_tile(p, p.bits_par, env, y >> 5, tx);
     } else {
         atomicAnd(line, ~bit);
     }
 }
+// k_eval, DIR_UNRING item: the cell carried a live sprite of plane `slot` when it was a candidate; if
+// it re-ignited in this call (its byte carries this call's code) the newer sprite replaces the older one
+template <typename CellT>
+__device__ __forceinline__ void bits_unring(const DevParams& p, const EnvMeta& m, int env, long long idx, int slot) {
+    const int c = (int)reinterpret_cast<const CellT*>(p.state)[idx] >> 3;
+    if (c != 1 + (m.t % Cell<CellT>::M)) return;
+    const long long cell = idx - (long long)env * p.plane;
+    const int y = (int)(cell / p.pitch), x = (int)(cell - (long long)y * p.pitch);
+    ring_set_cell(p, env, slot, y, x, false);
+}
+
+// the dense form of the same (k_eval after a queue overflow): a cell that ignited in this call keeps no bit in
+// any source plane
+template <typename CellT>
+__device__ __forceinline__ void bits_unring_all(const DevParams& p, const EnvMeta& m, int env, int y, int x) {
+    const int e = m.t % p.ring;
+    for (int slot = 0; slot < p.ring; ++slot)
+        if (slot != e) ring_set_cell(p, env, slot, y, x, false);
+}
 
 // (re)derive every plane of n envs (a device list, or [env0, env0 + n)) from their state bytes; one
-// thread per word.  Durations are those the NEXT update() call will see.
+// thread per word.  Durations are those the NEXT update() call will see; flags are raised for that call.
 template <typename CellT>
 __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* envs, const int env0, const int n) {
     const long long per_env = (long long)p.tiles_x * p.H, total = (long long)n * per_env;
@@ -72,18 +126,20 @@ __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* 
         const int k = (int)(i / per_env);
         const int env = envs ? envs[k] : env0 + k;
         const long long r = i - (long long)k * per_env;
-        const int y = (int)(r % p.H), tx = (int)(r / p.H);  // consecutive threads: consecutive rows of one tile column
+        const int y = (int)(r % p.H), tx = (int)(r / p.H);  // consecutive threads: consecutive rows of one word column
         const int t = p.meta[(long long)par * p.meta_stride + env].t;
         const int tm1 = (t - 1) % Cell<CellT>::M;
-        const CellT* row = state + (long long)env * p.plane + (long long)y * p.pitch + tx * 32;
+        const CellT* row = state + (long long)env * p.plane + (long long)y * p.pitch;
         uint32_t ign = 0, line = 0, ring[BITS_MAX_DUR + 1];
         for (int s = 0; s <= BITS_MAX_DUR; ++s) ring[s] = 0;
-        const int nx = min(32, p.W - tx * 32);
-        for (int b = 0; b < nx; ++b) {
-            const int c = row[b];
+        for (int b = 0; b < 32; ++b) {
+            const int x = tx * TW - 1 + b;
+            if (x < 0 || x >= p.W) continue;
+            const int c = row[x];
             const int st = c & 7;
-            if (ignitable(st)) ign |= 1u << b;
-            if (st & ST_LINE_BIT) line |= 1u << b;
+            const bool own = b >= 1 && b <= TW;
+            if (own && ignitable(st)) ign |= 1u << b;
+            if (own && (st & ST_LINE_BIT)) line |= 1u << b;
             if ((c >> 3) != 0) {
                 const int a = min(sprite_age<CellT>(c >> 3, tm1), p.max_dur);  // >= max_dur: pruned by the next call
                 ring[ring_slot(t, a, p.ring)] |= 1u << b;
@@ -96,9 +152,10 @@ __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* 
             *bits_word(p, env, BP_RING + s, tx, y) = ring[s];
             any |= ring[s];
         }
-        if (any) {  // flag every tile whose 34 x 34 window can see this word (generously)
-            mark_tiles_around(p, env, y, tx * 32);
-            mark_tiles_around(p, env, y, min(tx * 32 + 31, p.W - 1));
+        if (any) {  // every tile whose window can see a bit of this word (generously)
+            const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int txx = max(tx - 1, 0); txx <= min(tx + 1, p.tiles_x - 1); ++txx) raise_tile(p, par, env, ty, txx);
         }
     }
 }
@@ -108,30 +165,37 @@ __device__ __forceinline__ unsigned long long make_tile_task(int env, int ty, in
     return (unsigned long long)(unsigned)ty | ((unsigned long long)(unsigned)tx << 16) | ((unsigned long long)(unsigned)env << 32);
 }
 
-// compacts the flagged tiles of running envs into this step's task list (the same scan as k_row_list)
+// compacts the flagged tiles of running envs into this step's task list and lowers their flags (the step
+// raises the other buffer); 16 flags per lane per load
 __global__ void __launch_bounds__(256) k_tile_list(const DevParams p, const int par) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long n4 = (long long)p.E * p.tile_stride / 4;  // tile_stride is a multiple of 4
+    const long long n16 = (long long)p.E * p.tile_stride / 16;  // tile_stride is a multiple of 16
     const long long used = (long long)p.tiles_y * p.tiles_x;
-    const uint32_t* flags = reinterpret_cast<const uint32_t*>(p.tile_act);
-    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n4; base += stride) {
+    uint4* const flags = reinterpret_cast<uint4*>(p.tile_act + (long long)par * p.tile_buf);
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n16; base += stride) {
         const long long w = base + lane;
-        const uint32_t f = w < n4 ? flags[w] : 0u;
-        if (!__any_sync(0xffffffffu, f != 0)) continue;
-        unsigned long long task[4];
+        uint4 f = make_uint4(0, 0, 0, 0);
+        if (w < n16) f = flags[w];
+        const bool some = (f.x | f.y | f.z | f.w) != 0;
+        if (!__any_sync(0xffffffffu, some)) continue;
         int cnt = 0;
-        if (f) {
+        uint32_t mask = 0;  // which of the 16 flags become tasks
+        int env = 0;
+        long long r0 = 0;
+        if (some) {
+            flags[w] = make_uint4(0, 0, 0, 0);
+            const long long u0 = 16 * w;
+            env = (int)(u0 / p.tile_stride);  // 16 | tile_stride: the 16 flags belong to one env
+            r0 = u0 - (long long)env * p.tile_stride;
+            if (p.meta[(long long)par * p.meta_stride + env].running) {  // an env that has quit only comes back through a reset
+                const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (!((f >> (8 * b)) & 0xFFu)) continue;
-                const long long u = 4 * w + b;
-                const int env = (int)(u / p.tile_stride);
-                if (!p.meta[(long long)par * p.meta_stride + env].running) continue;
-                const long long r = u - (long long)env * p.tile_stride;
-                if (r >= used) continue;  // pad flag (a map upload sets whole envs, pads included)
-                const int ty = (int)(r / p.tiles_x);
-                task[cnt++] = make_tile_task(env, ty, (int)(r - (long long)ty * p.tiles_x));
+                for (int b = 0; b < 16; ++b)
+                    if (((fw[b >> 2] >> (8 * (b & 3))) & 0xFFu) && r0 + b < used) mask |= 1u << b;  // pad flags: uploads set whole envs
+                cnt = __popc(mask);
             }
         }
         int incl = cnt;
@@ -145,136 +209,176 @@ __global__ void __launch_bounds__(256) k_tile_list(const DevParams p, const int 
         unsigned long long slot = 0;
         if (lane == 0) slot = atomicAdd(p.rows_count + par, (unsigned long long)total);
         slot = __shfl_sync(0xffffffffu, slot, 0) + (unsigned long long)(incl - cnt);
-        for (int i = 0; i < cnt; ++i)
-            if (slot + i < (unsigned long long)p.rows_cap) p.rows[slot + i] = task[i];
+        for (; mask; mask &= mask - 1, ++slot) {
+            const long long r = r0 + (__ffs(mask) - 1);
+            const int ty = (int)(r / p.tiles_x);
+            if (slot < (unsigned long long)p.rows_cap) p.rows[slot] = make_tile_task(env, ty, (int)(r - (long long)ty * p.tiles_x));
+        }
     }
 }
 
-constexpr int TILES_WARPS = 4;
+#ifndef SFB_TILES_WARPS
+#define SFB_TILES_WARPS 4
+#endif
+#ifndef SFB_TILES_MIN_BLOCKS
+#define SFB_TILES_MIN_BLOCKS 8
+#endif
+constexpr int TILES_WARPS = SFB_TILES_WARPS;
 
 template <typename CellT>
-__global__ void __launch_bounds__(TILES_WARPS * 32) k_tiles(const DevParams p, const int par) {
+__global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tiles(const DevParams p, const int par) {
     using C = Cell<CellT>;
-    __shared__ unsigned long long wq_all[TILES_WARPS][WQ_CAP];  // per-warp staging of work items
+    grid_dep_wait();
+    grid_dep_launch();
+    __shared__ uint16_t cq_all[TILES_WARPS][WQ_CAP];            // candidates of the tile in hand: row | bit << 5
+    __shared__ unsigned long long dq_all[TILES_WARPS][WQ_CAP];  // staging of items for k_eval (deferred line cells, replaced sprites)
+    __shared__ uint32_t nb_all[TILES_WARPS][32];                // cells of the tile that ignited, per row
+    __shared__ unsigned long long lq_all[TILES_WARPS][WQ_CAP];  // staging of change-log entries (SFB_TRACK_CHANGES)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    unsigned long long* const wq = wq_all[warp];
-    int wcount = 0;
+    uint16_t* const cq = cq_all[warp];
+    unsigned long long* const dq = dq_all[warp];
+    uint32_t* const nb = nb_all[warp];
+    unsigned long long* const lq = lq_all[warp];
+    int dcount = 0, lcount = 0;  // warp-uniform
+    unsigned int st_tiles = 0, st_cand = 0, st_ign = 0, st_pruned = 0, st_def = 0;  // statistics (kernel-timing passes only)
     const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
     const unsigned long long n_warps = (unsigned long long)gridDim.x * TILES_WARPS;
     CellT* const state = reinterpret_cast<CellT*>(p.state);
     const int R = p.ring, H = p.H, TX = p.tiles_x;
+    uint8_t* const flags_nxt = p.tile_act + (long long)(par ^ 1) * p.tile_buf;
 
-    auto flush = [&]() {
-        if (wcount == 0) return;
+    auto dflush = [&]() {
+        if (dcount == 0) return;
         __syncwarp();
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(p.qcount + par, (unsigned long long)wcount);
+        if (lane == 0) base = atomicAdd(p.qcount + par, (unsigned long long)dcount);
         base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < wcount; i += 32) {
+        for (int i = lane; i < dcount; i += 32) {
             const unsigned long long slot = base + i;
-            if (slot < (unsigned long long)p.qcap) p.queue[slot] = wq[i];
+            if (slot < (unsigned long long)p.qcap) p.queue[slot] = dq[i];
             else p.overflow[par] = 1;
         }
-        wcount = 0;
+        dcount = 0;
         __syncwarp();
     };
-    // every lane pushes the cells of `mask` (bits of its row) as work items, a bit per round
-    auto push_bits = [&](uint32_t mask, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t line, bool with_dir, int fixed_dir,
-                         long long row_idx, int x0) {
-        while (__any_sync(0xffffffffu, mask != 0)) {
-            const bool have = mask != 0;
-            const int b = have ? __ffs(mask) - 1 : 0;
-            mask &= mask - 1;
-            const uint32_t m = __ballot_sync(0xffffffffu, have);
-            if (have) {
-                const long long idx = row_idx + x0 + b;
-                const int dir = with_dir ? (int)(((d0 >> b) & 1u) | (((d1 >> b) & 1u) << 1) | (((d2 >> b) & 1u) << 2)) : fixed_dir;
-                // an ignitable cell that is no control line is UNBURNED; a line's kind is in its byte
-                const int s = ((line >> b) & 1u) ? ((int)state[idx] & 7) : (fixed_dir == DIR_PRUNED ? ST_BURNED : ST_UNBURNED);
-                wq[wcount + __popc(m & lt)] = make_item(idx, dir, s);
-            }
-            wcount += __popc(m);
-            if (wcount > WQ_CAP - 32) flush();
+    // change-log entries are staged per warp and appended in runs: the log lives in mapped host memory, and a run
+    // of entries is a few full PCIe writes where single entries would be one small write each
+    auto lflush = [&]() {
+        if (lcount == 0) return;
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.chg_count, (unsigned long long)lcount);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < lcount; i += 32) {
+            const unsigned long long slot = base + i;
+            if (slot < (unsigned long long)p.chg_cap) p.chg[slot] = lq[i];
+            else *p.chg_overflow = 1;
         }
+        lcount = 0;
+        __syncwarp();
+    };
+    auto lpush = [&](bool have, long long idx, int burn_status) {
+        const uint32_t m = __ballot_sync(0xffffffffu, have);
+        if (!m) return;
+        if (have) lq[lcount + __popc(m & lt)] = (unsigned long long)(idx + p.idx_base) | ((unsigned long long)burn_status << 48);
+        lcount += __popc(m);
+        if (lcount > WQ_CAP - 32) lflush();
+    };
+    // every lane calls; lanes with `have` contribute one item for k_eval
+    auto dpush = [&](bool have, unsigned long long item) {
+        const uint32_t m = __ballot_sync(0xffffffffu, have);
+        if (!m) return;
+        if (have) dq[dcount + __popc(m & lt)] = item;
+        dcount += __popc(m);
+        if (dcount > WQ_CAP - 32) dflush();
     };
 
     for (unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp; ti < n; ti += n_warps) {
         const unsigned long long task = p.rows[ti];
         const int ty = (int)(task & 0xFFFFu), tx = (int)((task >> 16) & 0xFFFFu), env = (int)(task >> 32);
         EnvMeta* const mp = p.meta + (long long)par * p.meta_stride + env;
-        const int t = mp->t;
-        const bool spread = !mp->time_quit;
-        const int y = ty * 32 + lane;
+        const EnvMeta m = *mp;
+        const int t = m.t;
+        const bool spread = !m.time_quit;
+        const int y0 = ty * 32, y = y0 + lane;
         const bool valid = y < H;
-        const int x0 = tx * 32;
-        const long long row_idx = (long long)env * p.plane + (long long)y * p.pitch;  // cell index of (y, x = 0)
-        const uint32_t* const base = p.bits + (long long)env * p.bits_env;
-        const bool has_l = tx > 0, has_r = tx + 1 < TX;
-        auto word = [&](int plane, int txx, int yy) -> uint32_t { return base[(long long)plane * p.bits_plane + (long long)txx * H + yy]; };
+        const int x0 = tx * TW;  // column of bit 1
+        const long long row0_idx = (long long)env * p.plane + (long long)y0 * p.pitch + x0 - 1;  // cell of (row 0, bit 0)
+        // word (plane 0, row 0) of this word column; plane k is PL * k words further (PL < 2^28: sfb_create)
+        uint32_t* const base = p.bits + (long long)env * p.bits_env + (long long)tx * H;
+        const uint32_t PL = (uint32_t)p.bits_plane;
+        // the two rows outside the tile ride in lanes 0 (row y0 - 1) and 1 (row y0 + 32)
+        const int yh = lane == 0 ? y0 - 1 : y0 + 32;
+        const bool hvalid = lane < 2 && yh >= 0 && yh < H;
 
-        uint32_t ign = valid ? word(BP_IGN, tx, y) : 0u;
-        uint32_t line = valid ? word(BP_LINE, tx, y) : 0u;
-
-        // sprites that reached max_fire_duration: BURNED, out of the ring (fire.py:116-161)
-        const int e = ring_slot(t, R - 1, R);  // = t mod R: duration max_fire_duration; this call's ignitions go here
-        uint32_t ew = valid ? word(BP_RING + e, tx, y) : 0u;
-        uint32_t window = ew;  // any ring bit in the 34 x 34 window (for lowering the flag)
-        uint32_t pruned = 0;
-        if (__any_sync(0xffffffffu, ew != 0)) {
-            for (uint32_t m = ew; m; m &= m - 1) {
-                const int b = __ffs(m) - 1;
-                const long long idx = row_idx + x0 + b;
-                const int c = state[idx];
-                // a bit whose sprite was replaced by a newer one on the same cell (a line drawn over a burning
-                // cell that re-ignited) is stale: the byte carries the newer sprite's code
-                if ((c >> 3) != 0 && sprite_age<CellT>(c >> 3, (t - 1) % C::M) >= p.max_dur) {
-                    state[idx] = (CellT)ST_BURNED;
-                    pruned |= 1u << b;
+        // ---- every word of the tile's window, all loads in flight together
+        const int slot0 = (t - 1) % R;                      // plane of the sprites of duration 0 (t >= 1)
+        const int e = slot0 + 1 == R ? 0 : slot0 + 1;       // = t mod R: duration max_fire_duration; this call's ignitions go here
+        uint32_t c[BITS_MAX_DUR], h[BITS_MAX_DUR];
+        {
+            uint32_t off = (uint32_t)(BP_RING + slot0) * PL;
+            const uint32_t wrap = (uint32_t)(R - 1) * PL;
+            int slot = slot0;
+#pragma unroll
+            for (int a = 0; a < BITS_MAX_DUR; ++a) {
+                c[a] = h[a] = 0;
+                if (a < R - 1) {
+                    if (valid) c[a] = base[off + (uint32_t)y];
+                    if (hvalid) h[a] = base[off + (uint32_t)yh];
+                    if (slot == 0) { slot = R - 1; off += wrap; } else { --slot; off -= PL; }
                 }
             }
-            if (ew != 0) *bits_word(p, env, BP_RING + e, tx, y) = 0u;
-            // a control line drawn over a burning cell (mitigation.py:77) burns out with its sprite (fire.py:157-159)
-            if (pruned & ign) *bits_word(p, env, BP_IGN, tx, y) = (ign &= ~pruned);
-            if (pruned & line) *bits_word(p, env, BP_LINE, tx, y) = (line &= ~pruned);
-            if (p.track) push_bits(pruned, 0, 0, 0, 0, false, DIR_PRUNED, row_idx, x0);
+        }
+        uint32_t* const w_ign = base + (uint32_t)y;              // this lane's words of the IGN / LINE / expiring planes
+        uint32_t* const w_line = base + (PL + (uint32_t)y);
+        uint32_t* const w_e = base + ((uint32_t)(BP_RING + e) * PL + (uint32_t)y);
+        uint32_t ign = 0, line = 0, ew = 0;
+        if (valid) {
+            ign = *w_ign;
+            line = *w_line;
+            ew = *w_e & OWN;
+        }
+        nb[lane] = 0;
+        st_tiles += lane == 0;
+        st_pruned += __popc(ew);
+
+        // ---- sprites that reached max_fire_duration: BURNED, out of the ring (fire.py:116-161)
+        if (__any_sync(0xffffffffu, ew != 0)) {
+            if (ew) {
+                atomicAnd(w_e, ~ew);
+                if ((ew & 2u) && tx > 0) atomicAnd(w_e - H, ~(1u << 31));
+                if ((ew & (1u << TW)) && tx + 1 < TX) atomicAnd(w_e + H, ~1u);
+                // a control line drawn over a burning cell (mitigation.py:77) burns out with its sprite
+                if (ew & ign) *w_ign = (ign &= ~ew);
+                if (ew & line) *w_line = (line &= ~ew);
+                const long long ri = row0_idx + (long long)lane * p.pitch;
+                for (uint32_t mm = ew; mm; mm &= mm - 1) state[ri + (__ffs(mm) - 1)] = (CellT)ST_BURNED;
+            }
+            if (p.track) {
+                uint32_t mm = ew;
+                while (__any_sync(0xffffffffu, mm != 0)) {
+                    const bool have = mm != 0;
+                    const int b = have ? __ffs(mm) - 1 : 0;
+                    mm &= mm - 1;
+                    lpush(have, row0_idx + (long long)lane * p.pitch + b, 2);  // BurnStatus.BURNED
+                }
+            }
         }
 
-        // candidate search: youngest sources first, then the reference's write order
-        uint32_t und = spread ? ign : 0u, d0 = 0, d1 = 0, d2 = 0, live = 0;
-        for (int a = 0; a < R - 1; ++a) {
-            const int k = BP_RING + ring_slot(t, a, R);
-            uint32_t c = 0, lr = 0;  // own word; bit 0: the cell left of the tile, bit 1: the cell right of it
-            if (valid) {
-                c = word(k, tx, y);
-                if (has_l) lr |= word(k, tx - 1, y) >> 31;
-                if (has_r) lr |= (word(k, tx + 1, y) & 1u) << 1;
-            }
-            uint32_t cu = __shfl_up_sync(0xffffffffu, c, 1), lru = __shfl_up_sync(0xffffffffu, lr, 1);
-            uint32_t cd = __shfl_down_sync(0xffffffffu, c, 1), lrd = __shfl_down_sync(0xffffffffu, lr, 1);
-            if (lane == 0) {  // the row above the tile
-                cu = lru = 0;
-                if (y > 0 && valid) {
-                    cu = word(k, tx, y - 1);
-                    if (has_l) lru |= word(k, tx - 1, y - 1) >> 31;
-                    if (has_r) lru |= (word(k, tx + 1, y - 1) & 1u) << 1;
-                }
-            }
-            if (lane == 31) {  // the row below it
-                cd = lrd = 0;
-                if (y + 1 < H) {
-                    cd = word(k, tx, y + 1);
-                    if (has_l) lrd |= word(k, tx - 1, y + 1) >> 31;
-                    if (has_r) lrd |= (word(k, tx + 1, y + 1) & 1u) << 1;
-                }
-            }
-            live |= c;
-            window |= c | lr | cu | lru | cd | lrd;
+        // ---- candidate search: youngest sources first, then the reference's write order
+        uint32_t und = spread ? ign : 0u, d0 = 0, d1 = 0, d2 = 0, live = 0, window = 0;
+#pragma unroll
+        for (int a = 0; a < BITS_MAX_DUR; ++a) {
+            if (a >= R - 1) break;
+            const uint32_t ca = c[a];
+            uint32_t cu = __shfl_up_sync(0xffffffffu, ca, 1), cd = __shfl_down_sync(0xffffffffu, ca, 1);
+            const uint32_t hu = __shfl_sync(0xffffffffu, h[a], 0), hd = __shfl_sync(0xffffffffu, h[a], 1);
+            if (lane == 0) cu = hu;
+            if (lane == 31) cd = hd;
+            live |= ca & OWN;
+            window |= ca | h[a];
             if (!__any_sync(0xffffffffu, und != 0)) continue;
-            // destination bit x <- source at (x + 1): shift right, the tile to the right supplies bit 31
-            const uint32_t sE = (c >> 1) | ((lr >> 1) << 31), sW = (c << 1) | (lr & 1u);
-            const uint32_t sSE = (cd >> 1) | ((lrd >> 1) << 31), sSW = (cd << 1) | (lrd & 1u);
-            const uint32_t sNE = (cu >> 1) | ((lru >> 1) << 31), sNW = (cu << 1) | (lru & 1u);
             auto take = [&](uint32_t src, int dir) {
                 const uint32_t w = src & und;
                 und &= ~w;
@@ -282,30 +386,145 @@ __global__ void __launch_bounds__(TILES_WARPS * 32) k_tiles(const DevParams p, c
                 if (dir & 2) d1 |= w;
                 if (dir & 4) d2 |= w;
             };
-            if (p.diagonal) take(sSE, 5);
+            // destination bit b <- source at column b + 1: shift right
+            if (p.diagonal) take(cd >> 1, 5);
             take(cd, 6);
-            if (p.diagonal) take(sSW, 7);
-            take(sE, 4);
-            take(sW, 0);
-            if (p.diagonal) take(sNE, 3);
+            if (p.diagonal) take(cd << 1, 7);
+            take(ca >> 1, 4);
+            take(ca << 1, 0);
+            if (p.diagonal) take(cu >> 1, 3);
             take(cu, 2);
-            if (p.diagonal) take(sNW, 1);
+            if (p.diagonal) take(cu << 1, 1);
         }
-        const uint32_t cand = spread ? (ign & ~und) : 0u;
+        uint32_t cand = spread ? (ign & ~und) : 0u;
+        st_cand += __popc(cand);
         if (__any_sync(0xffffffffu, live != 0) && lane == 0) mp->any_live = 1;  // fire.py:637
-        if (__any_sync(0xffffffffu, cand != 0)) {
-            if (lane == 0) mp->any_cand = 1;  // fire.py:651
-            push_bits(cand, d0, d1, d2, line, true, 0, row_idx, x0);
-        }
+        const bool any_cand = __any_sync(0xffffffffu, cand != 0);
+        if (any_cand && lane == 0) mp->any_cand = 1;  // fire.py:651
+
         // control lines no fire touches are attenuated like all others if the env gets past the early
-        // return (fire.py:271-278, :651-652): deferred items, k_eval decides
-        const bool att_lines = p.attenuate && spread;
-        if (att_lines && __any_sync(0xffffffffu, (line & ~cand) != 0)) push_bits(line & ~cand, 0, 0, 0, line, false, DIR_NONE, row_idx, x0);
-        // nothing left to look at: the tile leaves the list until an ignition / line / upload flags it again
-        if (!__any_sync(0xffffffffu, (window | (p.attenuate ? line : 0u)) != 0) && lane == 0)
-            p.tile_act[(long long)env * p.tile_stride + (long long)ty * TX + tx] = 0;
+        // return (fire.py:271-278, :651-652): a whole-env fact -> k_eval
+        if (p.attenuate && spread) {
+            uint32_t mm = line & ~cand;
+            st_def += __popc(mm);
+            while (__any_sync(0xffffffffu, mm != 0)) {
+                const bool have = mm != 0;
+                const int b = have ? __ffs(mm) - 1 : 0;
+                mm &= mm - 1;
+                const long long idx = row0_idx + (long long)lane * p.pitch + b;
+                dpush(have, have ? make_item(idx, DIR_NONE, (int)state[idx] & 7) : 0ull);
+            }
+        }
+        // a candidate that still carries a live sprite (a burning cell that was made ignitable again from
+        // outside): if it re-ignites, its old ring bit has to go -- after every tile has read it
+        if (__any_sync(0xffffffffu, (cand & live) != 0)) {
+            uint32_t mm = cand & live;
+            while (__any_sync(0xffffffffu, mm != 0)) {
+                const bool have = mm != 0;
+                const int b = have ? __ffs(mm) - 1 : 0;
+                mm &= mm - 1;
+                int slot = slot0, found = 0;
+#pragma unroll
+                for (int a = 0; a < BITS_MAX_DUR; ++a) {
+                    if (a < R - 1 && ((c[a] >> b) & 1u)) found = slot;
+                    slot = slot == 0 ? R - 1 : slot - 1;
+                }
+                dpush(have, make_item(row0_idx + (long long)lane * p.pitch + b, DIR_UNRING, found));
+            }
+        }
+
+        // ---- the tile's candidates, one per lane: rate look-up, burn +=, ignition (process_item)
+        bool ignited_any = false;
+        while (__any_sync(0xffffffffu, cand != 0)) {
+            const int cnt = __popc(cand);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = min(__shfl_sync(0xffffffffu, incl, 31), WQ_CAP);
+            int at = incl - cnt;
+            while (cand && at < WQ_CAP) {  // the first WQ_CAP candidates in (row, column) order
+                const int b = __ffs(cand) - 1;
+                cand &= cand - 1;
+                cq[at++] = (uint16_t)(lane | (b << 5));
+            }
+            __syncwarp();
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const bool have = i0 + lane < total;
+                const int it = have ? cq[i0 + lane] : 0;
+                const int row = it & 31, b = it >> 5;
+                // the winning direction and the control-line bit sit in the registers of lane `row`
+                const uint32_t r0 = __shfl_sync(0xffffffffu, d0, row), r1 = __shfl_sync(0xffffffffu, d1, row);
+                const uint32_t r2 = __shfl_sync(0xffffffffu, d2, row), rl = __shfl_sync(0xffffffffu, line, row);
+                bool ignited = false;
+                long long idx = 0;
+                if (have) {
+                    idx = row0_idx + (long long)(row * p.pitch + b);
+                    const int dir = (int)(((r0 >> b) & 1u) | (((r1 >> b) & 1u) << 1) | (((r2 >> b) & 1u) << 2));
+                    // an ignitable cell that is no control line is UNBURNED; a line's kind is in its byte
+                    const int st = ((rl >> b) & 1u) ? ((int)state[idx] & 7) : ST_UNBURNED;
+                    ignited = process_item<CellT>(p, m, env, idx, dir, st);
+                    if (ignited) atomicOr(&nb[row], 1u << b);
+                }
+                if (p.track) lpush(ignited, idx, 1);  // BurnStatus.BURNING
+                ignited_any |= __any_sync(0xffffffffu, ignited);
+            }
+            __syncwarp();
+        }
+
+        // ---- this call's sprites join plane t mod R; they are no longer ignitable
+        uint8_t* const fl = flags_nxt + ((long long)env * p.tile_stride + (long long)(ty * TX + tx));  // this tile's flag for the next step
+        uint32_t mine = 0;
+        if (ignited_any) {
+            mine = nb[lane];
+            st_ign += __popc(mine);
+            if (mine) {
+                atomicOr(w_e, mine);
+                if ((mine & 2u) && tx > 0) atomicOr(w_e - H, 1u << 31);
+                if ((mine & (1u << TW)) && tx + 1 < TX) atomicOr(w_e + H, 1u);
+                *w_ign = ign & ~mine;
+                if (line & mine) *w_line = (line &= ~mine);
+            }
+            // the neighbours whose window holds a cell that ignited
+            const uint32_t all = __reduce_or_sync(0xffffffffu, mine);
+            const uint32_t top = __shfl_sync(0xffffffffu, mine, 0);
+            const int last = min(31, H - 1 - y0);
+            const uint32_t bot = __shfl_sync(0xffffffffu, mine, last);
+            if (lane == 0) {
+                const bool l = (all & 2u) && tx > 0, r = (all & (1u << TW)) && tx + 1 < TX;
+                if (l) fl[-1] = 1;
+                if (r) fl[1] = 1;
+                if (top && ty > 0) {
+                    fl[-TX] = 1;
+                    if ((top & 2u) && tx > 0) fl[-TX - 1] = 1;
+                    if ((top & (1u << TW)) && tx + 1 < TX) fl[-TX + 1] = 1;
+                }
+                if (bot && ty + 1 < p.tiles_y) {
+                    fl[TX] = 1;
+                    if ((bot & 2u) && tx > 0) fl[TX - 1] = 1;
+                    if ((bot & (1u << TW)) && tx + 1 < TX) fl[TX + 1] = 1;
+                }
+            }
+        }
+        // still something to look at: the tile is listed again
+        const bool stay = __any_sync(0xffffffffu, (window | mine | (p.attenuate ? line : 0u)) != 0);
+        if (stay && lane == 0) fl[0] = 1;
     }
-    flush();
+    dflush();
+    lflush();
+    if (p.tile_stats) {  // one atomic per warp and counter that has something
+        const unsigned int v[5] = {st_tiles * (32u * TW), st_cand, st_ign, st_pruned, st_def};
+        const int slot[5] = {0, 1, 2, 3, 6};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const unsigned int w = __reduce_add_sync(0xffffffffu, v[k]);
+            if (lane == 0 && w) atomicAdd(p.tile_stats + slot[k], (unsigned long long)w);
+        }
+        const unsigned int w = __reduce_add_sync(0xffffffffu, st_tiles);
+        if (lane == 0 && w) atomicAdd(p.tile_stats + 5, (unsigned long long)w);
+    }
 }
 
 }  // namespace sfb

@@ -108,6 +108,7 @@ struct DevParams {
     void* state;
     double* burn;
     double* ros;
+    double* ros_w;           // where a step writes its rates: `ros`, or (bitboard handles) a plane committed after k_eval
     int32_t* ign;            // update() call that ignited the cell (SFB_KEEP_IGNITION), else nullptr
     const StaticRec* stat;   // raw inputs as uploaded
     const DerivedRec* drv;   // derived from `stat` by k_derive_static before the first step that needs it
@@ -171,15 +172,31 @@ struct DevParams {
     int64_t ros_cap;
     // bitboard front end (sfb_bits.cuh): bit planes next to the state bytes, one word per (env, tile column, row)
     uint32_t* bits;                  // [E][2 + ring][tiles_x][H] (nullptr: not a bitboard handle)
-    int32_t ring, tiles_x, tiles_y, bits_pad_;
+    int32_t ring, tiles_x, tiles_y, bits_pad_;  // tiles_x = ceil(W / 30): a word owns 30 cells
     int64_t bits_plane, bits_env;    // words per plane (tiles_x * H) and per env
-    uint8_t* tile_act;               // [E][tile_stride] activity flag per 32 x 32 tile
-    int64_t tile_stride;
+    uint8_t* tile_act;               // [2][E][tile_stride] activity flag per tile of 32 rows x 30 columns, by step parity
+    int64_t tile_stride, tile_buf;   // flags per env (a multiple of 16) and per buffer (all envs of the handle)
+    int32_t bits_par, bits_pad2_;    // setup kernels: the buffer the next step reads
+    unsigned long long* tile_stats;  // [FRONT_N_STATS] accumulated by k_tiles while kernel timing is on, else nullptr
     unsigned long long* late;        // cells that re-ignite while still a source for this step (rewritten by the last block)
     unsigned int* late_count;
     int64_t late_cap;
     unsigned long long* front_stats; // [FRONT_N_STATS] accumulated by k_front, read and reset by sfb_get_front_stats
 };
+
+// kernels that may be launched with programmatic stream serialization (SFB_LAUNCH_DEP): nothing the preceding
+// kernel of the stream wrote is read before this returns; a no-op for ordinary launches
+__device__ __forceinline__ void grid_dep_wait() {
+#ifndef SFB_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+// ... and the successor may be scheduled from here on (it still waits for this grid to finish)
+__device__ __forceinline__ void grid_dep_launch() {
+#ifndef SFB_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ const LogRef& log_of_env(const DevParams& p, int env) {
     int g = 0;
@@ -256,30 +273,6 @@ __device__ __forceinline__ void mark_units_of_cell(const DevParams& p, int env, 
     mark_units_around<CellT>(p, env, y, x);
 }
 
-// bitboard handles (sfb_bits.cuh): a cell ignited in update() call t joins ring plane t mod R (its sprite has
-// duration 0 in call t + 1), leaves the IGN / LINE planes, and the tiles within one cell of it are flagged
-__device__ __forceinline__ void bits_ignite_cell(const DevParams& p, int env, long long cell, int t) {
-    int y, x;
-    if (p.plane <= 0x7fffffffll) {
-        const uint32_t c = (uint32_t)cell;
-        y = (int)(c / (uint32_t)p.pitch);
-        x = (int)(c - (uint32_t)y * (uint32_t)p.pitch);
-    } else {
-        y = (int)(cell / p.pitch);
-        x = (int)(cell - (long long)y * p.pitch);
-    }
-    const uint32_t bit = 1u << (x & 31);
-    uint32_t* const w = p.bits + (long long)env * p.bits_env + (long long)(x >> 5) * p.H + y;  // word of plane 0 (IGN)
-    atomicAnd(w, ~bit);
-    atomicAnd(w + p.bits_plane, ~bit);                                  // LINE
-    atomicOr(w + (long long)(2 + t % p.ring) * p.bits_plane, bit);      // RING slot t mod R
-    const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
-    const int tx0 = (x > 0 ? x - 1 : 0) >> 5, tx1 = (x + 1 < p.W ? x + 1 : p.W - 1) >> 5;
-    uint8_t* f = p.tile_act + (long long)env * p.tile_stride;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) f[ty * p.tiles_x + tx] = 1;
-}
-
 __device__ __forceinline__ unsigned long long make_item(long long idx, int dir, int s) {
     return (unsigned long long)idx | ((unsigned long long)dir << 48) | ((unsigned long long)s << 52);
 }
@@ -310,6 +303,20 @@ __device__ __forceinline__ void log_append(const DevParams& p, bool have, long l
     }
 }
 
+// handles without a rate table (it did not fit): the rate from the derived record, float64 pow / cos per item.
+// Not inlined: the callers' common path (one table read) should not carry its registers.
+#ifdef SFB_EMU
+#define SFB_NOINLINE __attribute__((noinline))
+#else
+#define SFB_NOINLINE __noinline__
+#endif
+static __device__ SFB_NOINLINE double rate_from_record(const DevParams& p, long long sc, int dir) {
+    const float4* rp = reinterpret_cast<const float4*>(p.drv + sc);
+    const float4 t0 = __ldg(rp), t1 = __ldg(rp + 1), e = __ldg(rp + 2);
+    const SfbFuelTerms t = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    return sfb_spread_from_terms(dir, t, e.x, e.y, e.z, e.w);
+}
+
 // returns true if the cell ignited
 template <typename CellT>
 __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& m, int env, long long idx,
@@ -323,10 +330,7 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
             // the eight float64 rates of the cell once, through the same device function as below
             ros = __ldg(p.rtab + sc * 8 + dir) * p.dt;  // fire.py:696
         } else {
-            const float4* rp = reinterpret_cast<const float4*>(p.drv + sc);
-            const float4 t0 = __ldg(rp), t1 = __ldg(rp + 1), e = __ldg(rp + 2);
-            const SfbFuelTerms t = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            ros = sfb_spread_from_terms(dir, t, e.x, e.y, e.z, e.w) * p.dt;  // rothermel.py:4-136, fire.py:696
+            ros = rate_from_record(p, sc, dir) * p.dt;  // rothermel.py:4-136, fire.py:696
         }
         if (s & ST_LINE_BIT) ros = p.attenuate ? ros - line_attenuation(s) : 0.0;  // fire.py:271-282
     } else {
@@ -335,7 +339,7 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
         if (!m.any_cand) return false;
         ros = 0.0 - line_attenuation(s);
     }
-    if (p.keep_ros) p.ros[idx] = ros;
+    if (p.keep_ros) p.ros_w[idx] = ros;
     double b = p.burn[idx];
     if (ros != 0.0) {  // burn + 0 == burn: skip the store
         b += ros;      // fire.py:710
@@ -346,7 +350,6 @@ __device__ __forceinline__ bool process_item(const DevParams& p, const EnvMeta& 
         reinterpret_cast<CellT*>(p.state)[idx] = (CellT)(ST_BURNING | (code << 3));  // fire.py:571-587
         if (p.ign) p.ign[idx] = m.t;
         if (p.unit_act) mark_units_of_cell<CellT>(p, env, idx);
-        if (p.bits) bits_ignite_cell(p, env, idx - (long long)env * p.plane, m.t);
         return true;
     }
     return false;
@@ -1089,6 +1092,13 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
 // k_eval: persistent grid-stride over the work queue (or, if the queue overflowed, over
 // every cell).  Threads 0..E-1 also write the next step's EnvMeta.
 // ---------------------------------------------------------------------------------------
+// bitboard handles (sfb_bits.cuh)
+template <typename CellT>
+__device__ __forceinline__ void bits_unring(const DevParams& p, const EnvMeta& m, int env, long long idx, int slot);
+template <typename CellT>
+__device__ __forceinline__ void bits_unring_all(const DevParams& p, const EnvMeta& m, int env, int y, int x);
+constexpr int DIR_UNRING = 10;  // work item of a bitboard handle: the ring bit of a sprite replaced by a re-ignition
+
 template <typename CellT>
 __device__ void dense_cell(const DevParams& p, const int par, long long idx) {
     using C = Cell<CellT>;
@@ -1100,6 +1110,8 @@ __device__ void dense_cell(const DevParams& p, const int par, long long idx) {
     if (!m.running || m.time_quit) return;
     const CellT* st = reinterpret_cast<const CellT*>(p.state);
     const int s = st[idx] & 7;
+    // bitboard handles: k_tiles has evaluated the candidates; the items it left for k_eval were lost with the queue
+    if (p.bits && ((int)st[idx] >> 3) == 1 + (m.t % C::M)) bits_unring_all<CellT>(p, m, env, y, x);
     if (!ignitable(s)) return;
     const int tm1 = (m.t - 1) % C::M;
     int best = p.max_dur, dir = DIR_NONE;
@@ -1126,11 +1138,14 @@ __device__ void dense_cell(const DevParams& p, const int par, long long idx) {
     look(-1, 0, 2);
     if (p.diagonal) look(-1, -1, 1);
     if (dir == DIR_NONE && !((s & ST_LINE_BIT) && p.attenuate)) return;
+    if (p.bits && dir != DIR_NONE) return;  // a candidate: done by k_tiles
     process_item<CellT>(p, m, env, idx, dir, s);
 }
 
 template <typename CellT>
 __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gstride = (long long)gridDim.x * blockDim.x;
 
@@ -1151,6 +1166,9 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
                 const int dir = (int)((it >> 48) & 0xF), s = (int)((it >> 52) & 7);
                 if (dir == DIR_PRUNED) {
                     logged = 2;  // BurnStatus.BURNED
+                } else if (dir == DIR_UNRING) {
+                    const int env = (int)(idx / p.plane);
+                    bits_unring<CellT>(p, p.meta[(long long)par * p.meta_stride + env], env, idx, s);
                 } else {
                     const int env = (int)(idx / p.plane);
                     const EnvMeta m = p.meta[(long long)par * p.meta_stride + env];

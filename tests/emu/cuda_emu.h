@@ -221,6 +221,11 @@ static inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) {
     for (int b = 0; b < 32; ++b) r |= (emu::ballot((v >> b) & 1u, 9 + b) != 0 ? 1u : 0u) << b;  // 32 votes: slow, simple
     return r;
 }
+static inline unsigned int __reduce_add_sync(uint32_t, unsigned int v) {
+    unsigned int r = 0;
+    for (int b = 0; b < 32; ++b) r += (unsigned int)__builtin_popcount(emu::ballot((v >> b) & 1u, 50 + b)) << b;  // bit-sliced sum
+    return r;
+}
 template <class T>
 static inline T __shfl_sync(uint32_t, T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");

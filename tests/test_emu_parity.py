@@ -115,7 +115,7 @@ def test_bench_gpu_arm_dry_run_under_emulation():
     bench before the GPU box does.  The numbers mean nothing; the line's shape is checked."""
     import json
 
-    for front in ("lists", "rows", "dense"):
+    for front in ("lists", "bits", "rows", "dense"):
         res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dry_run.py"), "--workload", "small",
                               "--steps", "3", "--warmup", "3", "--burn-in", "5", "--roofline-steps", "2", "--e2e-steps", "3",
                               "--age-curve", "50" if front == "lists" else "0", "--parity-updates", "12",
@@ -136,6 +136,8 @@ def test_bench_gpu_arm_dry_run_under_emulation():
             assert rf["kernel"] == "k_front" and rf["per_launch"]["examined"] > 0 and not rf["went_dense"]
             assert line["gpu_launches"] == 3  # one kernel per step (the small workload has no attenuation)
             assert line["fire_age"]["updates"] == 50 and len(line["fire_age"]["blocks"]) == 1
+        if front == "bits":
+            assert rf["kernel"] in ("k_tile_list", "k_tiles", "k_eval") and rf["per_launch"]["candidates"] > 0
         if front == "dense":
             assert rf["unit_skipping"]["units_listed"] == rf["unit_skipping"]["units_total"]
         else:  # the CPU leg also checks the device against the reference (or the port) on the envs it names

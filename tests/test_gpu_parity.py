@@ -357,14 +357,16 @@ def _random_case(seed):
     return wl, kw, start, lines, steps, actions
 
 
+@pytest.mark.parametrize("front", ["sweeps", "bits"])
 @pytest.mark.parametrize("seed", range(24))
-def test_random_scenarios_against_oracle(seed):
+def test_random_scenarios_against_oracle(seed, front):
     """Seeded random terrains, parameters, control lines and between-step actions: fire_map,
     GameStatus and elapsed_time bit-exact against the NumPy oracle every step, the burn plane
     within tolerance.  The oracle runs first; a scenario in which some cell's accumulated burn
     comes within 2e-3 (relative to its increment) of the ignition threshold is not a fair test of
     bit-exactness ("Ties at the ignition threshold") and is skipped.  Odd
-    seeds force row-unit skipping, seeds divisible by 4 chunk units, the rest sweep densely."""
+    seeds force row-unit skipping, seeds divisible by 4 chunk units, the rest sweep densely; "bits" runs
+    every seed on the bitboard front end (k_tile_list + k_tiles)."""
     from oracle.dense_numpy import DenseFire, DenseParams
     from simfire_b200 import FireEngine
 
@@ -394,7 +396,10 @@ def test_random_scenarios_against_oracle(seed):
                 uploads[t] = m
                 oracle.set_fire_map(m)
     mode = dict(unit_skip=True) if seed % 2 else (dict(unit_skip=True, unit_chunks=True, rows_per_chunk=4) if seed % 4 == 0 else dict(unit_skip=False))
+    if front == "bits":
+        mode = dict(front_bits=True, wide_cells=bool(seed % 5 == 0))
     with FireEngine(wl.H, wl.W, 1, keep_ros=True, sweep_ldg=bool(seed % 3 == 0), **mode, **kw) as eng:
+        assert front != "bits" or eng.unit_mode() == "bits"
         eng.set_static(wl.planes)
         eng.reset([start])
         if lines:

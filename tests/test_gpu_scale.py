@@ -83,7 +83,7 @@ def test_cfg2_1024_against_oracle_short():
     _run_against_oracle(wl, wl.init_pos, 40, check_every=20)
 
 
-@pytest.mark.parametrize("front", ["lists", "rows"])
+@pytest.mark.parametrize("front", ["lists", "rows", "bits"])
 def test_target_batch_2048x1024_against_oracle(front):
     """The benchmarked configuration itself: 2048 x 2048 x 1024 envs on the bench terrain with the bench's
     ignition cells (bench.bench_starts), 150 updates, eight envs compared with the NumPy oracle -- each on
@@ -109,7 +109,7 @@ def test_target_batch_2048x1024_against_oracle(front):
         planes = {k: np.ascontiguousarray(np.broadcast_to(v, (H, W))[y0 : y0 + h, x0 : x0 + w]) for k, v in wl.planes.items()}
         oracles.append(DenseFire(planes, DenseParams(**wl.engine_kwargs()), (int(starts[e][0]) - x0, int(starts[e][1]) - y0)))
         wins.append(win)
-    kw = dict(front_lists=True) if front == "lists" else dict(unit_skip=True)
+    kw = {"lists": dict(front_lists=True), "rows": dict(unit_skip=True), "bits": dict(front_bits=True)}[front]
     margin = np.inf
     with FireEngine(H, W, E, shared_static=True, **kw, **wl.engine_kwargs()) as eng:
         assert eng.unit_mode() == front
@@ -167,14 +167,18 @@ def test_front_ends_agree_at_batch_size(shape):
     lines = np.stack([rng.integers(0, E, 4 * E), rng.integers(0, W, 4 * E), rng.integers(0, H, 4 * E),
                       rng.integers(3, 6, 4 * E)], axis=1)  # fmt: skip
     # row units (the default at this size), the 16-bit layout, the dense TMA / LDG sweeps and the list-driven step
-    variants = {"rows": {}, "wide": dict(wide_cells=True), "tma": dict(unit_skip=False), "lists": dict(front_lists=True),
-                "lists_wide": dict(front_lists=True, wide_cells=True), "ldg": dict(sweep_ldg=True)}
+    variants = {"rows": dict(unit_skip=True), "default": {}, "wide": dict(wide_cells=True, unit_skip=True), "tma": dict(unit_skip=False),
+                "lists": dict(front_lists=True),
+                "lists_wide": dict(front_lists=True, wide_cells=True), "ldg": dict(sweep_ldg=True),
+                "bits": dict(front_bits=True), "bits_wide_1group": dict(front_bits=True, wide_cells=True, env_groups=1)}
     if H == 512:
         variants["overflow"] = dict(queue_capacity=1000)
         variants["lists_overflow"] = dict(front_lists=True, queue_capacity=1000)
     results = {}
     for name, extra in variants.items():
         with FireEngine(H, W, E, shared_static=True, **kw, **extra) as eng:
+            if name == "default":  # what a caller who asks for nothing gets at this size
+                assert eng.unit_mode() == "bits"
             eng.set_static(wl.planes)
             eng.reset(starts)
             eng.apply_points(lines)
@@ -282,7 +286,8 @@ def test_cell_life_cycle_is_monotone():
 
 @pytest.mark.parametrize("shape,start", [((1, 1), (0, 0)), ((1, 40), (39, 0)), ((40, 1), (0, 0)), ((3, 3), (2, 2)),
                                           ((17, 513), (512, 16)), ((70, 1030), (0, 69))])
-def test_degenerate_and_ragged_grids_against_oracle(shape, start):
+@pytest.mark.parametrize("front", ["default", "bits"])
+def test_degenerate_and_ragged_grids_against_oracle(shape, start, front):
     """Single cells, single rows / columns, widths that are not a multiple of the 16-cell load or
     of the 512-cell strip, ignition in a corner: the reference's bounds handling (fire.py:192-205)."""
     from simfire_b200.workloads import Workload
@@ -297,7 +302,7 @@ def test_degenerate_and_ragged_grids_against_oracle(shape, start):
     planes["w_0"][start[1], start[0]] = 0.2
     wl = Workload("ragged", H, W, planes, pixel_scale=60.0, update_rate=1.5, max_fire_duration=3, max_time=90.0,
                   attenuate_line_ros=True, diagonal_spread=True, M_f=0.02, init_pos=start)  # fmt: skip
-    _run_against_oracle(wl, start, 70)
+    _run_against_oracle(wl, start, 70, **(dict(front_bits=True) if front == "bits" else {}))
 
 
 @pytest.mark.parametrize("max_dur", [1, 30, 31, 200])
@@ -309,3 +314,18 @@ def test_fire_duration_limits_of_the_two_cell_layouts(max_dur):
     wl.max_fire_duration = max_dur
     wl.pixel_scale = 400.0  # slow spread: sprites really live for many steps
     _run_against_oracle(wl, wl.init_pos, 90 if max_dur < 100 else 260, check_every=5)
+
+
+@pytest.mark.parametrize("max_dur", [1, 2, 7])
+def test_fire_duration_limits_of_the_bitboard_ring(max_dur):
+    """One sprite plane per duration: a ring of 2 (max_fire_duration 1) up to the 8 planes the tile kernel
+    holds in registers; longer-lived sprites fall back to the byte front ends."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    wl = synthetic_operational(64, 96, seed=13, patch=8)
+    wl.max_fire_duration = max_dur
+    wl.pixel_scale = 400.0
+    _run_against_oracle(wl, wl.init_pos, 90, check_every=5, front_bits=True)
+    with FireEngine(64, 96, 1, front_bits=True, **dict(wl.engine_kwargs(), max_fire_duration=8)) as eng:
+        assert eng.unit_mode() != "bits"
