@@ -532,7 +532,7 @@ def roofline_lists(eng, args, cells_rank, peak_gbs, peak_src, workload):
 
 
 def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
-    """The bitboard front end: k_tile_list + k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
+    """The bitboard front end: k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
     per launch of k_tiles, from the kernel's own counters over the per-launch-timed
     pass: per tile its 8-byte task, the 32 words of the ignitable and control-line planes and of the
     expiring sprite plane, 34 words of each of the ring - 1 source planes (32 rows + the row above and
@@ -542,19 +542,18 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
     eng.front_stats()  # reset the counters
     eng.set_kernel_timing(True)
     eng.step(args.roofline_steps)
-    list_ms, tiles_ms, eval_ms, n_t = eng.kernel_ms()
+    _, tiles_ms, eval_ms, n_t = eng.kernel_ms()
     eng.set_kernel_timing(False)
     fs = {k: v / n_t for k, v in eng.front_stats().items()}
     tiles, cand = fs["entries_read"], fs["candidates"]
     units_listed, units_total = eng.unit_stats()
     q_entries, q_cap, q_ovf = eng.queue_stats()
-    list_s, tiles_s, eval_s = list_ms / n_t * 1e-3, tiles_ms / n_t * 1e-3, eval_ms / n_t * 1e-3
-    tiles_bytes = (tiles * (8.0 + 3 * 128.0 + (ring - 1) * 34 * 4.0 + 1.0) + cand * 24.0 + fs["ignited"] * (1.0 + 12.0) +
+    tiles_s, eval_s = tiles_ms / n_t * 1e-3, eval_ms / n_t * 1e-3
+    tiles_bytes = (tiles * (8.0 + 3 * 128.0 + (ring - 1) * 34 * 4.0 + 2.0 + 8.0) + cand * 24.0 + fs["ignited"] * (1.0 + 12.0) +
                    fs["pruned"] * (1.0 + 4.0))
-    list_bytes = units_total * 1.0 + tiles * 8.0
     eval_bytes = q_entries * (8.0 + 16.0) + 64.0 * eng.E
-    kernel_ms = {"k_tile_list": list_s * 1e3, "k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
-    kernel_bytes = {"k_tile_list": list_bytes, "k_tiles": tiles_bytes, "k_eval": eval_bytes}
+    kernel_ms = {"k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
+    kernel_bytes = {"k_tiles": tiles_bytes, "k_eval": eval_bytes}
     dominant = max(kernel_ms, key=kernel_ms.get)
     dom_s = kernel_ms[dominant] * 1e-3
     achieved = kernel_bytes[dominant] / dom_s / 1e9
@@ -573,7 +572,7 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
                           "cells_swept_per_step": 0.0, "cells_per_step": cells_rank},
         "kernel_ms_per_launch": kernel_ms, "bytes_per_launch": kernel_bytes[dominant],
         "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank, "ms_per_launch": dom_s * 1e3,
-        "share_of_step": dom_s / (list_s + tiles_s + eval_s),
+        "share_of_step": dom_s / (tiles_s + eval_s),
         "per_launch": {k: round(v, 1) for k, v in fs.items()},
         "row_tasks_per_step": tiles, "work_items_per_step": cand, "items_left_to_k_eval": q_entries,
         "queue_overflowed": q_ovf, "front": "bits",

@@ -203,6 +203,7 @@ struct sfb_sim {
     int pdl;          // bitboard handles: programmatic dependent launch of the step kernels (SFB_PDL=0 turns it off)
     int front_bits;   // bitboard front end (sfb_bits.cuh): k_tile_list + k_tiles instead of k_row_list + k_rows
     int tiles_blocks; // grid of k_tiles
+    void (*tiles_fn)(DevParams, int);  // k_tiles<cell type, max_fire_duration>
     int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
     int lpar;         // which watch-list buffer the NEXT step reads
     int front_blocks; // persistent grid of k_front
@@ -714,6 +715,24 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     delete s;
 }
 
+// k_tiles is compiled once per number of source planes (max_fire_duration 1 .. BITS_MAX_DUR) and cell type
+typedef void (*tiles_fn_t)(DevParams, int);
+template <typename CellT>
+static tiles_fn_t tiles_kernel_of(int max_dur) {
+    switch (max_dur) {
+        case 1: return k_tiles<CellT, 1>;
+        case 2: return k_tiles<CellT, 2>;
+        case 3: return k_tiles<CellT, 3>;
+        case 4: return k_tiles<CellT, 4>;
+        case 5: return k_tiles<CellT, 5>;
+        case 6: return k_tiles<CellT, 6>;
+        default: return k_tiles<CellT, 7>;
+    }
+}
+static tiles_fn_t tiles_kernel(int cell_bytes, int max_dur) {
+    return cell_bytes == 1 ? tiles_kernel_of<uint8_t>(max_dur) : tiles_kernel_of<uint16_t>(max_dur);
+}
+
 static int create_impl(const sfb_params* prm, sfb_sim* s) {
     s->prm = *prm;
     CU(cudaSetDevice(prm->device));
@@ -864,9 +883,10 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
     int G = prm->env_groups;
     if (G <= 0) G = prm->slab_total_H != 0 ? 1 : (d.E >= 512 ? 4 : (d.E >= 64 ? 2 : 1));
     if (prm->slab_total_H != 0) G = 1;
-    // bitboard handles: a step is three short kernels whose tails are not worth hiding behind another group's
-    // launches (measured on the target batch: 1 group 128 T, 2 groups 117 T, 4 groups 67 T cell-updates/s)
-    if (prm->env_groups <= 0 && s->front_bits) G = 1;
+    // bitboard handles step all envs as one group: a step is two short kernels whose tails are not worth hiding
+    // behind another group's launches (measured on the target batch with the three-kernel form: 1 group 128 T,
+    // 2 groups 117 T, 4 groups 67 T cell-updates/s), and one group means one tile list for the setup kernels
+    if (s->front_bits) G = 1;
     G = std::min(G, std::min(d.E, 16));
     d.meta_stride = d.E;
     d.idx_base = 0;
@@ -917,7 +937,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         if (const char* e = getenv("SFB_FRONT_BLOCKS")) s->front_blocks = std::max(1, atoi(e));
     } else {
         if ((rc = dmalloc(s, &d.queue, (size_t)d.qcap * 8))) return rc;
-        if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8))) return rc;
+        // (bitboard handles: two tile lists, one per step parity)
+        if ((rc = dmalloc(s, &d.rows, (size_t)d.rows_cap * 8 * (s->front_bits ? 2 : 1)))) return rc;
     }
     // unit skipping: on for handles with enough units to make a list worth its launch, never in slab
     // mode (a neighbour slab's fire enters through the halo rows, which nobody here would flag)
@@ -960,9 +981,9 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(s->list_ctr, 0, 16 * sizeof(unsigned long long), s->stream));
         // (the row-task list allocated above is sized for the tile tasks)
         int per_sm = 0;
-        if (s->cell_bytes == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint8_t>, TILES_WARPS * 32, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles<uint16_t>, TILES_WARPS * 32, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiles_kernel(s->cell_bytes, prm->max_fire_duration), TILES_WARPS * 32, 0));
         if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_tiles does not fit on an SM");
+        s->tiles_fn = tiles_kernel(s->cell_bytes, prm->max_fire_duration);
         s->tiles_blocks = per_sm * s->n_sm;
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
@@ -1020,7 +1041,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         v.rows_count = gr.counters + 4;
         v.rows_next = gr.counters + 6;
         v.overflow = reinterpret_cast<int32_t*>(gr.counters + 8);
-        v.units_count = d.unit_act ? gr.counters + 10 : nullptr;
+        v.units_count = (d.unit_act || d.bits) ? gr.counters + 10 : nullptr;
         if (s->use_tma) {
             const cuuint64_t row_bytes = (cuuint64_t)d.pitch * s->cell_bytes;
             const cuuint64_t dims[3] = {row_bytes / 4, (cuuint64_t)d.H, (cuuint64_t)cnt};
@@ -1406,12 +1427,7 @@ static int derive_if_dirty(sfb_sim* s) {
 }
 
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
-    if (gr.d.bits) {  // the flagged tiles are this step's tasks
-        SFB_LAUNCH_DEP(s->pdl, k_tile_list, gr.units_blocks, 256, 0, st, gr.d, par);
-        s->launches_all++;
-        s->launches_step++;
-        return;
-    }
+    if (gr.d.bits) return;  // this step's tile list was written by the step before (and by the setup kernels)
     if (gr.d.unit_rows) {  // the flagged rows are this step's row tasks: nothing is swept
         SFB_LAUNCH(k_row_list, gr.units_blocks, 256, 0, st, gr.d, par);
         s->launches_all++;
@@ -1440,8 +1456,7 @@ static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
             s->launches_all++;
         }
         const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)gr.d.E * gr.d.tiles_y * gr.d.tiles_x + TILES_WARPS - 1) / TILES_WARPS, s->tiles_blocks));
-        if (s->cell_bytes == 1) SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, k_tiles<uint8_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
-        else SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, k_tiles<uint16_t>, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, s->tiles_fn, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
         s->launches_all++;
         s->launches_step++;
         return;
@@ -2350,7 +2365,7 @@ extern "C" int sfb_get_row_tasks(sfb_sim* s, int64_t* tasks, int64_t* capacity) 
         EnvGroup& gr = *grp;
         unsigned long long c[10];
         CU(cudaMemcpy(c, gr.counters, sizeof(c), cudaMemcpyDeviceToHost));
-        tot += (int64_t)c[4 + par];
+        tot += (int64_t)c[(gr.d.bits ? 10 : 4) + par];
         cap += gr.d.rows_cap;
     }
     if (tasks) *tasks = tot;
@@ -2382,7 +2397,7 @@ extern "C" int sfb_get_unit_stats(sfb_sim* s, int64_t* listed, int64_t* total, i
         for (EnvGroup* grp : views) {
             unsigned long long c[N_COUNTERS];
             CU(cudaMemcpy(c, grp->counters, sizeof(c), cudaMemcpyDeviceToHost));
-            act += (int64_t)c[4 + par];
+            act += (int64_t)c[10 + par];  // k_eval keeps the length of the list it emptied here
         }
         if (listed) *listed = act;
         if (total) *total = tot;

@@ -19,7 +19,8 @@
 //          all updates are atomic bit operations), and nothing but the owner of a cell touches its state
 //          byte or burn value: tiles never race, whatever the order the warps take them in.
 //
-// A step is k_tile_list (compacts the flagged tiles of running envs), k_tiles, k_eval.
+// A step is k_tiles + k_eval: the list of tiles a step has to look at is written by the step before it
+// (and by whatever touches the maps between steps), so nothing is scanned to find them.
 //
 // k_tiles, one warp per listed tile, lane = row:
 //   * prune: the owned bits of plane t mod R -> BURNED state bytes, bits cleared (also the copies);
@@ -34,11 +35,13 @@
 //     (fire.py:271-278, :651-652): a whole-env fact, so they go to the work queue and k_eval, which runs
 //     after every tile, applies them; k_eval also advances the per-env clocks, as in every front end.
 //
-// A tile is flagged (tile_act) while the 34 x 32 window of its words holds a sprite bit or (with
-// attenuation) the tile holds a control line.  The flags are double-buffered by step parity: a step
-// consumes the flags of its parity and raises those of the next step (the tile itself if it still has
-// something to look at, the neighbours of a cell that ignites on the tile's border), so lowering and
-// raising never meet on one byte.  Resets, mitigation and map uploads raise the flags the next step reads.
+// A tile is listed while the 34 x 32 window of its words holds a sprite bit or (with attenuation) the
+// tile holds a control line.  Lists and their flags (tile_act: "this tile is on the list", so that nobody
+// lists it twice) are double-buffered by step parity: a step takes the tiles of its parity off their list
+// and puts on the next step's list the tile itself if it still has something to look at and the neighbours of
+// a cell that ignites on the tile's border, so taking off and putting on never meet on one byte.  Resets,
+// mitigation and map uploads list tiles for the step that comes next.  Bitboard handles step all their envs
+// as one group (a step is two short kernels; there is nothing to overlap).
 #pragma once
 #include "sfb_kernels.cuh"
 
@@ -57,15 +60,26 @@ __device__ __forceinline__ int ring_slot(int t, int a, int R) {
     int s = (t - 1 - a) % R;
     return s < 0 ? s + R : s;
 }
-__device__ __forceinline__ void raise_tile(const DevParams& p, int buf, int env, int ty, int tx) {
-    p.tile_act[(long long)buf * p.tile_buf + (long long)env * p.tile_stride + (long long)ty * p.tiles_x + tx] = 1;
+// "tile is on list `buf`": one byte per tile, set with an atomic OR on the word that holds it; true if this
+// call set it (the caller then appends the tile)
+__device__ __forceinline__ bool tile_set_atomic(const DevParams& p, int buf, long long tile) {
+    uint8_t* const f = p.tile_act + (long long)buf * p.tile_buf;
+    const uint32_t bit = 1u << (8 * (int)(tile & 3));
+    return (atomicOr(reinterpret_cast<uint32_t*>(f) + (tile >> 2), bit) & bit) == 0;
 }
-// every tile whose 34 x 32 window holds cell (y, x)
-__device__ __forceinline__ void raise_tiles_around(const DevParams& p, int buf, int env, int y, int x) {
-    const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
-    const int tx0 = (x > 0 ? x - 1 : 0) / TW, tx1 = (x + 1 < p.W ? x + 1 : p.W - 1) / TW;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) raise_tile(p, buf, env, ty, tx);
+__device__ __forceinline__ bool tile_test_and_set(const DevParams& p, int buf, long long tile) {
+    if (*reinterpret_cast<volatile uint8_t*>(p.tile_act + (long long)buf * p.tile_buf + tile)) return false;  // listed already
+    return tile_set_atomic(p, buf, tile);
+}
+// tile task: ty | tx << 16 | env << 32
+__device__ __forceinline__ unsigned long long make_tile_task(int env, int ty, int tx) {
+    return (unsigned long long)(unsigned)ty | ((unsigned long long)(unsigned)tx << 16) | ((unsigned long long)(unsigned)env << 32);
+}
+// put tile (ty, tx) of `env` on list `buf` (setup kernels; k_tiles stages its appends per block)
+__device__ __forceinline__ void tile_list_add(const DevParams& p, int buf, int env, int ty, int tx) {
+    if (!tile_test_and_set(p, buf, (long long)env * p.tile_stride + (long long)ty * p.tiles_x + tx)) return;
+    const unsigned long long slot = atomicAdd(p.rows_count + buf, 1ULL);
+    if (slot < (unsigned long long)p.rows_cap) p.rows[(long long)buf * p.rows_cap + slot] = make_tile_task(env, ty, tx);
 }
 // set / clear the bit of cell (y, x) in a sprite plane: the owned bit and its copies in the neighbour words
 __device__ __forceinline__ void ring_set_cell(const DevParams& p, int env, int slot, int y, int x, bool on) {
@@ -91,7 +105,7 @@ __device__ __forceinline__ void bits_on_status(const DevParams& p, int env, int 
     else atomicAnd(ign, ~bit);
     if (s & ST_LINE_BIT) {
         atomicOr(line, bit);
-        if (p.attenuate) raise_tile(p, p.bits_par, env, y >> 5, tx);
+        if (p.attenuate) tile_list_add(p, p.bits_par, env, y >> 5, tx);
     } else {
         atomicAnd(line, ~bit);
     }
@@ -155,64 +169,7 @@ __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* 
         if (any) {  // every tile whose window can see a bit of this word (generously)
             const int ty0 = (y > 0 ? y - 1 : 0) >> 5, ty1 = (y + 1 < p.H ? y + 1 : p.H - 1) >> 5;
             for (int ty = ty0; ty <= ty1; ++ty)
-                for (int txx = max(tx - 1, 0); txx <= min(tx + 1, p.tiles_x - 1); ++txx) raise_tile(p, par, env, ty, txx);
-        }
-    }
-}
-
-// tile task: ty | tx << 16 | env << 32
-__device__ __forceinline__ unsigned long long make_tile_task(int env, int ty, int tx) {
-    return (unsigned long long)(unsigned)ty | ((unsigned long long)(unsigned)tx << 16) | ((unsigned long long)(unsigned)env << 32);
-}
-
-// compacts the flagged tiles of running envs into this step's task list and lowers their flags (the step
-// raises the other buffer); 16 flags per lane per load
-__global__ void __launch_bounds__(256) k_tile_list(const DevParams p, const int par) {
-    grid_dep_wait();
-    grid_dep_launch();
-    const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long n16 = (long long)p.E * p.tile_stride / 16;  // tile_stride is a multiple of 16
-    const long long used = (long long)p.tiles_y * p.tiles_x;
-    uint4* const flags = reinterpret_cast<uint4*>(p.tile_act + (long long)par * p.tile_buf);
-    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n16; base += stride) {
-        const long long w = base + lane;
-        uint4 f = make_uint4(0, 0, 0, 0);
-        if (w < n16) f = flags[w];
-        const bool some = (f.x | f.y | f.z | f.w) != 0;
-        if (!__any_sync(0xffffffffu, some)) continue;
-        int cnt = 0;
-        uint32_t mask = 0;  // which of the 16 flags become tasks
-        int env = 0;
-        long long r0 = 0;
-        if (some) {
-            flags[w] = make_uint4(0, 0, 0, 0);
-            const long long u0 = 16 * w;
-            env = (int)(u0 / p.tile_stride);  // 16 | tile_stride: the 16 flags belong to one env
-            r0 = u0 - (long long)env * p.tile_stride;
-            if (p.meta[(long long)par * p.meta_stride + env].running) {  // an env that has quit only comes back through a reset
-                const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-                for (int b = 0; b < 16; ++b)
-                    if (((fw[b >> 2] >> (8 * (b & 3))) & 0xFFu) && r0 + b < used) mask |= 1u << b;  // pad flags: uploads set whole envs
-                cnt = __popc(mask);
-            }
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        unsigned long long slot = 0;
-        if (lane == 0) slot = atomicAdd(p.rows_count + par, (unsigned long long)total);
-        slot = __shfl_sync(0xffffffffu, slot, 0) + (unsigned long long)(incl - cnt);
-        for (; mask; mask &= mask - 1, ++slot) {
-            const long long r = r0 + (__ffs(mask) - 1);
-            const int ty = (int)(r / p.tiles_x);
-            if (slot < (unsigned long long)p.rows_cap) p.rows[slot] = make_tile_task(env, ty, (int)(r - (long long)ty * p.tiles_x));
+                for (int txx = max(tx - 1, 0); txx <= min(tx + 1, p.tiles_x - 1); ++txx) tile_list_add(p, par, env, ty, txx);
         }
     }
 }
@@ -224,8 +181,10 @@ __global__ void __launch_bounds__(256) k_tile_list(const DevParams p, const int 
 #define SFB_TILES_MIN_BLOCKS 8
 #endif
 constexpr int TILES_WARPS = SFB_TILES_WARPS;
+constexpr int AQ_CAP = 32 * TILES_WARPS;
 
-template <typename CellT>
+// NSRC = max_fire_duration = the number of sprite planes a step reads as sources (the ring has NSRC + 1)
+template <typename CellT, int NSRC>
 __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tiles(const DevParams p, const int par) {
     using C = Cell<CellT>;
     grid_dep_wait();
@@ -234,6 +193,10 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     __shared__ unsigned long long dq_all[TILES_WARPS][WQ_CAP];  // staging of items for k_eval (deferred line cells, replaced sprites)
     __shared__ uint32_t nb_all[TILES_WARPS][32];                // cells of the tile that ignited, per row
     __shared__ unsigned long long lq_all[TILES_WARPS][WQ_CAP];  // staging of change-log entries (SFB_TRACK_CHANGES)
+    __shared__ unsigned long long aq[AQ_CAP];                   // the block's appends to the next step's tile list
+    __shared__ unsigned int aq_n, aq_base;
+    if (threadIdx.x == 0) aq_n = 0;
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     uint16_t* const cq = cq_all[warp];
@@ -243,10 +206,14 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     int dcount = 0, lcount = 0;  // warp-uniform
     unsigned int st_tiles = 0, st_cand = 0, st_ign = 0, st_pruned = 0, st_def = 0;  // statistics (kernel-timing passes only)
     const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
+    const unsigned long long* const tasks = p.rows + (long long)par * p.rows_cap;
+    unsigned long long* const tasks_nxt = p.rows + (long long)(par ^ 1) * p.rows_cap;
+    uint8_t* const flags_cur = p.tile_act + (long long)par * p.tile_buf;
+    uint8_t* const flags_nxt = p.tile_act + (long long)(par ^ 1) * p.tile_buf;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * TILES_WARPS;
     CellT* const state = reinterpret_cast<CellT*>(p.state);
-    const int R = p.ring, H = p.H, TX = p.tiles_x;
-    uint8_t* const flags_nxt = p.tile_act + (long long)(par ^ 1) * p.tile_buf;
+    constexpr int R = NSRC + 1;
+    const int H = p.H, TX = p.tiles_x;
 
     auto dflush = [&]() {
         if (dcount == 0) return;
@@ -294,11 +261,51 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         if (dcount > WQ_CAP - 32) dflush();
     };
 
-    for (unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp; ti < n; ti += n_warps) {
-        const unsigned long long task = p.rows[ti];
+    // appends to the next step's list: lane k < 9 may have set the "listed" byte of one neighbour tile with an
+    // atomic whose answer (was it me who set it?) is only consumed here, a tile later
+    bool pend_want = false;
+    uint32_t pend_old = 0, pend_bit = 0;
+    unsigned long long pend_task = 0;
+    auto resolve = [&]() {
+        const bool won = pend_want && (pend_old & pend_bit) == 0;
+        pend_want = false;
+        const uint32_t wm = __ballot_sync(0xffffffffu, won);
+        if (!wm) return;
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(&aq_n, (unsigned int)__popc(wm));
+        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(wm & lt);
+        if (won) {
+            if (slot < AQ_CAP) {
+                aq[slot] = pend_task;
+            } else {  // the block's stage is full: straight to the list
+                const unsigned long long g = atomicAdd(p.rows_count + (par ^ 1), 1ULL);
+                if (g < (unsigned long long)p.rows_cap) tasks_nxt[g] = pend_task;
+            }
+        }
+    };
+    // tiles are dealt to the warps round-robin.  -DSFB_TILES_DYNAMIC: the first tile of a warp is its own number,
+    // further tiles are handed out by a counter, one ahead of the tile in hand (lane 0 holds the ticket; it is
+    // only looked at when the tile in hand is done), so that a warp that drew cheap tiles takes more of them
+#ifdef SFB_TILES_DYNAMIC  // measured on the target batch: no gain over the static deal (126 vs 136 T cell-updates/s)
+    const bool dynamic = n > n_warps;
+#else
+    const bool dynamic = false;
+#endif
+    unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp;
+    while (ti < n) {
+        unsigned long long ticket = ti + n_warps;
+        if (dynamic && lane == 0) ticket = n_warps + atomicAdd(p.rows_next + par, 1ULL);
+        const unsigned long long task = tasks[ti];
+        ti = ~0ull;  // (set from the ticket at the end of the iteration)
         const int ty = (int)(task & 0xFFFFu), tx = (int)((task >> 16) & 0xFFFFu), env = (int)(task >> 32);
         EnvMeta* const mp = p.meta + (long long)par * p.meta_stride + env;
         const EnvMeta m = *mp;
+        const long long tile_id = (long long)env * p.tile_stride + (long long)(ty * TX + tx);
+        if (lane == 0) flags_cur[tile_id] = 0;  // off this step's list
+        if (!m.running) {  // an env that has quit only comes back through a reset, which lists its tiles
+            ti = __shfl_sync(0xffffffffu, ticket, 0);
+            continue;
+        }
         const int t = m.t;
         const bool spread = !m.time_quit;
         const int y0 = ty * 32, y = y0 + lane;
@@ -315,19 +322,17 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         // ---- every word of the tile's window, all loads in flight together
         const int slot0 = (t - 1) % R;                      // plane of the sprites of duration 0 (t >= 1)
         const int e = slot0 + 1 == R ? 0 : slot0 + 1;       // = t mod R: duration max_fire_duration; this call's ignitions go here
-        uint32_t c[BITS_MAX_DUR], h[BITS_MAX_DUR];
+        uint32_t c[NSRC], h[NSRC];
         {
             uint32_t off = (uint32_t)(BP_RING + slot0) * PL;
             const uint32_t wrap = (uint32_t)(R - 1) * PL;
             int slot = slot0;
 #pragma unroll
-            for (int a = 0; a < BITS_MAX_DUR; ++a) {
+            for (int a = 0; a < NSRC; ++a) {
                 c[a] = h[a] = 0;
-                if (a < R - 1) {
-                    if (valid) c[a] = base[off + (uint32_t)y];
-                    if (hvalid) h[a] = base[off + (uint32_t)yh];
-                    if (slot == 0) { slot = R - 1; off += wrap; } else { --slot; off -= PL; }
-                }
+                if (valid) c[a] = base[off + (uint32_t)y];
+                if (hvalid) h[a] = base[off + (uint32_t)yh];
+                if (slot == 0) { slot = R - 1; off += wrap; } else { --slot; off -= PL; }
             }
         }
         uint32_t* const w_ign = base + (uint32_t)y;              // this lane's words of the IGN / LINE / expiring planes
@@ -339,6 +344,14 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             line = *w_line;
             ew = *w_e & OWN;
         }
+        // lane k < 9 speaks for the tile at (ty + k / 3 - 1, tx + k % 3 - 1) when the next step's list is written:
+        // its "already listed" byte is fetched with the planes (a stale 0 only costs the atomic)
+        const int ndy = lane / 3 - 1, ndx = lane % 3 - 1;
+        const bool nvalid = lane < 9 && ty + ndy >= 0 && ty + ndy < p.tiles_y && tx + ndx >= 0 && tx + ndx < TX;
+        const long long ntile = tile_id + (long long)(ndy * TX + ndx);
+        uint8_t nlisted = 1;
+        if (nvalid) nlisted = *reinterpret_cast<volatile uint8_t*>(flags_nxt + ntile);
+        resolve();  // the previous tile's appends
         nb[lane] = 0;
         st_tiles += lane == 0;
         st_pruned += __popc(ew);
@@ -369,8 +382,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         // ---- candidate search: youngest sources first, then the reference's write order
         uint32_t und = spread ? ign : 0u, d0 = 0, d1 = 0, d2 = 0, live = 0, window = 0;
 #pragma unroll
-        for (int a = 0; a < BITS_MAX_DUR; ++a) {
-            if (a >= R - 1) break;
+        for (int a = 0; a < NSRC; ++a) {
             const uint32_t ca = c[a];
             uint32_t cu = __shfl_up_sync(0xffffffffu, ca, 1), cd = __shfl_down_sync(0xffffffffu, ca, 1);
             const uint32_t hu = __shfl_sync(0xffffffffu, h[a], 0), hd = __shfl_sync(0xffffffffu, h[a], 1);
@@ -425,8 +437,8 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
                 mm &= mm - 1;
                 int slot = slot0, found = 0;
 #pragma unroll
-                for (int a = 0; a < BITS_MAX_DUR; ++a) {
-                    if (a < R - 1 && ((c[a] >> b) & 1u)) found = slot;
+                for (int a = 0; a < NSRC; ++a) {
+                    if ((c[a] >> b) & 1u) found = slot;
                     slot = slot == 0 ? R - 1 : slot - 1;
                 }
                 dpush(have, make_item(row0_idx + (long long)lane * p.pitch + b, DIR_UNRING, found));
@@ -475,8 +487,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         }
 
         // ---- this call's sprites join plane t mod R; they are no longer ignitable
-        uint8_t* const fl = flags_nxt + ((long long)env * p.tile_stride + (long long)(ty * TX + tx));  // this tile's flag for the next step
-        uint32_t mine = 0;
+        uint32_t mine = 0, all = 0, top = 0, bot = 0;
         if (ignited_any) {
             mine = nb[lane];
             st_ign += __popc(mine);
@@ -487,33 +498,38 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
                 *w_ign = ign & ~mine;
                 if (line & mine) *w_line = (line &= ~mine);
             }
-            // the neighbours whose window holds a cell that ignited
-            const uint32_t all = __reduce_or_sync(0xffffffffu, mine);
-            const uint32_t top = __shfl_sync(0xffffffffu, mine, 0);
-            const int last = min(31, H - 1 - y0);
-            const uint32_t bot = __shfl_sync(0xffffffffu, mine, last);
-            if (lane == 0) {
-                const bool l = (all & 2u) && tx > 0, r = (all & (1u << TW)) && tx + 1 < TX;
-                if (l) fl[-1] = 1;
-                if (r) fl[1] = 1;
-                if (top && ty > 0) {
-                    fl[-TX] = 1;
-                    if ((top & 2u) && tx > 0) fl[-TX - 1] = 1;
-                    if ((top & (1u << TW)) && tx + 1 < TX) fl[-TX + 1] = 1;
-                }
-                if (bot && ty + 1 < p.tiles_y) {
-                    fl[TX] = 1;
-                    if ((bot & 2u) && tx > 0) fl[TX - 1] = 1;
-                    if ((bot & (1u << TW)) && tx + 1 < TX) fl[TX + 1] = 1;
-                }
-            }
+            all = __reduce_or_sync(0xffffffffu, mine);
+            top = __shfl_sync(0xffffffffu, mine, 0);
+            bot = __shfl_sync(0xffffffffu, mine, min(31, H - 1 - y0));
         }
-        // still something to look at: the tile is listed again
+        // ---- the next step's list: the tile itself if it still has something to look at, and the neighbours
+        // whose window holds a cell that ignited
         const bool stay = __any_sync(0xffffffffu, (window | mine | (p.attenuate ? line : 0u)) != 0);
-        if (stay && lane == 0) fl[0] = 1;
+        {
+            const uint32_t rowbits = ndy < 0 ? top : (ndy > 0 ? bot : all);          // what ignited next to that row of tiles
+            const uint32_t colmask = ndx < 0 ? 2u : (ndx > 0 ? (1u << TW) : OWN);    // ... and next to that column
+            bool want = nvalid && (rowbits & colmask) != 0;
+            if (lane == 4) want = stay;
+            const int ty2 = ty + ndy, tx2 = tx + ndx;
+            // the atomic is issued now and looked at while the next tile's loads are in flight (resolve)
+            pend_want = want && !nlisted;
+            pend_bit = 1u << (8 * (int)(ntile & 3));
+            pend_old = pend_bit;
+            if (pend_want) pend_old = atomicOr(reinterpret_cast<uint32_t*>(flags_nxt) + (ntile >> 2), pend_bit);
+            pend_task = make_tile_task(env, ty2, tx2);
+        }
+        ti = __shfl_sync(0xffffffffu, ticket, 0);
     }
+    resolve();
     dflush();
     lflush();
+    // the block's appends, one atomic for all of them
+    __syncthreads();
+    const unsigned int n_app = min(aq_n, (unsigned int)AQ_CAP);
+    if (threadIdx.x == 0 && n_app) aq_base = (unsigned int)atomicAdd(p.rows_count + (par ^ 1), (unsigned long long)n_app);
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < n_app; i += blockDim.x)
+        if ((long long)aq_base + i < p.rows_cap) tasks_nxt[aq_base + i] = aq[i];
     if (p.tile_stats) {  // one atomic per warp and counter that has something
         const unsigned int v[5] = {st_tiles * (32u * TW), st_cand, st_ign, st_pruned, st_def};
         const int slot[5] = {0, 1, 2, 3, 6};

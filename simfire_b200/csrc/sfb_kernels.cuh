@@ -1198,8 +1198,14 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
         p.qcount[par ^ 1] = 0;
         p.overflow[par ^ 1] = 0;
         p.unit_next[par ^ 1] = 0;
-        p.rows_count[par ^ 1] = 0;
-        if (p.units_count) p.units_count[par ^ 1] = 0;
+        p.rows_next[par ^ 1] = 0;
+        if (p.bits) {  // the tile list of the next step is being written: the one just consumed is emptied
+            p.units_count[par] = p.rows_count[par];  // (kept for sfb_get_unit_stats)
+            p.rows_count[par] = 0;
+        } else {
+            p.rows_count[par ^ 1] = 0;
+            if (p.units_count) p.units_count[par ^ 1] = 0;
+        }
     }
 }
 
