@@ -531,14 +531,18 @@ def roofline_lists(eng, args, cells_rank, peak_gbs, peak_src, workload):
     }
 
 
-def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
+def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, step_ms):
     """The bitboard front end: k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
     per launch of k_tiles, from the kernel's own counters over the per-launch-timed
     pass: per tile its 8-byte task, the 32 words of the ignitable and control-line planes and of the
     expiring sprite plane, 34 words of each of the ring - 1 source planes (32 rows + the row above and
     below); per candidate the 8-byte rate of its (cell, direction) pair and the float64 burn value read
     and written; one state byte per ignition / burn-out; per tile up to three 128-byte plane rows written
-    back and one flag byte."""
+    back and one flag byte.
+    Launch duration: a step is these two kernels back to back on one stream, so the time of the dominant one
+    is taken as (the device-timed step of the timed region) x (its share of the two in a pass with CUDA events
+    around every launch); the event-bracketed times themselves carry ~10 us of launch and event latency per
+    launch, which is not kernel time, and are reported next to it."""
     eng.front_stats()  # reset the counters
     eng.set_kernel_timing(True)
     eng.step(args.roofline_steps)
@@ -552,16 +556,30 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
     tiles_bytes = (tiles * (8.0 + 3 * 128.0 + (ring - 1) * 34 * 4.0 + 2.0 + 8.0) + cand * 24.0 + fs["ignited"] * (1.0 + 12.0) +
                    fs["pruned"] * (1.0 + 4.0))
     eval_bytes = q_entries * (8.0 + 16.0) + 64.0 * eng.E
-    kernel_ms = {"k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
+    bracketed_ms = {"k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
+    share = {k: v / (tiles_s + eval_s) / 1e3 for k, v in bracketed_ms.items()}
+    kernel_ms = {k: step_ms * share[k] for k in bracketed_ms}
     kernel_bytes = {"k_tiles": tiles_bytes, "k_eval": eval_bytes}
     dominant = max(kernel_ms, key=kernel_ms.get)
     dom_s = kernel_ms[dominant] * 1e-3
     achieved = kernel_bytes[dominant] / dom_s / 1e9
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_kernel_traffic.json")) as f:
+            j = json.load(f)
+        if j.get("workload") == workload and dominant == "k_tiles" and "k_tiles" in j.get("kernels", {}):
+            k = j["kernels"]["k_tiles"]
+            traffic = k["dram_bytes_per_launch"] * tiles / max(1.0, k["tiles_at_capture"])
+            traffic_src = ("committed ncu capture, not a measurement of the timed run: %.1f MB read + %.1f MB written at %d tiles per "
+                           "launch with a cold L2 for every replay pass (profiles/r02/r02_k_tiles_ncu.json), scaled to this run's %d tiles"
+                           % (k["dram_bytes_read"] / 1e6, k["dram_bytes_write"] / 1e6, k["tiles_at_capture"], tiles))
+    except Exception:
+        pass
     return {
         "bound": "latency", "kernel": dominant, "env_groups_timed_one_after_the_other": True, "achieved": achieved,
         "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
         "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-        "traffic": None, "traffic_source": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "note": "front-proportional kernels: a step touches a few tens of MB (bit planes of the listed tiles, rate / burn "
                 "of the candidates), so HBM bandwidth is not what bounds it -- dependent-load latency and the launches "
                 "are; the HBM-bound kernel of this design is the dense TMA sweep (`dense_sweep`).",
@@ -570,9 +588,11 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring):
                     for k in kernel_ms},
         "unit_skipping": {"on": True, "mode": "bits", "units_listed": units_listed, "units_total": units_total,
                           "cells_swept_per_step": 0.0, "cells_per_step": cells_rank},
-        "kernel_ms_per_launch": kernel_ms, "bytes_per_launch": kernel_bytes[dominant],
+        "kernel_ms_per_launch": kernel_ms, "kernel_ms_per_launch_event_bracketed": bracketed_ms,
+        "launch_duration_method": "device-timed step of the timed region x the kernel's share of the event-bracketed pass",
+        "bytes_per_launch": kernel_bytes[dominant],
         "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank, "ms_per_launch": dom_s * 1e3,
-        "share_of_step": dom_s / (tiles_s + eval_s),
+        "share_of_step": share[dominant],
         "per_launch": {k: round(v, 1) for k, v in fs.items()},
         "row_tasks_per_step": tiles, "work_items_per_step": cand, "items_left_to_k_eval": q_entries,
         "queue_overflowed": q_ovf, "front": "bits",
@@ -689,6 +709,7 @@ def gpu_arm(args):
         barrier()
     launches = eng.launch_counts()[1] - l0
     ms_max = ctx.max(ms)
+    ms_min = -ctx.max(-ms)  # the fastest rank: ranks light different fires, so their steps are not equally long
     cells_rank = H * W * E
     cells_per_step = cells_rank * world
     value = cells_per_step * args.steps / (ms_max * 1e-3)
@@ -697,7 +718,7 @@ def gpu_arm(args):
     peak_gbs, peak_src = load_peak()
     unit_mode = eng.unit_mode()
     if unit_mode == "bits":
-        roof = roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, args.workload, wl.max_fire_duration + 1)
+        roof = roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, args.workload, wl.max_fire_duration + 1, ms_max / args.steps)
     else:
         roof = (roofline_lists if unit_mode == "lists" else roofline_sweeps)(eng, args, cells_rank, peak_gbs, peak_src, args.workload)
 
@@ -821,7 +842,11 @@ def gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32/f64", "data": "synthetic",
         "config": bench_config(args, wl, E, shared, world),
         "timing_notes": {"front": unit_mode, "timed_updates": [args.burn_in + args.warmup + 1, args.burn_in + args.warmup + args.steps],
-                         "footprint_per_step_MB": roof["bytes_per_launch"] / 1e6},
+                         "footprint_per_step_MB": roof["bytes_per_launch"] / 1e6,
+                         "ms_per_step_slowest_rank": ms_max / args.steps, "ms_per_step_fastest_rank": ms_min / args.steps,
+                         "ranks": "every rank lights its own random ignition cells (bench_starts(rank)), so the ranks' fire "
+                                  "fronts -- and with them the front-proportional step -- differ by a few per cent; `value` "
+                                  "uses the slowest rank"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes) * world,
                 "d2h_bytes_per_step": (int(log_b * e2e_changes / e2e_steps) + 16 if not args.no_track else int(maps_np.nbytes)) * world,

@@ -91,10 +91,14 @@ enum sfb_flags {
                                   kernel per step (k_front), no env groups.  Fewer instructions and bytes per
                                   step than the sweep front ends, but all of it scattered 32-byte reads: it pays
                                   where the planes fit L2 (single envs, small batches).  Results are identical  */
-    SFB_FRONT_BITS = 16384,    /* the bitboard front end (sfb_bits.cuh): bit planes next to the state bytes (ignitable,
+    SFB_FRONT_BITS = 16384,    /* the bitboard step (sfb_bits.cuh): bit planes next to the state bytes (ignitable,
                                   control line, one plane per sprite duration), the candidate search as word-wide
-                                  bit operations on 32 x 32 tiles (k_tile_list + k_tiles instead of k_row_list +
-                                  k_rows).  Needs max_fire_duration <= 7; results are identical                  */
+                                  bit operations on tiles of 32 rows x 30 columns, candidates evaluated by the
+                                  same warp, the next step's tile list written by the step itself: k_tiles +
+                                  k_eval, all envs as one group.  Needs max_fire_duration <= 7; results are
+                                  identical.  It is what a handle of >= 1024 row units gets when none of the
+                                  front-end flags (SFB_UNIT_*, SFB_SWEEP_LDG, SFB_FRONT_LISTS, rows_per_chunk,
+                                  slab mode) is given; the flag forces it on smaller handles                  */
     SFB_STEP_GRAPH = 4096      /* multi-group handles: replay pairs of steps of sfb_step(n) as one CUDA
                                   graph forked over the group streams instead of enqueueing every
                                   kernel (single-group handles always replay a graph).  Off by
@@ -144,7 +148,7 @@ typedef struct sfb_params {
     float M_f;                 /* Environment.M_f */
     int32_t env_groups;        /* 0 = auto; envs are stepped as this many independent groups on
                                   separate CUDA streams (k_sweep of one overlaps k_rows / k_eval of
-                                  another); 1 in slab mode */
+                                  another); 1 in slab mode and for bitboard handles */
     int64_t queue_capacity;    /* 0 = auto; work-queue entries (8 B each) */
     /* Slab mode (single huge grid split in rows across handles): this handle holds rows
      * [slab_y0, slab_y0 + H) of a grid with slab_total_H rows.  0/0 = whole grid. */
@@ -311,7 +315,7 @@ int sfb_get_stream(sfb_sim* sim, void** stream);
 /* Kernel launches issued by this handle so far (all kernels / hot-path kernels only). */
 int sfb_get_launch_counts(sfb_sim* sim, int64_t* all_kernels, int64_t* step_kernels);
 /* Per-kernel device time: while enabled every step records events around its three kernels
- * (k_sweep, k_rows, k_eval).  sfb_get_kernel_ms returns the accumulated milliseconds and the
+ * (k_sweep, k_rows, k_eval; a bitboard handle has no first kernel and reports k_tiles as the second).  sfb_get_kernel_ms returns the accumulated milliseconds and the
  * number of steps since enabling and resets them. */
 int sfb_set_kernel_timing(sfb_sim* sim, int32_t enabled);
 int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* eval_ms, int64_t* n_steps);
@@ -319,7 +323,8 @@ int sfb_get_kernel_ms(sfb_sim* sim, double* sweep_ms, double* rows_ms, double* e
 int sfb_get_row_tasks(sfb_sim* sim, int64_t* tasks, int64_t* capacity);
 /* Units = (env, chunk of rows or single row, strip of columns) the last completed step listed,
  * and the number of units of the handle; mode: 0 = no unit skipping (every unit is swept, the two
- * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks, 4 = flagged 32 x 32 tiles (bitboard front end), 3 = list-driven step
+ * counts are equal), 1 = flagged chunks are swept, 2 = flagged rows are the row tasks, 4 = listed tiles of 32 x 30 cells
+ * (bitboard step: listed = tiles the last step looked at, total = tiles of the handle), 3 = list-driven step
  * (listed = entries of the watch list, total = cells of the handle). */
 int sfb_get_unit_stats(sfb_sim* sim, int64_t* listed, int64_t* total, int32_t* mode);
 /* Work-queue statistics of the last completed step: entries pushed, capacity, and

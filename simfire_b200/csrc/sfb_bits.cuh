@@ -174,6 +174,15 @@ __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* 
     }
 }
 
+// L1 prefetch (a hint: no register, nobody waits for it)
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+#if !defined(SFB_EMU) && !defined(SFB_TILES_NO_PREFETCH)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+
 #ifndef SFB_TILES_WARPS
 #define SFB_TILES_WARPS 4
 #endif
@@ -296,6 +305,8 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         unsigned long long ticket = ti + n_warps;
         if (dynamic && lane == 0) ticket = n_warps + atomicAdd(p.rows_next + par, 1ULL);
         const unsigned long long task = tasks[ti];
+        // the warp's next tile (round-robin deal): its plane lines are prefetched while this tile's candidates are evaluated
+        const unsigned long long task2 = (!dynamic && ti + n_warps < n) ? tasks[ti + n_warps] : ~0ull;
         ti = ~0ull;  // (set from the ticket at the end of the iteration)
         const int ty = (int)(task & 0xFFFFu), tx = (int)((task >> 16) & 0xFFFFu), env = (int)(task >> 32);
         EnvMeta* const mp = p.meta + (long long)par * p.meta_stride + env;
@@ -413,6 +424,19 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         if (__any_sync(0xffffffffu, live != 0) && lane == 0) mp->any_live = 1;  // fire.py:637
         const bool any_cand = __any_sync(0xffffffffu, cand != 0);
         if (any_cand && lane == 0) mp->any_cand = 1;  // fire.py:651
+
+        // ---- the next tile of this warp: one prefetch per 128-byte line of its window.  Lane k < 10 takes the 32
+        // rows of plane k, lanes 10.. / 20.. the row above / below them in sprite plane k - 10 / k - 20, lane 30
+        // the env's clock.
+        if (task2 != ~0ull) {
+            const int ty2 = (int)(task2 & 0xFFFFu), tx2 = (int)((task2 >> 16) & 0xFFFFu), env2 = (int)(task2 >> 32);
+            const uint32_t* const b2 = p.bits + (long long)env2 * p.bits_env + (long long)tx2 * H;
+            const int grp = lane / 10, k = lane - grp * 10;
+            const int yy = ty2 * 32 + (grp == 0 ? 0 : (grp == 1 ? -1 : 32));
+            if (lane == 30) prefetch_l1(p.meta + (long long)par * p.meta_stride + env2);
+            else if (lane < 30 && yy >= 0 && yy < H && (grp == 0 ? k < 2 + R : k < R))
+                prefetch_l1(b2 + ((uint32_t)(grp == 0 ? k : BP_RING + k) * PL + (uint32_t)yy));
+        }
 
         // control lines no fire touches are attenuated like all others if the env gets past the early
         // return (fire.py:271-278, :651-652): a whole-env fact -> k_eval
