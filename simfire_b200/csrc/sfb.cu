@@ -203,7 +203,8 @@ struct sfb_sim {
     int pdl;          // bitboard handles: programmatic dependent launch of the step kernels (SFB_PDL=0 turns it off)
     int front_bits;   // bitboard front end (sfb_bits.cuh): k_tile_list + k_tiles instead of k_row_list + k_rows
     int tiles_blocks; // grid of k_tiles
-    void (*tiles_fn)(DevParams, int);  // k_tiles<cell type, max_fire_duration>
+    void (*tiles_fn)(DevParams, int);  // k_tiles<cell type, max_fire_duration, no statistics>
+    void (*tiles_fn_stats)(DevParams, int);
     int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
     int lpar;         // which watch-list buffer the NEXT step reads
     int front_blocks; // persistent grid of k_front
@@ -715,22 +716,24 @@ extern "C" void sfb_destroy(sfb_sim* s) {
     delete s;
 }
 
-// k_tiles is compiled once per number of source planes (max_fire_duration 1 .. BITS_MAX_DUR) and cell type
+// k_tiles is compiled once per number of source planes (max_fire_duration 1 .. BITS_MAX_DUR), cell type and
+// with / without the statistics counters (kernel-timing passes only)
 typedef void (*tiles_fn_t)(DevParams, int);
-template <typename CellT>
+template <typename CellT, bool STATS>
 static tiles_fn_t tiles_kernel_of(int max_dur) {
     switch (max_dur) {
-        case 1: return k_tiles<CellT, 1>;
-        case 2: return k_tiles<CellT, 2>;
-        case 3: return k_tiles<CellT, 3>;
-        case 4: return k_tiles<CellT, 4>;
-        case 5: return k_tiles<CellT, 5>;
-        case 6: return k_tiles<CellT, 6>;
-        default: return k_tiles<CellT, 7>;
+        case 1: return k_tiles<CellT, 1, STATS>;
+        case 2: return k_tiles<CellT, 2, STATS>;
+        case 3: return k_tiles<CellT, 3, STATS>;
+        case 4: return k_tiles<CellT, 4, STATS>;
+        case 5: return k_tiles<CellT, 5, STATS>;
+        case 6: return k_tiles<CellT, 6, STATS>;
+        default: return k_tiles<CellT, 7, STATS>;
     }
 }
-static tiles_fn_t tiles_kernel(int cell_bytes, int max_dur) {
-    return cell_bytes == 1 ? tiles_kernel_of<uint8_t>(max_dur) : tiles_kernel_of<uint16_t>(max_dur);
+static tiles_fn_t tiles_kernel(int cell_bytes, int max_dur, bool stats = false) {
+    if (stats) return cell_bytes == 1 ? tiles_kernel_of<uint8_t, true>(max_dur) : tiles_kernel_of<uint16_t, true>(max_dur);
+    return cell_bytes == 1 ? tiles_kernel_of<uint8_t, false>(max_dur) : tiles_kernel_of<uint16_t, false>(max_dur);
 }
 
 static int create_impl(const sfb_params* prm, sfb_sim* s) {
@@ -984,6 +987,7 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiles_kernel(s->cell_bytes, prm->max_fire_duration), TILES_WARPS * 32, 0));
         if (per_sm < 1) return fail(SFB_ERR_CUDA, "sfb_create: k_tiles does not fit on an SM");
         s->tiles_fn = tiles_kernel(s->cell_bytes, prm->max_fire_duration);
+        s->tiles_fn_stats = tiles_kernel(s->cell_bytes, prm->max_fire_duration, true);
         s->tiles_blocks = per_sm * s->n_sm;
     }
     CU(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
@@ -1456,7 +1460,7 @@ static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
             s->launches_all++;
         }
         const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)gr.d.E * gr.d.tiles_y * gr.d.tiles_x + TILES_WARPS - 1) / TILES_WARPS, s->tiles_blocks));
-        SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, s->tiles_fn, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, gr.d.tile_stats ? s->tiles_fn_stats : s->tiles_fn, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
         s->launches_all++;
         s->launches_step++;
         return;

@@ -174,15 +174,6 @@ __global__ void k_bits_rebuild(const DevParams p, const int par, const int32_t* 
     }
 }
 
-// L1 prefetch (a hint: no register, nobody waits for it)
-__device__ __forceinline__ void prefetch_l1(const void* ptr) {
-#if !defined(SFB_EMU) && !defined(SFB_TILES_NO_PREFETCH)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-#else
-    (void)ptr;
-#endif
-}
-
 #ifndef SFB_TILES_WARPS
 #define SFB_TILES_WARPS 4
 #endif
@@ -193,7 +184,7 @@ constexpr int TILES_WARPS = SFB_TILES_WARPS;
 constexpr int AQ_CAP = 32 * TILES_WARPS;
 
 // NSRC = max_fire_duration = the number of sprite planes a step reads as sources (the ring has NSRC + 1)
-template <typename CellT, int NSRC>
+template <typename CellT, int NSRC, bool STATS>
 __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tiles(const DevParams p, const int par) {
     using C = Cell<CellT>;
     grid_dep_wait();
@@ -292,31 +283,16 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             }
         }
     };
-    // tiles are dealt to the warps round-robin.  -DSFB_TILES_DYNAMIC: the first tile of a warp is its own number,
-    // further tiles are handed out by a counter, one ahead of the tile in hand (lane 0 holds the ticket; it is
-    // only looked at when the tile in hand is done), so that a warp that drew cheap tiles takes more of them
-#ifdef SFB_TILES_DYNAMIC  // measured on the target batch: no gain over the static deal (126 vs 136 T cell-updates/s)
-    const bool dynamic = n > n_warps;
-#else
-    const bool dynamic = false;
-#endif
-    unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp;
-    while (ti < n) {
-        unsigned long long ticket = ti + n_warps;
-        if (dynamic && lane == 0) ticket = n_warps + atomicAdd(p.rows_next + par, 1ULL);
+    // tiles are dealt to the warps round-robin (a dynamic hand-out through a counter, and an L1 prefetch of the
+    // warp's next tile, were measured and bought nothing: DESIGN.md section 4)
+    for (unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp; ti < n; ti += n_warps) {
         const unsigned long long task = tasks[ti];
-        // the warp's next tile (round-robin deal): its plane lines are prefetched while this tile's candidates are evaluated
-        const unsigned long long task2 = (!dynamic && ti + n_warps < n) ? tasks[ti + n_warps] : ~0ull;
-        ti = ~0ull;  // (set from the ticket at the end of the iteration)
         const int ty = (int)(task & 0xFFFFu), tx = (int)((task >> 16) & 0xFFFFu), env = (int)(task >> 32);
         EnvMeta* const mp = p.meta + (long long)par * p.meta_stride + env;
         const EnvMeta m = *mp;
         const long long tile_id = (long long)env * p.tile_stride + (long long)(ty * TX + tx);
         if (lane == 0) flags_cur[tile_id] = 0;  // off this step's list
-        if (!m.running) {  // an env that has quit only comes back through a reset, which lists its tiles
-            ti = __shfl_sync(0xffffffffu, ticket, 0);
-            continue;
-        }
+        if (!m.running) continue;  // an env that has quit only comes back through a reset, which lists its tiles
         const int t = m.t;
         const bool spread = !m.time_quit;
         const int y0 = ty * 32, y = y0 + lane;
@@ -364,8 +340,10 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         if (nvalid) nlisted = *reinterpret_cast<volatile uint8_t*>(flags_nxt + ntile);
         resolve();  // the previous tile's appends
         nb[lane] = 0;
-        st_tiles += lane == 0;
-        st_pruned += __popc(ew);
+        if (STATS) {
+            st_tiles += lane == 0;
+            st_pruned += __popc(ew);
+        }
 
         // ---- sprites that reached max_fire_duration: BURNED, out of the ring (fire.py:116-161)
         if (__any_sync(0xffffffffu, ew != 0)) {
@@ -420,29 +398,16 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             if (p.diagonal) take(cu << 1, 1);
         }
         uint32_t cand = spread ? (ign & ~und) : 0u;
-        st_cand += __popc(cand);
+        if (STATS) st_cand += __popc(cand);
         if (__any_sync(0xffffffffu, live != 0) && lane == 0) mp->any_live = 1;  // fire.py:637
         const bool any_cand = __any_sync(0xffffffffu, cand != 0);
         if (any_cand && lane == 0) mp->any_cand = 1;  // fire.py:651
-
-        // ---- the next tile of this warp: one prefetch per 128-byte line of its window.  Lane k < 10 takes the 32
-        // rows of plane k, lanes 10.. / 20.. the row above / below them in sprite plane k - 10 / k - 20, lane 30
-        // the env's clock.
-        if (task2 != ~0ull) {
-            const int ty2 = (int)(task2 & 0xFFFFu), tx2 = (int)((task2 >> 16) & 0xFFFFu), env2 = (int)(task2 >> 32);
-            const uint32_t* const b2 = p.bits + (long long)env2 * p.bits_env + (long long)tx2 * H;
-            const int grp = lane / 10, k = lane - grp * 10;
-            const int yy = ty2 * 32 + (grp == 0 ? 0 : (grp == 1 ? -1 : 32));
-            if (lane == 30) prefetch_l1(p.meta + (long long)par * p.meta_stride + env2);
-            else if (lane < 30 && yy >= 0 && yy < H && (grp == 0 ? k < 2 + R : k < R))
-                prefetch_l1(b2 + ((uint32_t)(grp == 0 ? k : BP_RING + k) * PL + (uint32_t)yy));
-        }
 
         // control lines no fire touches are attenuated like all others if the env gets past the early
         // return (fire.py:271-278, :651-652): a whole-env fact -> k_eval
         if (p.attenuate && spread) {
             uint32_t mm = line & ~cand;
-            st_def += __popc(mm);
+            if (STATS) st_def += __popc(mm);
             while (__any_sync(0xffffffffu, mm != 0)) {
                 const bool have = mm != 0;
                 const int b = have ? __ffs(mm) - 1 : 0;
@@ -514,7 +479,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         uint32_t mine = 0, all = 0, top = 0, bot = 0;
         if (ignited_any) {
             mine = nb[lane];
-            st_ign += __popc(mine);
+            if (STATS) st_ign += __popc(mine);
             if (mine) {
                 atomicOr(w_e, mine);
                 if ((mine & 2u) && tx > 0) atomicOr(w_e - H, 1u << 31);
@@ -542,7 +507,6 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             if (pend_want) pend_old = atomicOr(reinterpret_cast<uint32_t*>(flags_nxt) + (ntile >> 2), pend_bit);
             pend_task = make_tile_task(env, ty2, tx2);
         }
-        ti = __shfl_sync(0xffffffffu, ticket, 0);
     }
     resolve();
     dflush();
@@ -554,7 +518,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < n_app; i += blockDim.x)
         if ((long long)aq_base + i < p.rows_cap) tasks_nxt[aq_base + i] = aq[i];
-    if (p.tile_stats) {  // one atomic per warp and counter that has something
+    if (STATS && p.tile_stats) {  // one atomic per warp and counter that has something
         const unsigned int v[5] = {st_tiles * (32u * TW), st_cand, st_ign, st_pruned, st_def};
         const int slot[5] = {0, 1, 2, 3, 6};
 #pragma unroll

@@ -531,3 +531,23 @@ def test_reset_rebuilds_the_engine_when_the_config_changed():
     assert np.array_equal(ref.fire_map, short)
     ref.close()
     sim.close()
+
+
+def test_api_suite_on_the_bitboard_step():
+    """The drop-in surface above (managers, FireSimulation replays of reference-recorded call sequences,
+    save_data, spread graph, ConstantSpread) once more with every engine forced onto the bitboard step
+    (SFB_FRONT=bits; the grids of these tests are small, so they get the dense sweep by default)."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("SFB_FRONT"):
+        pytest.skip("already running under SFB_FRONT")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SFB_FRONT="bits")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gpu_api.py",
+           "tests/test_spread_graph.py", "-k", "not api_suite_on_the_bitboard_step" +
+           (" and not device_view" if os.environ.get("SFB_EMULATED") else "")]  # fmt: skip
+    res = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert res.returncode == 0, "\n".join((res.stdout + res.stderr).splitlines()[-25:])
+    assert " passed" in res.stdout

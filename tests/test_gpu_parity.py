@@ -73,8 +73,9 @@ def test_rate_of_spread_golden_pairs():
     err = np.abs(R - want)
     tol = RTOL * np.abs(want) + 3e-6 * np.maximum(R_flat, np.abs(want))
     assert np.all(err <= tol), f"max excess {np.max(err - tol)} at {np.argmax(err - tol)}"
-    # and without the cancellation allowance almost everywhere
-    assert np.mean(err <= RTOL * np.abs(want)) > 0.999
+    # and within the north star's 1e-5 relative without the cancellation allowance for all but the two pairs
+    # where 1 + phi_w + phi_s cancels: the count is pinned, not just bounded
+    assert int(np.sum(err > RTOL * np.abs(want))) <= 2, int(np.sum(err > RTOL * np.abs(want)))
 
 
 def test_rate_of_spread_known_answer():
