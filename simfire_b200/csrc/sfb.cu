@@ -1476,8 +1476,11 @@ static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
         s->launches_all++;
     }
     const bool dep = s->pdl && gr.d.bits && !gr.d.keep_ros;
-    if (s->cell_bytes == 1) SFB_LAUNCH_DEP(dep, k_eval<uint8_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
-    else SFB_LAUNCH_DEP(dep, k_eval<uint16_t>, s->n_sm * 8, 256, 0, st, gr.d, par);
+    // (bitboard handles leave k_eval only the control-line cells no fire touches and the per-env clocks; a smaller
+    // grid for them was measured -- 1, 2, 4 or 8 blocks per SM: the same 4 us, it is launch and drain latency)
+    const int eval_blocks = s->n_sm * 8;
+    if (s->cell_bytes == 1) SFB_LAUNCH_DEP(dep, k_eval<uint8_t>, eval_blocks, 256, 0, st, gr.d, par);
+    else SFB_LAUNCH_DEP(dep, k_eval<uint16_t>, eval_blocks, 256, 0, st, gr.d, par);
     s->launches_all++;
     s->launches_step++;
     if (gr.d.keep_ros && gr.d.bits) {

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     __shared__ unsigned long long dq_all[TILES_WARPS][WQ_CAP];  // staging of items for k_eval (deferred line cells, replaced sprites)
     __shared__ uint32_t nb_all[TILES_WARPS][32];                // cells of the tile that ignited, per row
     __shared__ unsigned long long lq_all[TILES_WARPS][WQ_CAP];  // staging of change-log entries (SFB_TRACK_CHANGES)
+    __shared__ unsigned long long pq_all[TILES_WARPS][32];      // per lane: the tile it may have listed (resolve)
     __shared__ unsigned long long aq[AQ_CAP];                   // the block's appends to the next step's tile list
     __shared__ unsigned int aq_n, aq_base;
     if (threadIdx.x == 0) aq_n = 0;
@@ -263,12 +264,14 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
 
     // appends to the next step's list: lane k < 9 may have set the "listed" byte of one neighbour tile with an
     // atomic whose answer (was it me who set it?) is only consumed here, a tile later
-    bool pend_want = false;
-    uint32_t pend_old = 0, pend_bit = 0;
-    unsigned long long pend_task = 0;
+    // (all that stays in registers across the tile is the atomic's answer: ~0 = nothing pending / listed already;
+    // the task and the byte's position in its word wait in shared memory)
+    uint32_t pend_old = ~0u;
+    unsigned long long* const pq = pq_all[warp];
     auto resolve = [&]() {
-        const bool won = pend_want && (pend_old & pend_bit) == 0;
-        pend_want = false;
+        const unsigned long long pend_task = pq[lane] & ~(3ull << 60);
+        const bool won = ((pend_old >> (8 * (int)((pq[lane] >> 60) & 3))) & 1u) == 0;
+        pend_old = ~0u;
         const uint32_t wm = __ballot_sync(0xffffffffu, won);
         if (!wm) return;
         unsigned int slot = 0;
@@ -322,22 +325,22 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
                 if (slot == 0) { slot = R - 1; off += wrap; } else { --slot; off -= PL; }
             }
         }
-        uint32_t* const w_ign = base + (uint32_t)y;              // this lane's words of the IGN / LINE / expiring planes
-        uint32_t* const w_line = base + (PL + (uint32_t)y);
-        uint32_t* const w_e = base + ((uint32_t)(BP_RING + e) * PL + (uint32_t)y);
+        // this lane's words of the IGN / LINE / expiring planes are base[o_ign], base[o_line], base[o_e]
+        const uint32_t o_ign = (uint32_t)y, o_line = PL + (uint32_t)y, o_e = (uint32_t)(BP_RING + e) * PL + (uint32_t)y;
         uint32_t ign = 0, line = 0, ew = 0;
         if (valid) {
-            ign = *w_ign;
-            line = *w_line;
-            ew = *w_e & OWN;
+            ign = base[o_ign];
+            line = base[o_line];
+            ew = base[o_e] & OWN;
         }
         // lane k < 9 speaks for the tile at (ty + k / 3 - 1, tx + k % 3 - 1) when the next step's list is written:
         // its "already listed" byte is fetched with the planes (a stale 0 only costs the atomic)
-        const int ndy = lane / 3 - 1, ndx = lane % 3 - 1;
-        const bool nvalid = lane < 9 && ty + ndy >= 0 && ty + ndy < p.tiles_y && tx + ndx >= 0 && tx + ndx < TX;
-        const long long ntile = tile_id + (long long)(ndy * TX + ndx);
-        uint8_t nlisted = 1;
-        if (nvalid) nlisted = *reinterpret_cast<volatile uint8_t*>(flags_nxt + ntile);
+        uint8_t nlisted = 1;  // (also for the lanes that speak for no tile)
+        {
+            const int ndy = lane / 3 - 1, ndx = lane % 3 - 1;
+            const bool nvalid = lane < 9 && ty + ndy >= 0 && ty + ndy < p.tiles_y && tx + ndx >= 0 && tx + ndx < TX;
+            if (nvalid) nlisted = *reinterpret_cast<volatile uint8_t*>(flags_nxt + (tile_id + (long long)(ndy * TX + ndx)));
+        }
         resolve();  // the previous tile's appends
         nb[lane] = 0;
         if (STATS) {
@@ -348,12 +351,12 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         // ---- sprites that reached max_fire_duration: BURNED, out of the ring (fire.py:116-161)
         if (__any_sync(0xffffffffu, ew != 0)) {
             if (ew) {
-                atomicAnd(w_e, ~ew);
-                if ((ew & 2u) && tx > 0) atomicAnd(w_e - H, ~(1u << 31));
-                if ((ew & (1u << TW)) && tx + 1 < TX) atomicAnd(w_e + H, ~1u);
+                atomicAnd(base + o_e, ~ew);
+                if ((ew & 2u) && tx > 0) atomicAnd(base + o_e - H, ~(1u << 31));
+                if ((ew & (1u << TW)) && tx + 1 < TX) atomicAnd(base + o_e + H, ~1u);
                 // a control line drawn over a burning cell (mitigation.py:77) burns out with its sprite
-                if (ew & ign) *w_ign = (ign &= ~ew);
-                if (ew & line) *w_line = (line &= ~ew);
+                if (ew & ign) base[o_ign] = (ign &= ~ew);
+                if (ew & line) base[o_line] = (line &= ~ew);
                 const long long ri = row0_idx + (long long)lane * p.pitch;
                 for (uint32_t mm = ew; mm; mm &= mm - 1) state[ri + (__ffs(mm) - 1)] = (CellT)ST_BURNED;
             }
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             if (lane == 0) cu = hu;
             if (lane == 31) cd = hd;
             live |= ca & OWN;
-            window |= ca | h[a];
+            window |= ca | h[a];  // (lanes 0 / 1 carry the rows outside the tile)
             if (!__any_sync(0xffffffffu, und != 0)) continue;
             auto take = [&](uint32_t src, int dir) {
                 const uint32_t w = src & und;
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             take(cu, 2);
             if (p.diagonal) take(cu << 1, 1);
         }
+        const bool has_window = __any_sync(0xffffffffu, window != 0);  // a sprite bit anywhere in the 34 x 32 window
         uint32_t cand = spread ? (ign & ~und) : 0u;
         if (STATS) st_cand += __popc(cand);
         if (__any_sync(0xffffffffu, live != 0) && lane == 0) mp->any_live = 1;  // fire.py:637
@@ -481,11 +485,11 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
             mine = nb[lane];
             if (STATS) st_ign += __popc(mine);
             if (mine) {
-                atomicOr(w_e, mine);
-                if ((mine & 2u) && tx > 0) atomicOr(w_e - H, 1u << 31);
-                if ((mine & (1u << TW)) && tx + 1 < TX) atomicOr(w_e + H, 1u);
-                *w_ign = ign & ~mine;
-                if (line & mine) *w_line = (line &= ~mine);
+                atomicOr(base + o_e, mine);
+                if ((mine & 2u) && tx > 0) atomicOr(base + o_e - H, 1u << 31);
+                if ((mine & (1u << TW)) && tx + 1 < TX) atomicOr(base + o_e + H, 1u);
+                base[o_ign] = ign & ~mine;
+                if (line & mine) base[o_line] = (line &= ~mine);
             }
             all = __reduce_or_sync(0xffffffffu, mine);
             top = __shfl_sync(0xffffffffu, mine, 0);
@@ -493,19 +497,19 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
         }
         // ---- the next step's list: the tile itself if it still has something to look at, and the neighbours
         // whose window holds a cell that ignited
-        const bool stay = __any_sync(0xffffffffu, (window | mine | (p.attenuate ? line : 0u)) != 0);
+        const bool stay = has_window || __any_sync(0xffffffffu, (mine | (p.attenuate ? line : 0u)) != 0);
         {
+            const int ndy = lane / 3 - 1, ndx = lane % 3 - 1;
             const uint32_t rowbits = ndy < 0 ? top : (ndy > 0 ? bot : all);          // what ignited next to that row of tiles
             const uint32_t colmask = ndx < 0 ? 2u : (ndx > 0 ? (1u << TW) : OWN);    // ... and next to that column
-            bool want = nvalid && (rowbits & colmask) != 0;
+            bool want = (rowbits & colmask) != 0;
             if (lane == 4) want = stay;
-            const int ty2 = ty + ndy, tx2 = tx + ndx;
             // the atomic is issued now and looked at while the next tile's loads are in flight (resolve)
-            pend_want = want && !nlisted;
-            pend_bit = 1u << (8 * (int)(ntile & 3));
-            pend_old = pend_bit;
-            if (pend_want) pend_old = atomicOr(reinterpret_cast<uint32_t*>(flags_nxt) + (ntile >> 2), pend_bit);
-            pend_task = make_tile_task(env, ty2, tx2);
+            if (want && !nlisted) {  // (nlisted is 1 for tiles outside the grid and for lanes >= 9)
+                const long long ntile = (long long)env * p.tile_stride + (long long)((ty + ndy) * TX + tx + ndx);
+                pend_old = atomicOr(reinterpret_cast<uint32_t*>(flags_nxt) + (ntile >> 2), 1u << (8 * (int)(ntile & 3)));
+                pq[lane] = make_tile_task(env, ty + ndy, tx + ndx) | ((unsigned long long)(ntile & 3) << 60);
+            }
         }
     }
     resolve();
