@@ -206,8 +206,12 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     unsigned long long* const lq = lq_all[warp];
     int dcount = 0, lcount = 0;  // warp-uniform
     unsigned int st_tiles = 0, st_cand = 0, st_ign = 0, st_pruned = 0, st_def = 0;  // statistics (kernel-timing passes only)
-    const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
     const unsigned long long* const tasks = p.rows + (long long)par * p.rows_cap;
+    // the warp's first task is fetched together with the length of the list, not after it (stale or not, the
+    // slot exists; it is only used if the list is that long)
+    const unsigned long long ti0 = (unsigned long long)blockIdx.x * TILES_WARPS + (threadIdx.x >> 5);
+    unsigned long long task = tasks[min(ti0, (unsigned long long)p.rows_cap - 1)];
+    const unsigned long long n = min(p.rows_count[par], (unsigned long long)p.rows_cap);
     unsigned long long* const tasks_nxt = p.rows + (long long)(par ^ 1) * p.rows_cap;
     uint8_t* const flags_cur = p.tile_act + (long long)par * p.tile_buf;
     uint8_t* const flags_nxt = p.tile_act + (long long)(par ^ 1) * p.tile_buf;
@@ -288,8 +292,7 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     };
     // tiles are dealt to the warps round-robin (a dynamic hand-out through a counter, and an L1 prefetch of the
     // warp's next tile, were measured and bought nothing: DESIGN.md section 4)
-    for (unsigned long long ti = (unsigned long long)blockIdx.x * TILES_WARPS + warp; ti < n; ti += n_warps) {
-        const unsigned long long task = tasks[ti];
+    for (unsigned long long ti = ti0; ti < n; ti += n_warps, task = tasks[min(ti, (unsigned long long)p.rows_cap - 1)]) {
         const int ty = (int)(task & 0xFFFFu), tx = (int)((task >> 16) & 0xFFFFu), env = (int)(task >> 32);
         EnvMeta* const mp = p.meta + (long long)par * p.meta_stride + env;
         const EnvMeta m = *mp;
