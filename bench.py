@@ -371,6 +371,8 @@ def gpu_arm_slab(args):
         torch.cuda.synchronize()
         ctx.barrier()
     launches = eng.launch_counts()[1] - l0
+    # diagnostic (--diag-back-to-back): the same K steps once more right away, the GPU still busy, no barrier before
+    ms_b2b = ctx.max(eng.step_timed(args.steps)) if args.diag_back_to_back else None
     ms_max = ctx.max(ms)
     value = H * W * E * args.steps / (ms_max * 1e-3)
     # e2e: one mitigation point in, this rank's rows of the fire_map mirrored on the host, per step
@@ -692,9 +694,11 @@ def gpu_arm(args):
     eng.reset(starts)
     eng.step(args.burn_in)  # untimed: let the fronts develop so the timed steps see real fires
 
+    host_barrier = os.environ.get("SFB_BENCH_BARRIER", "host") == "host"
+
     def barrier():
         torch.cuda.synchronize()
-        ctx.barrier()
+        ctx.barrier(host=host_barrier)  # NCCL still carries the reductions of the timings (ctx.max / ctx.sum)
         torch.cuda.synchronize()
 
     # device-resident phases (value, roofline): nothing leaves the GPU, so the change log that
@@ -708,6 +712,8 @@ def gpu_arm(args):
         ms = eng.step_timed(args.steps)
         barrier()
     launches = eng.launch_counts()[1] - l0
+    # diagnostic (--diag-back-to-back): the same K steps once more right away, the GPU still busy, no barrier before
+    ms_b2b = ctx.max(eng.step_timed(args.steps)) if args.diag_back_to_back else None
     ms_max = ctx.max(ms)
     ms_min = -ctx.max(-ms)  # the fastest rank: ranks light different fires, so their steps are not equally long
     cells_rank = H * W * E
@@ -844,6 +850,12 @@ def gpu_arm(args):
         "timing_notes": {"front": unit_mode, "timed_updates": [args.burn_in + args.warmup + 1, args.burn_in + args.warmup + args.steps],
                          "footprint_per_step_MB": roof["bytes_per_launch"] / 1e6,
                          "ms_per_step_slowest_rank": ms_max / args.steps, "ms_per_step_fastest_rank": ms_min / args.steps,
+                         **({"ms_per_step_next_K_steps_without_a_barrier_before": ms_b2b / args.steps} if ms_b2b else {}),
+                         "barrier": ("host-side (gloo) barrier + torch.cuda.synchronize() on both sides of the timed region; an NCCL "
+                                     "barrier kernel in front of it costs every rank ~45 us before its first step kernel starts "
+                                     "(profiles/r02/r03g_*: rank 0, same fires, 0.0274 ms/step after a host barrier, 0.0297 after an "
+                                     "NCCL one), which a 0.56 ms region reads as an 8 % scaling loss; NCCL carries the reductions")
+                                    if host_barrier else "NCCL barrier + torch.cuda.synchronize() on both sides of the timed region",
                          "ranks": "every rank lights its own random ignition cells (bench_starts(rank)), so the ranks' fire "
                                   "fronts -- and with them the front-proportional step -- differ by a few per cent; `value` "
                                   "uses the slowest rank"},
@@ -935,6 +947,8 @@ def main():
     ap.add_argument("--as-batch", action="store_true",
                     help="cfg5: step the 8192^2 grid as an ordinary one-env engine on one GPU (row units) instead of slab mode")
     ap.add_argument("--slab-sync", default="p2p", choices=["p2p", "nccl"], help="cfg5: how the slabs agree per step")
+    ap.add_argument("--diag-back-to-back", action="store_true",
+                    help="also time the next K steps right after the timed region (no barrier / idle GPU before them)")
     ap.add_argument("--no-track", action="store_true", help="e2e downloads every fire_map in full each step")
     ap.add_argument("--mirror", default="pinned", choices=["pinned", "thp"],
                     help="memory of the host fire_map mirror in the e2e phase")

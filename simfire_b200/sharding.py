@@ -51,11 +51,19 @@ class RankContext:
         dev = "cuda" if (self.backend or "nccl") == "nccl" else "cpu"
         return torch.tensor([float(value)], dtype=torch.float64, device=dev)
 
-    def barrier(self) -> None:
+    def barrier(self, host: bool = False) -> None:
+        """All ranks meet.  host=True: on a gloo group, i.e. without putting a collective kernel on the GPUs
+        (an NCCL barrier right before a timed region costs every rank some tens of microseconds before its next
+        kernel starts, which a sub-millisecond region would report as a scaling loss)."""
         if self.world > 1:
             import torch.distributed as dist
 
-            dist.barrier()
+            if host and (self.backend or "nccl") == "nccl":
+                if getattr(self, "_host_group", None) is None:
+                    self._host_group = dist.new_group(backend="gloo")
+                dist.barrier(group=self._host_group)
+            else:
+                dist.barrier()
 
     def max(self, value: float) -> float:
         """Max over ranks (timings are reported as the slowest rank's)."""
