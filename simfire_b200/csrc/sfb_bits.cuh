@@ -379,13 +379,16 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
 #pragma unroll
         for (int a = 0; a < NSRC; ++a) {
             const uint32_t ca = c[a];
+            // no sprite of this duration anywhere in the window (tiles listed for a control line only, the far
+            // side of a front), or nothing left to decide: next duration
+            if (!__any_sync(0xffffffffu, (ca | h[a]) != 0)) continue;  // (lanes 0 / 1 carry the rows outside the tile)
+            live |= ca & OWN;
+            window |= ca | h[a];
+            if (!__any_sync(0xffffffffu, und != 0)) continue;
             uint32_t cu = __shfl_up_sync(0xffffffffu, ca, 1), cd = __shfl_down_sync(0xffffffffu, ca, 1);
             const uint32_t hu = __shfl_sync(0xffffffffu, h[a], 0), hd = __shfl_sync(0xffffffffu, h[a], 1);
             if (lane == 0) cu = hu;
             if (lane == 31) cd = hd;
-            live |= ca & OWN;
-            window |= ca | h[a];  // (lanes 0 / 1 carry the rows outside the tile)
-            if (!__any_sync(0xffffffffu, und != 0)) continue;
             auto take = [&](uint32_t src, int dir) {
                 const uint32_t w = src & und;
                 und &= ~w;
