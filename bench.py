@@ -533,7 +533,7 @@ def roofline_lists(eng, args, cells_rank, peak_gbs, peak_src, workload):
     }
 
 
-def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, step_ms):
+def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, step_ms, launches_per_step):
     """The bitboard front end: k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
     per launch of k_tiles, from the kernel's own counters over the per-launch-timed
     pass: per tile its 8-byte task, the 32 words of the ignitable and control-line planes and of the
@@ -559,9 +559,12 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, ste
                    fs["pruned"] * (1.0 + 4.0))
     eval_bytes = q_entries * (8.0 + 16.0) + 64.0 * eng.E
     bracketed_ms = {"k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
+    if launches_per_step < 1.5:  # no control lines anywhere: k_tiles closes the step itself, there is no k_eval launch
+        bracketed_ms = {"k_tiles": tiles_s * 1e3}
+        eval_s = 0.0
     share = {k: v / (tiles_s + eval_s) / 1e3 for k, v in bracketed_ms.items()}
     kernel_ms = {k: step_ms * share[k] for k in bracketed_ms}
-    kernel_bytes = {"k_tiles": tiles_bytes, "k_eval": eval_bytes}
+    kernel_bytes = {"k_tiles": tiles_bytes + (eval_bytes if "k_eval" not in bracketed_ms else 0.0), "k_eval": eval_bytes}
     dominant = max(kernel_ms, key=kernel_ms.get)
     dom_s = kernel_ms[dominant] * 1e-3
     achieved = kernel_bytes[dominant] / dom_s / 1e9
@@ -592,6 +595,7 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, ste
                           "cells_swept_per_step": 0.0, "cells_per_step": cells_rank},
         "kernel_ms_per_launch": kernel_ms, "kernel_ms_per_launch_event_bracketed": bracketed_ms,
         "launch_duration_method": "device-timed step of the timed region x the kernel's share of the event-bracketed pass",
+        "launches_per_step": launches_per_step,
         "bytes_per_launch": kernel_bytes[dominant],
         "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank, "ms_per_launch": dom_s * 1e3,
         "share_of_step": share[dominant],
@@ -724,7 +728,7 @@ def gpu_arm(args):
     peak_gbs, peak_src = load_peak()
     unit_mode = eng.unit_mode()
     if unit_mode == "bits":
-        roof = roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, args.workload, wl.max_fire_duration + 1, ms_max / args.steps)
+        roof = roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, args.workload, wl.max_fire_duration + 1, ms_max / args.steps, launches / args.steps)
     else:
         roof = (roofline_lists if unit_mode == "lists" else roofline_sweeps)(eng, args, cells_rank, peak_gbs, peak_src, args.workload)
 

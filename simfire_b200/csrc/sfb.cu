@@ -201,10 +201,13 @@ struct sfb_sim {
     int unit_skip;    // the sweep only reads flagged units (DevParams::unit_act)
     int unit_rows;    // ... and a unit is a single row of a strip: no sweep at all (k_row_list)
     int pdl;          // bitboard handles: programmatic dependent launch of the step kernels (SFB_PDL=0 turns it off)
-    int front_bits;   // bitboard front end (sfb_bits.cuh): k_tile_list + k_tiles instead of k_row_list + k_rows
+    int front_bits;   // bitboard step (sfb_bits.cuh): k_tiles + k_eval instead of k_row_list + k_rows + k_eval
     int tiles_blocks; // grid of k_tiles
-    void (*tiles_fn)(DevParams, int);  // k_tiles<cell type, max_fire_duration, no statistics>
-    void (*tiles_fn_stats)(DevParams, int);
+    void (*tiles_fn)(DevParams, int, int);  // k_tiles<cell type, max_fire_duration, no statistics>
+    void (*tiles_fn_stats)(DevParams, int, int);
+    int ext_writes;   // bitboard handles: a status was written from outside (mitigation, map upload) since all envs
+                      // were last reset: control lines may exist, so a step needs k_eval; without, k_tiles closes the step
+    int fuse_eval;    // SFB_FUSE_EVAL=1 turns the one-kernel step on (measured slower than two kernels: off by default)
     int front_lists;  // list-driven step (sfb_lists.cuh): k_front (+ k_tail with attenuation); no env groups
     int lpar;         // which watch-list buffer the NEXT step reads
     int front_blocks; // persistent grid of k_front
@@ -256,7 +259,7 @@ struct sfb_sim {
 static int use(sfb_sim* s) {
     CU(cudaSetDevice(s->prm.device));
     s->head_valid = 0;  // any call may append to the change logs; only a grouped step re-validates
-    s->d.bits_par = s->parity;  // bitboard handles: setup kernels raise the tile flags the next step reads
+    s->d.bits_par = s->parity;  // bitboard handles: setup kernels put tiles on the list the next step reads
     return 0;
 }
 
@@ -718,7 +721,7 @@ extern "C" void sfb_destroy(sfb_sim* s) {
 
 // k_tiles is compiled once per number of source planes (max_fire_duration 1 .. BITS_MAX_DUR), cell type and
 // with / without the statistics counters (kernel-timing passes only)
-typedef void (*tiles_fn_t)(DevParams, int);
+typedef void (*tiles_fn_t)(DevParams, int, int);
 template <typename CellT, bool STATS>
 static tiles_fn_t tiles_kernel_of(int max_dur) {
     switch (max_dur) {
@@ -980,8 +983,15 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         CU(cudaMemsetAsync(d.bits, 0, (size_t)d.E * d.bits_env * 4, s->stream));
         CU(cudaMemsetAsync(d.tile_act, 0, (size_t)2 * d.tile_buf, s->stream));
         if (d.keep_ros && (rc = dmalloc(s, &d.ros_w, (size_t)total * 8))) return rc;
-        if ((rc = dmalloc(s, &s->list_ctr, 16 * sizeof(unsigned long long)))) return rc;  // statistics of timed passes
+        if ((rc = dmalloc(s, &s->list_ctr, 16 * sizeof(unsigned long long)))) return rc;  // ticket, statistics of timed passes
         CU(cudaMemsetAsync(s->list_ctr, 0, 16 * sizeof(unsigned long long), s->stream));
+        d.ticket = reinterpret_cast<unsigned int*>(s->list_ctr + 4);
+        // one kernel per step (k_tiles' last block closes the step) while no control line can exist: built, parity-
+        // tested and measured SLOWER than k_tiles + k_eval on the target batch (138-141 vs 150-151 T cell-updates/s:
+        // every thread's __threadfence before the ticket and one block advancing 1024 clocks cost more than the 4 us
+        // of a second launch) -> opt-in
+        s->fuse_eval = 0;
+        if (const char* e = getenv("SFB_FUSE_EVAL")) s->fuse_eval = atoi(e) != 0;
         // (the row-task list allocated above is sized for the tile tasks)
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiles_kernel(s->cell_bytes, prm->max_fire_duration), TILES_WARPS * 32, 0));
@@ -1306,11 +1316,17 @@ extern "C" int sfb_reset(sfb_sim* s, const int32_t* envs, int32_t n, const int32
     if (s->front_lists) CU(cudaMemsetAsync(s->env_mark, 0, (size_t)d.E, s->stream));
     if (s->front_bits) {  // planes of the fresh maps (one ignitable plane, one sprite of duration 0)
         DISPATCH(s, k_bits_rebuild, cap_grid(s, (long long)n * d.bits_plane, 256), 256, d, s->parity, (const int32_t*)d_envs, 0, n);
+        if (!envs && n == d.E && s->ext_writes) {  // every env is fresh: no control line is left anywhere
+            s->ext_writes = 0;
+            s->view_epoch++;
+        }
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));  // host buffers are borrowed for the call only
     return 0;
 }
+
+static void note_ext_write(sfb_sim* s);
 
 extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     if (!s || (n > 0 && !pts)) return fail(SFB_ERR_INVALID, "sfb_apply_points: null argument");
@@ -1328,6 +1344,7 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     int rc;
     if ((rc = use(s))) return rc;
     if (s->steps_since_sync > 0) s->setup_after_step = 1;  // its log entries follow a step's
+    note_ext_write(s);
     const size_t bytes = (size_t)n * 4 * sizeof(int32_t);
     if ((rc = ensure_small(s, bytes))) return rc;
     const bool staged = bytes <= PTS_STAGE_BYTES;  // per-step mitigation points: no device round trip
@@ -1356,6 +1373,14 @@ extern "C" int sfb_apply_points(sfb_sim* s, const int32_t* pts, int64_t n) {
     return 0;
 }
 
+// a status written from outside: control lines (and burning cells made ignitable again) may exist from now on
+static void note_ext_write(sfb_sim* s) {
+    if (s->front_bits && !s->ext_writes) {
+        s->ext_writes = 1;
+        s->view_epoch++;  // captured step graphs launch the other set of kernels
+    }
+}
+
 static int check_env_range(sfb_sim* s, const char* who, int env0, int n) {
     if (env0 < 0 || n < 1 || env0 + n > s->d.E)
         return fail(SFB_ERR_INVALID, "%s: envs [%d, %d) of %d", who, env0, env0 + n, s->d.E);
@@ -1365,6 +1390,7 @@ static int check_env_range(sfb_sim* s, const char* who, int env0, int n) {
 static int upload_maps(sfb_sim* s, int env0, int n, const int8_t* maps) {
     const DevParams& d = s->d;
     s->full_resync = 1;  // the change log does not describe wholesale map replacement
+    note_ext_write(s);
     const size_t bytes = (size_t)n * d.H * d.W;
     int rc;
     if ((rc = ensure_stage(s, bytes))) return rc;
@@ -1430,6 +1456,12 @@ static int derive_if_dirty(sfb_sim* s) {
     return 0;
 }
 
+// bitboard handles with SFB_FUSE_EVAL=1: one kernel per step while no status has been written from outside (no
+// control lines: nothing for k_eval to decide) and the rate-of-spread plane is not kept
+static bool step_is_fused(const sfb_sim* s, const EnvGroup& gr) {
+    return gr.d.bits && s->fuse_eval && !s->ext_writes && !gr.d.keep_ros;
+}
+
 static void launch_sweep(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     if (gr.d.bits) return;  // this step's tile list was written by the step before (and by the setup kernels)
     if (gr.d.unit_rows) {  // the flagged rows are this step's row tasks: nothing is swept
@@ -1460,7 +1492,8 @@ static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
             s->launches_all++;
         }
         const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)gr.d.E * gr.d.tiles_y * gr.d.tiles_x + TILES_WARPS - 1) / TILES_WARPS, s->tiles_blocks));
-        SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, gr.d.tile_stats ? s->tiles_fn_stats : s->tiles_fn, blocks, TILES_WARPS * 32, 0, st, gr.d, par);
+        SFB_LAUNCH_DEP(s->pdl && !gr.d.keep_ros, gr.d.tile_stats ? s->tiles_fn_stats : s->tiles_fn, blocks, TILES_WARPS * 32, 0, st, gr.d, par,
+                       step_is_fused(s, gr) ? 1 : 0);
         s->launches_all++;
         s->launches_step++;
         return;
@@ -1471,6 +1504,7 @@ static void launch_rows(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
     s->launches_step++;
 }
 static void launch_eval(sfb_sim* s, EnvGroup& gr, cudaStream_t st, int par) {
+    if (step_is_fused(s, gr)) return;  // k_tiles closed the step itself
     if (gr.d.keep_ros && !gr.d.bits) {
         SFB_LAUNCH(k_clear_ros, cap_grid(s, (long long)gr.d.E * gr.d.plane, 256), 256, 0, st, gr.d, par);
         s->launches_all++;

@@ -184,8 +184,13 @@ constexpr int TILES_WARPS = SFB_TILES_WARPS;
 constexpr int AQ_CAP = 32 * TILES_WARPS;
 
 // NSRC = max_fire_duration = the number of sprite planes a step reads as sources (the ring has NSRC + 1)
+// fuse != 0 (SFB_FUSE_EVAL=1, off by default: measured slower than the second launch it saves): there is no
+// k_eval behind this launch -- the block that finishes last (atomic ticket) closes the step: whatever is in the
+// work queue, the per-env clocks, the counters.  The host only asks for it while nothing has written a status from
+// outside since the envs were reset (no control lines, so the queue stays empty and closing the step is E clock
+// updates); with control lines the queue can be long and k_eval's whole grid takes it.
 template <typename CellT, int NSRC, bool STATS>
-__global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tiles(const DevParams p, const int par) {
+__global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tiles(const DevParams p, const int par, const int fuse) {
     using C = Cell<CellT>;
     grid_dep_wait();
     grid_dep_launch();
@@ -521,13 +526,46 @@ __global__ void __launch_bounds__(TILES_WARPS * 32, SFB_TILES_MIN_BLOCKS) k_tile
     resolve();
     dflush();
     lflush();
-    // the block's appends, one atomic for all of them
+    // the block's appends, one atomic for all of them -- and, in a step without k_eval, the block's ticket (the
+    // list entries themselves are only read by the next kernel: they need not be out before it)
+    __shared__ unsigned int is_last;
+    if (fuse) __threadfence();  // this block's env flags and queue items before its ticket
     __syncthreads();
     const unsigned int n_app = min(aq_n, (unsigned int)AQ_CAP);
-    if (threadIdx.x == 0 && n_app) aq_base = (unsigned int)atomicAdd(p.rows_count + (par ^ 1), (unsigned long long)n_app);
+    if (threadIdx.x == 0) {
+        if (n_app) aq_base = (unsigned int)atomicAdd(p.rows_count + (par ^ 1), (unsigned long long)n_app);
+        is_last = (fuse && atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < n_app; i += blockDim.x)
         if ((long long)aq_base + i < p.rows_cap) tasks_nxt[aq_base + i] = aq[i];
+    if (fuse) {
+        if (is_last) {
+            __threadfence();
+            const long long nq = (long long)min(*reinterpret_cast<volatile unsigned long long*>(p.qcount + par), (unsigned long long)p.qcap);
+            if (*reinterpret_cast<volatile int32_t*>(p.overflow + par)) {  // (a queue too short for the control lines: the dense form)
+                const long long total = (long long)p.E * p.plane;
+                for (long long i = threadIdx.x; i < total; i += blockDim.x) dense_cell<CellT>(p, par, i);
+                if (p.track && threadIdx.x == 0) *p.chg_overflow = 1;
+            } else {
+                for (long long i = threadIdx.x; i < nq; i += blockDim.x) {
+                    const unsigned long long it = *reinterpret_cast<volatile unsigned long long*>(p.queue + i);
+                    const long long idx = (long long)(it & 0xFFFFFFFFFFFFull);
+                    const int dir = (int)((it >> 48) & 0xF), st = (int)((it >> 52) & 7), env = (int)(idx / p.plane);
+                    EnvMeta m = p.meta[(long long)par * p.meta_stride + env];
+                    m.any_cand = reinterpret_cast<volatile EnvMeta*>(p.meta + (long long)par * p.meta_stride + env)->any_cand;
+                    if (dir == DIR_UNRING) bits_unring<CellT>(p, m, env, idx, st);
+                    else process_item<CellT>(p, m, env, idx, dir, st);  // DIR_NONE: never ignites, nothing to log
+                }
+            }
+            __syncthreads();
+            for (long long env = threadIdx.x; env < p.E; env += blockDim.x) advance_env(p, par, env);
+            if (threadIdx.x == 0) {
+                close_step(p, par);
+                *p.ticket = 0;
+            }
+        }
+    }
     if (STATS && p.tile_stats) {  // one atomic per warp and counter that has something
         const unsigned int v[5] = {st_tiles * (32u * TW), st_cand, st_ign, st_pruned, st_def};
         const int slot[5] = {0, 1, 2, 3, 6};

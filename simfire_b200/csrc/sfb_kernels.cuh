@@ -1092,6 +1092,52 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const DevParams p, con
 // k_eval: persistent grid-stride over the work queue (or, if the queue overflowed, over
 // every cell).  Threads 0..E-1 also write the next step's EnvMeta.
 // ---------------------------------------------------------------------------------------
+// the per-env clock of the next step from this step's flags (fire.py:633-652, :717).  The flags were raised by
+// other blocks (of an earlier kernel, or -- bitboard handles without a k_eval -- of this one): volatile reads
+__device__ __forceinline__ void advance_env(const DevParams& p, const int par, const long long env) {
+    // two 16-byte loads that bypass L1 (this SM may hold the line from before the flags were raised) and, unlike
+    // volatile loads, may be in flight together with those of the caller's other envs
+    const int4* c = reinterpret_cast<const int4*>(p.meta + (long long)par * p.meta_stride + env);
+#ifdef SFB_EMU
+    const int4 lo = c[0], hi = c[1];
+#else
+    const int4 lo = __ldcg(c), hi = __ldcg(c + 1);
+#endif
+    EnvMeta nxt;
+    nxt.t = lo.x;
+    nxt.running = lo.y;
+    const int time_quit = lo.z, any_live = lo.w, any_cand = hi.x;
+    nxt.pad = 0;
+    {  // bytes 24..31 of the record
+        const unsigned long long bits = (unsigned long long)(uint32_t)hi.z | ((unsigned long long)(uint32_t)hi.w << 32);
+        memcpy(&nxt.elapsed, &bits, sizeof(double));
+    }
+    if (nxt.running) {
+        if (!any_live) nxt.running = 0;            // fire.py:637
+        else if (time_quit) nxt.running = 0;       // fire.py:641-643
+        else if (any_cand) nxt.elapsed = nxt.elapsed + p.dt;  // fire.py:717 (skipped by :651)
+        nxt.t = nxt.t + 1;
+    }
+    nxt.any_live = 0;
+    nxt.any_cand = 0;
+    nxt.time_quit = p.has_max_time && (p.dt > p.max_time || nxt.elapsed > p.max_time);
+    p.meta[(long long)(par ^ 1) * p.meta_stride + env] = nxt;
+}
+// one thread, after the step's last work: counters of the next step
+__device__ __forceinline__ void close_step(const DevParams& p, const int par) {
+    p.qcount[par ^ 1] = 0;
+    p.overflow[par ^ 1] = 0;
+    p.unit_next[par ^ 1] = 0;
+    p.rows_next[par ^ 1] = 0;
+    if (p.bits) {  // the tile list of the next step is being written: the one just consumed is emptied
+        p.units_count[par] = p.rows_count[par];  // (kept for sfb_get_unit_stats)
+        p.rows_count[par] = 0;
+    } else {
+        p.rows_count[par ^ 1] = 0;
+        if (p.units_count) p.units_count[par ^ 1] = 0;
+    }
+}
+
 // bitboard handles (sfb_bits.cuh)
 template <typename CellT>
 __device__ __forceinline__ void bits_unring(const DevParams& p, const EnvMeta& m, int env, long long idx, int slot);
@@ -1180,33 +1226,8 @@ __global__ void __launch_bounds__(256) k_eval(const DevParams p, const int par) 
     }
 
     // per-env clock for the next step (reads only what k_sweep finalised)
-    for (long long env = gid; env < p.E; env += gstride) {
-        const EnvMeta cur = p.meta[(long long)par * p.meta_stride + env];
-        EnvMeta nxt = cur;
-        if (cur.running) {
-            if (!cur.any_live) nxt.running = 0;            // fire.py:637
-            else if (cur.time_quit) nxt.running = 0;       // fire.py:641-643
-            else if (cur.any_cand) nxt.elapsed = cur.elapsed + p.dt;  // fire.py:717 (skipped by :651)
-            nxt.t = cur.t + 1;
-        }
-        nxt.any_live = 0;
-        nxt.any_cand = 0;
-        nxt.time_quit = p.has_max_time && (p.dt > p.max_time || nxt.elapsed > p.max_time);
-        p.meta[(long long)(par ^ 1) * p.meta_stride + env] = nxt;
-    }
-    if (gid == 0) {
-        p.qcount[par ^ 1] = 0;
-        p.overflow[par ^ 1] = 0;
-        p.unit_next[par ^ 1] = 0;
-        p.rows_next[par ^ 1] = 0;
-        if (p.bits) {  // the tile list of the next step is being written: the one just consumed is emptied
-            p.units_count[par] = p.rows_count[par];  // (kept for sfb_get_unit_stats)
-            p.rows_count[par] = 0;
-        } else {
-            p.rows_count[par ^ 1] = 0;
-            if (p.units_count) p.units_count[par ^ 1] = 0;
-        }
-    }
+    for (long long env = gid; env < p.E; env += gstride) advance_env(p, par, env);
+    if (gid == 0) close_step(p, par);
 }
 
 // ---------------------------------------------------------------------------------------

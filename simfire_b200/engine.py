@@ -365,7 +365,8 @@ class FireEngine:
         _lib.check(self._lib.sfb_set_kernel_timing(self._h, 1 if enabled else 0))
 
     def kernel_ms(self):
-        """(k_sweep ms, k_rows ms, k_eval ms, steps) accumulated since timing was enabled."""
+        """(k_sweep ms, k_rows ms, k_eval ms, steps) accumulated since timing was enabled; a bitboard handle has no
+        first kernel (0) and reports k_tiles as the second."""
         a, r, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         _lib.check(self._lib.sfb_get_kernel_ms(self._h, C.byref(a), C.byref(r), C.byref(b), C.byref(n)))
         return float(a.value), float(r.value), float(b.value), int(n.value)
@@ -382,8 +383,9 @@ class FireEngine:
         return int(a.value), int(b.value)
 
     def unit_mode(self) -> str:
-        """'dense' (every unit swept), 'chunks' (flagged chunks swept), 'rows' (flagged rows are the row tasks)
-        or 'lists' (the list-driven step: no units, one watch list)."""
+        """'bits' (the bitboard step: k_tiles + k_eval on self-maintained tile lists; the default for big handles with
+        max_fire_duration <= 7), 'dense' (every unit swept), 'chunks' (flagged chunks swept), 'rows' (flagged rows are
+        the row tasks) or 'lists' (the list-driven step: no units, one watch list)."""
         a, b, m = C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(self._lib.sfb_get_unit_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
         return ("dense", "chunks", "rows", "lists", "bits")[int(m.value)]
@@ -394,7 +396,9 @@ class FireEngine:
         return int(a.value), int(b.value), bool(o.value)
 
     def front_stats(self) -> dict:
-        """List handles: what k_front did since the previous call (the counters are reset)."""
+        """List handles: what k_front did since the previous call (the counters are reset).  Bitboard handles: what
+        k_tiles did while kernel timing was on (examined = cells of the tiles looked at, entries_read = tiles,
+        neighbourhoods_read = control-line cells left to k_eval)."""
         a = (C.c_int64 * 7)()
         _lib.check(self._lib.sfb_get_front_stats(self._h, a, 7))
         names = ("examined", "candidates", "ignited", "pruned", "joined", "entries_read", "neighbourhoods_read")

@@ -131,7 +131,7 @@ def test_golden_trajectory_variants(name, variant, monkeypatch):
           "lists": dict(front_lists=True), "lists_wide": dict(front_lists=True, wide_cells=True),
           "lists_overflow": dict(front_lists=True, queue_capacity=3),
           "lists_no_rate_table": dict(front_lists=True),
-          # the bitboard front end (k_tile_list + k_tiles): bit planes per sprite duration, 32 x 32 tiles
+          # the bitboard step (k_tiles + k_eval): bit planes per sprite duration, tiles of 32 rows x 30 columns
           "bits": dict(front_bits=True), "bits_wide": dict(front_bits=True, wide_cells=True),
           "bits_overflow": dict(front_bits=True, queue_capacity=3),
           "bits_groups3": dict(front_bits=True, env_groups=3)}[variant]  # fmt: skip
@@ -296,6 +296,65 @@ def test_unit_skipping_changes_nothing(front_end, attenuate):
             eng.close()
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_bitboard_one_kernel_step_and_its_transitions(fuse, monkeypatch):
+    """The bitboard step is k_tiles + k_eval.  With SFB_FUSE_EVAL=1 (opt-in: measured slower) a handle steps with
+    ONE kernel (k_tiles closes the step itself) while no status has been written from outside since all envs
+    were reset, and with two once control lines may exist.  Same results as the dense sweep either way and through
+    the transitions: single and multi-step launches (graph replay), a control line (attenuation of untouched line
+    cells included), a partial reset, a reset of every env, envs that burn out."""
+    from simfire_b200 import FireEngine
+    from simfire_b200.workloads import synthetic_operational
+
+    monkeypatch.setenv("SFB_FUSE_EVAL", str(fuse))
+    one = 1 if fuse else 2  # kernels per step while no control line can exist
+
+    H, W, E = 70, 130, 4
+    wl = synthetic_operational(H, W, seed=4, patch=8)
+    kw = dict(wl.engine_kwargs(), attenuate_line_ros=True, max_fire_duration=3, pixel_scale=40.0)
+    starts = wl.burnable_starts(E, seed=2, margin=2)
+    with FireEngine(H, W, E, shared_static=True, front_bits=True, **kw) as a, \
+            FireEngine(H, W, E, shared_static=True, unit_skip=False, **kw) as b:
+        assert a.unit_mode() == "bits" and b.unit_mode() == "dense"
+        for eng in (a, b):
+            eng.set_static(wl.planes)
+            eng.reset(starts)
+
+        def same(what):
+            assert np.array_equal(a.fire_map(), b.fire_map()), what
+            for e in range(E):
+                assert np.array_equal(a.plane("burn", e), b.plane("burn", e)), (what, e)
+            for x, y in zip(a.status(), b.status()):
+                assert np.array_equal(x, y), what
+
+        def steps(n, chunks):
+            l0 = a.launch_counts()[1]
+            for k in chunks:
+                a.step(k)
+                b.step(k)
+            assert sum(chunks) == n
+            return (a.launch_counts()[1] - l0) / n
+
+        assert steps(12, [1] * 5 + [7]) == one  # also through the two-step graph
+        same("one-kernel steps")
+        line = [(e, x, 20, 3 + e % 3) for e in range(E) for x in range(10, 120)]
+        for eng in (a, b):
+            eng.apply_points(line)
+        assert steps(9, [1, 8]) == 2
+        same("with a control line")
+        for eng in (a, b):
+            eng.reset(np.array([[5, 5], [100, 60]]), envs=[1, 3])
+        assert steps(6, [6]) == 2  # envs 0 and 2 still carry their lines
+        same("after a partial reset")
+        for eng in (a, b):
+            eng.reset(starts)
+        assert steps(40, [3, 1, 36]) == one
+        same("after a reset of every env")
+        assert steps(200, [200]) == one  # until everything has burnt out
+        same("burnt out")
+        assert not a.status()[0].any()
+
+
 @pytest.mark.parametrize("unit_skip", [False, True])
 def test_grouped_multi_step_launch_equals_single_steps(unit_skip):
     """Multi-group handles can replay pairs of steps as one CUDA graph forked over the group streams
@@ -367,7 +426,7 @@ def test_random_scenarios_against_oracle(seed, front):
     comes within 2e-3 (relative to its increment) of the ignition threshold is not a fair test of
     bit-exactness ("Ties at the ignition threshold") and is skipped.  Odd
     seeds force row-unit skipping, seeds divisible by 4 chunk units, the rest sweep densely; "bits" runs
-    every seed on the bitboard front end (k_tile_list + k_tiles)."""
+    every seed on the bitboard step (k_tiles + k_eval)."""
     from oracle.dense_numpy import DenseFire, DenseParams
     from simfire_b200 import FireEngine
 
