@@ -46,6 +46,24 @@ def test_params_struct_layout_matches_header(lib_path):
     assert _lib.SfbParams.queue_capacity.offset == 80
 
 
+def test_flag_constants_match_the_header():
+    """The ctypes binding's copies of `enum sfb_flags` / plane ids are the header's values."""
+    from simfire_b200 import _lib
+
+    src = open(os.path.join(ROOT, "include", "simfire_b200.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"\b(SFB_[A-Z_0-9]+)\s*=\s*(\d+)\s*[,/}]", src))
+    want = {"SFB_DIAGONAL_SPREAD": _lib.DIAGONAL_SPREAD, "SFB_ATTENUATE_LINE_ROS": _lib.ATTENUATE_LINE_ROS,
+            "SFB_SHARED_STATIC": _lib.SHARED_STATIC, "SFB_KEEP_ROS": _lib.KEEP_ROS, "SFB_HAS_MAX_TIME": _lib.HAS_MAX_TIME,
+            "SFB_WIDE_CELLS": _lib.WIDE_CELLS, "SFB_SWEEP_LDG": _lib.SWEEP_LDG, "SFB_TRACK_CHANGES": _lib.TRACK_CHANGES,
+            "SFB_KEEP_IGNITION": _lib.KEEP_IGNITION, "SFB_UNIT_SKIP_OFF": _lib.UNIT_SKIP_OFF, "SFB_UNIT_SKIP_ON": _lib.UNIT_SKIP_ON,
+            "SFB_UNIT_CHUNKS": _lib.UNIT_CHUNKS, "SFB_STEP_GRAPH": _lib.STEP_GRAPH, "SFB_FRONT_LISTS": _lib.FRONT_LISTS,
+            "SFB_FRONT_BITS": _lib.FRONT_BITS}  # fmt: skip
+    for name, value in want.items():
+        assert enum.get(name) == value, (name, enum.get(name), value)
+    flags = [v for k, v in enum.items() if k in want]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags)  # distinct single bits
+
+
 def test_no_cpu_fallback(lib_path):
     """Without a CUDA device the product path must fail loudly."""
     import torch
