@@ -536,9 +536,9 @@ def roofline_lists(eng, args, cells_rank, peak_gbs, peak_src, workload):
 def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, step_ms, launches_per_step):
     """The bitboard front end: k_tiles + k_eval, k_tiles being the step.  Algorithmic bytes
     per launch of k_tiles, from the kernel's own counters over the per-launch-timed
-    pass: per tile its 8-byte task, the 32 words of the ignitable and control-line planes and of the
-    expiring sprite plane, 34 words of each of the ring - 1 source planes (32 rows + the row above and
-    below); per candidate the 8-byte rate of its (cell, direction) pair and the float64 burn value read
+    pass: per tile (16 rows x 30 columns) its 8-byte task, the 16 words of the ignitable and control-line
+    planes and of the expiring sprite plane, 18 words of each of the ring - 1 source planes (16 rows + the row
+    above and below); per candidate the 8-byte rate of its (cell, direction) pair and the float64 burn value read
     and written; one state byte per ignition / burn-out; per tile up to three 128-byte plane rows written
     back and one flag byte.
     Launch duration: a step is these two kernels back to back on one stream, so the time of the dominant one
@@ -555,8 +555,9 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, ste
     units_listed, units_total = eng.unit_stats()
     q_entries, q_cap, q_ovf = eng.queue_stats()
     tiles_s, eval_s = tiles_ms / n_t * 1e-3, eval_ms / n_t * 1e-3
-    tiles_bytes = (tiles * (8.0 + 3 * 128.0 + (ring - 1) * 34 * 4.0 + 2.0 + 8.0) + cand * 24.0 + fs["ignited"] * (1.0 + 12.0) +
-                   fs["pruned"] * (1.0 + 4.0))
+    tile_rows = round(fs["examined"] / max(1.0, tiles) / 30.0)  # 16 (two tiles per warp at a time) or 32
+    tiles_bytes = (tiles * (8.0 + 3 * 4.0 * tile_rows + (ring - 1) * (tile_rows + 2) * 4.0 + 2.0 + 8.0) + cand * 24.0 +
+                   fs["ignited"] * (1.0 + 12.0) + fs["pruned"] * (1.0 + 4.0))
     eval_bytes = q_entries * (8.0 + 16.0) + 64.0 * eng.E
     bracketed_ms = {"k_tiles": tiles_s * 1e3, "k_eval": eval_s * 1e3}
     if launches_per_step < 1.5:  # no control lines anywhere: k_tiles closes the step itself, there is no k_eval launch
@@ -600,7 +601,7 @@ def roofline_bits(eng, args, cells_rank, peak_gbs, peak_src, workload, ring, ste
         "bytes_per_cell_update": kernel_bytes[dominant] / cells_rank, "ms_per_launch": dom_s * 1e3,
         "share_of_step": share[dominant],
         "per_launch": {k: round(v, 1) for k, v in fs.items()},
-        "row_tasks_per_step": tiles, "work_items_per_step": cand, "items_left_to_k_eval": q_entries,
+        "tile_rows": tile_rows, "row_tasks_per_step": tiles, "work_items_per_step": cand, "items_left_to_k_eval": q_entries,
         "queue_overflowed": q_ovf, "front": "bits",
     }  # fmt: skip
 

@@ -226,30 +226,32 @@ static inline unsigned int __reduce_add_sync(uint32_t, unsigned int v) {
     for (int b = 0; b < 32; ++b) r += (unsigned int)__builtin_popcount(emu::ballot((v >> b) & 1u, 50 + b)) << b;  // bit-sliced sum
     return r;
 }
+// (width: a power of two; lanes exchange within their aligned group of `width` lanes, as the hardware does)
 template <class T>
-static inline T __shfl_sync(uint32_t, T v, int src) {
+static inline T __shfl_sync(uint32_t, T v, int src, int width = 32) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    const int lane = emu::st().cur->lane, base = lane & ~(width - 1);
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof(T));
-    raw = emu::exchange(raw, src & 31, 5);
+    raw = emu::exchange(raw, base + (src & (width - 1)), 5);
     memcpy(&v, &raw, sizeof(T));
     return v;
 }
 template <class T>
-static inline T __shfl_down_sync(uint32_t, T v, unsigned delta) {
-    const int lane = emu::st().cur->lane;
+static inline T __shfl_down_sync(uint32_t, T v, unsigned delta, int width = 32) {
+    const int lane = emu::st().cur->lane, base = lane & ~(width - 1);
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof(T));
-    raw = emu::exchange(raw, lane + (int)delta < 32 ? lane + (int)delta : lane, 6);
+    raw = emu::exchange(raw, lane + (int)delta < base + width ? lane + (int)delta : lane, 6);
     memcpy(&v, &raw, sizeof(T));
     return v;
 }
 template <class T>
-static inline T __shfl_up_sync(uint32_t, T v, unsigned delta) {
-    const int lane = emu::st().cur->lane;
+static inline T __shfl_up_sync(uint32_t, T v, unsigned delta, int width = 32) {
+    const int lane = emu::st().cur->lane, base = lane & ~(width - 1);
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof(T));
-    raw = emu::exchange(raw, lane - (int)delta >= 0 ? lane - (int)delta : lane, 7);
+    raw = emu::exchange(raw, lane - (int)delta >= base ? lane - (int)delta : lane, 7);
     memcpy(&v, &raw, sizeof(T));
     return v;
 }
@@ -536,7 +538,11 @@ void warp_sync(int tag) {
     const unsigned g = w->gen;
     const int par = g & 1;
     if (w->arrived == 0) w->tag[par] = tag;
-    else if (w->tag[par] != tag) die("lanes of one warp met at different collectives (divergent collective)");
+    else if (w->tag[par] != tag) {
+        fprintf(stderr, "cuda_emu: block %u thread %u arrives at collective tag %d, its warp is parked at tag %d\n",
+                g_state.block_idx.x, g_state.cur->tid.x, tag, w->tag[par]);
+        die("lanes of one warp met at different collectives (divergent collective)");
+    }
     w->arrived++;
     release_if_complete(w);
     while (w->gen == g) yield();
