@@ -1086,8 +1086,8 @@ static int create_impl(const sfb_params* prm, sfb_sim* s) {
         gr.sweep_blocks = (int)std::min<long long>(need, (long long)per_sm * s->n_sm);
         const long long rows_need = (v.rows_cap + ROWS_WARPS - 1) / ROWS_WARPS;
         gr.rows_blocks = (int)std::max<long long>(1, std::min<long long>(rows_need, (long long)rows_per_sm * s->n_sm));
-        const long long unit_items = d.bits ? (long long)cnt * d.tile_stride / 4 : (d.unit_rows ? (long long)cnt * d.unit_stride / 4 : v.n_units);  // words / flags
-        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((unit_items + 255) / 256, (long long)((d.unit_rows || d.bits) ? 8 : 4) * s->n_sm));
+        const long long unit_items = d.unit_rows ? (long long)cnt * d.unit_stride / 4 : v.n_units;  // words / flags
+        gr.units_blocks = (int)std::max<long long>(1, std::min<long long>((unit_items + 255) / 256, (long long)(d.unit_rows ? 8 : 4) * s->n_sm));
         return 0;
     };
     if ((rc = make_view(s->all, 0, d.E, 0, d.qcap, false))) return rc;
