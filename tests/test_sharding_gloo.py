@@ -36,6 +36,7 @@ def _worker(rank, world, port, q):
     ctx = RankContext.from_env(backend="gloo")
     first, n = env_shard(1023, ctx.world, ctx.rank)
     ctx.barrier()
+    ctx.barrier(host=True)  # the bench's bracket around its timed region (on an NCCL context: a gloo side group)
     ms = ctx.max(10.0 + 5.0 * rank)  # rank 1 is slower
     total = ctx.sum(n)
     thr = aggregate_throughput(ctx, cells_this_rank=n * 100, steps=4, seconds_this_rank=0.5 * (rank + 1))
